@@ -1,0 +1,199 @@
+"""CPU: the oracle (oracle/dqrm_oracle.py) against the golden vectors that
+oracle/make_golden.py produced by executing the reference.  Codes, scales and
+row sets bit-exact; floating outputs within 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import dqrm_oracle as O
+from deep_quantized_recommendation_model_dqrm_b200 import synthetic
+
+EMB_CASES = ["emb_multihot_d16", "emb_multihot_d64_b8", "emb_onehot_zipf_d16", "emb_onehot_tiny_d16",
+             "emb_ragged_d16"]
+RTOL = 1e-5
+
+
+@pytest.mark.parametrize("name", EMB_CASES)
+def test_emb_forward_spec(name):
+    g = load_golden(name)
+    bits = int(g["bits"])
+    scale, codes, out = O.embbag_forward_spec(g["W"], g["idx"], g["off"], bits)
+    assert scale.tobytes() == g["scale"].astype(np.float32).tobytes()
+    assert np.array_equal(codes, g["codes"])
+    np.testing.assert_allclose(out, g["out"], rtol=RTOL, atol=0)
+    _, _, pooled = O.embbag_forward_spec(g["W"], g["idx"], g["off"], bits, full_precision=True)
+    np.testing.assert_allclose(pooled, g["pooled"], rtol=RTOL, atol=1e-9)
+    # torch-layer scale scan issues the reference's op sequence: same bits
+    assert O.table_scale_torch(torch.from_numpy(g["W"]), bits).numpy().tobytes() == scale.tobytes()
+
+
+@pytest.mark.parametrize("name", EMB_CASES)
+def test_emb_backward_and_coalesce_spec(name):
+    g = load_golden(name)
+    rows, vals = O.embbag_backward_spec(g["dout"], g["idx"], g["off"], g["scale"])
+    assert np.array_equal(rows, g["grad_rows"])
+    assert np.array_equal(vals, g["grad_vals"])          # (g*s)/s reproduced bit-for-bit
+    urows, sums = O.coalesce_spec(rows, vals)
+    assert np.array_equal(urows, g["co_rows"])
+    # duplicate-fold order is implementation-defined in torch (unstable sort): fp32-rounding agreement ...
+    np.testing.assert_allclose(sums, g["co_vals"], rtol=RTOL, atol=1e-5 * np.abs(vals).max())
+    # ... and bit-exact once the fold follows torch.sort's own permutation
+    perm = torch.from_numpy(rows).sort(0)[1].numpy()
+    urows2, sums2 = O.coalesce_spec(rows, vals, order=perm)
+    assert np.array_equal(urows2, g["co_rows"]) and np.array_equal(sums2, g["co_vals"])
+
+
+def test_coalesce_fold_order_heavy_duplicates():
+    rng = np.random.RandomState(5)
+    rows = rng.randint(0, 37, size=20000)
+    vals = rng.randn(20000, 16).astype(np.float32)
+    sp = torch.sparse_coo_tensor(torch.from_numpy(rows)[None], torch.from_numpy(vals), size=(37, 16)).coalesce()
+    perm = torch.from_numpy(rows).sort(0)[1].numpy()
+    urows, sums = O.coalesce_spec(rows, vals, order=perm)
+    assert np.array_equal(urows, sp.indices()[0].numpy())
+    assert np.array_equal(sums, sp.values().numpy())
+    _, sums_stable = O.coalesce_spec(rows, vals)
+    np.testing.assert_allclose(sums_stable, sums, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["linear_13_64", "linear_367_32", "linear_64_1"])
+def test_quant_linear(name):
+    g = load_golden(name)
+    bits = int(g["bits"])
+    W_int, b_int, s = O.linear_fakequant_spec(g["W"], g["b"], bits)
+    assert np.array_equal(s, g["scale"])
+    assert np.array_equal(W_int, g["W_int"])
+    assert np.array_equal(b_int, g["b_int"])
+    x = torch.tensor(g["x"], requires_grad=True)
+    W = torch.nn.Parameter(torch.tensor(g["W"]))
+    b = torch.nn.Parameter(torch.tensor(g["b"]))
+    y, _ = O.quant_linear_forward_torch(x, W, b, bits)
+    y.backward(torch.tensor(g["dy"]))
+    for got, want in ((y, "y"), (x.grad, "dx"), (W.grad, "dW"), (b.grad, "db")):
+        np.testing.assert_allclose(got.detach().numpy(), g[want], rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["interact_kaggle", "interact_tb", "interact_small"])
+def test_interact(name):
+    g = load_golden(name)
+    x = torch.tensor(g["x"], requires_grad=True)
+    ly = [torch.tensor(t, requires_grad=True) for t in g["ly"]]
+    R = O.interact_features_torch(x, ly)
+    np.testing.assert_allclose(R.detach().numpy(), g["R"], rtol=RTOL, atol=1e-6)
+    R.backward(torch.tensor(g["dR"]))
+    np.testing.assert_allclose(x.grad.numpy(), g["dx"], rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(np.stack([t.grad.numpy() for t in ly]), g["dly"], rtol=RTOL, atol=1e-5)
+
+
+def _shard(world, rank, multihot, step, rows):
+    Bg = 16 * world
+    sl = slice(rank * 16, (rank + 1) * 16)
+    if multihot:
+        X, lS_o, lS_i, T = synthetic.random_batch(rows, Bg, 4, seed=400 + step)
+        li, lo = [], []
+        for i, o in zip(lS_i, lS_o):
+            ends = torch.cat([o[1:], torch.tensor([i.shape[0]])])
+            a, b = int(o[sl][0]), int(ends[sl][-1])
+            li.append(i[a:b])
+            lo.append(o[sl] - a)
+        return X[sl], lo, li, T[sl]
+    X, lS_o, lS_i, T = synthetic.criteo_batch(rows, Bg, seed=400 + step, zipf=1.3)
+    lS_i = lS_i[:, sl]
+    return X[sl], lS_o[:, 0:lS_i.shape[1]], lS_i, T[sl]
+
+
+def build_oracle_models(world, cfg, seed=300):
+    models = []
+    for _ in range(world):
+        rng = np.random.RandomState(seed)
+        emb = [torch.from_numpy(synthetic.table_weights_numpy(n, cfg["dim"], rng)) for n in cfg["rows"]]
+        ln_top = synthetic.top_mlp_sizes(len(cfg["rows"]), cfg["dim"], cfg["ln_top_hidden"])
+        bot = synthetic.mlp_params(cfg["ln_bot"], rng)
+        top = synthetic.mlp_params(ln_top, rng)
+        models.append(O.OracleDLRM(cfg["rows"], cfg["dim"], bot, top, emb_weights=emb))
+    return models
+
+
+C_SMALL = dict(rows=[50, 3, 1000, 200], dim=16, ln_bot=[13, 32, 16], ln_top_hidden=[32, 1])
+
+
+@pytest.mark.parametrize("name", ["dp1_onehot", "dp2_onehot", "dp2_multihot", "dp4_onehot"])
+def test_dp_train_steps(name):
+    """Two iterations of the reference's custom-DP loop (N Gloo ranks) against
+    the oracle's in-process replicas: union rows, averaged codes and scales
+    bit-exact; losses and final weights within 1e-5."""
+    g = load_golden(name)
+    world, multihot = int(g["world"]), bool(g["multihot"])
+    models = build_oracle_models(world, C_SMALL)
+    for step in range(2):
+        batches = [_shard(world, r, multihot, step, C_SMALL["rows"]) for r in range(world)]
+        scales_before = None
+        losses = O.train_step_torch(models, batches, lr=0.1) if False else None
+        # run the step in two halves so the exchanged artefacts can be inspected
+        losses = []
+        for m, (X, lS_o, lS_i, T) in zip(models, batches):
+            Z = m(X, lS_o, lS_i)
+            E = torch.nn.functional.binary_cross_entropy(Z, T)
+            O.clear_gradients_torch(m)
+            E.backward()
+            losses.append(float(E.detach()))
+        O.grad_update_torch(models)
+        for r in range(world):
+            assert abs(losses[r] - float(g[f"rank{r}_loss{step}"])) <= 1e-5 * abs(losses[r]) + 1e-7
+        m0 = models[0]
+        for k, e in enumerate(m0.emb_l):
+            assert np.array_equal(e.grad_rows.numpy(), g[f"s{step}_emb{k}_rows"]), (step, k)
+            assert e.eb_scaling_factor.numpy().tobytes() == g[f"s{step}_emb{k}_eb_scale"].tobytes()
+            if world <= 2:   # scale mean is order-free for N<=2: bit-exact
+                assert np.array_equal(e.emb_scaling_factor.numpy(), g[f"s{step}_emb{k}_sbar"]), (step, k)
+                assert np.array_equal(e.grad_q.numpy(), g[f"s{step}_emb{k}_qbar"]), (step, k)
+            else:
+                np.testing.assert_allclose(e.emb_scaling_factor.numpy(), g[f"s{step}_emb{k}_sbar"], rtol=1e-6)
+        for m in models:
+            O.weight_update_torch(m, 0.1)
+    m0 = models[0]
+    for k, e in enumerate(m0.emb_l):
+        np.testing.assert_allclose(e.embedding_bag.weight.data.numpy(), g[f"final_emb{k}"], rtol=RTOL, atol=1e-7)
+    for grp, layers in (("bot", m0.bot_l), ("top", m0.top_l)):
+        for i, l in enumerate(layers):
+            np.testing.assert_allclose(l.weight.data.numpy(), g[f"final_{grp}{i}_W"], rtol=RTOL, atol=1e-7)
+            np.testing.assert_allclose(l.bias.data.numpy(), g[f"final_{grp}{i}_b"], rtol=RTOL, atol=1e-7)
+
+
+def test_spec_exchange_matches_torch_layer():
+    """numpy spec of the exchange == torch-layer restatement (2 ranks)."""
+    rng = np.random.RandomState(9)
+    per_rank = []
+    for r in range(2):
+        rows = rng.randint(0, 40, size=64)
+        vals = rng.randn(64, 16).astype(np.float32) * 0.01
+        per_rank.append(O.coalesce_spec(rows, vals))
+    ex = O.exchange_emb_grad_spec(per_rank, 8, 40)
+    W = rng.randn(40, 16).astype(np.float32)
+    W2 = W.copy()
+    O.weight_update_emb_spec(W2, ex["union_rows"], ex["qbar"], ex["s_bar"], 0.1)
+    # torch layer
+    s_loc = [O.table_scale_torch(torch.from_numpy(s), 8) for _, s in per_rank]
+    s_bar = ((s_loc[0] + s_loc[1]) * 0.5).view(-1)
+    assert s_bar.numpy()[0].tobytes() == ex["s_bar"].tobytes()
+    sp = None
+    for rws, s in per_rank:
+        q = O.quantize_torch(torch.from_numpy(s), 8, s_bar)
+        t = torch.sparse_coo_tensor(torch.from_numpy(rws)[None], q, size=(40, 16))
+        sp = t if sp is None else sp + t
+    sp = sp.coalesce()
+    assert np.array_equal(sp.indices()[0].numpy(), ex["union_rows"])
+    assert np.array_equal((sp.values() * 0.5).numpy(), ex["qbar"])
+    Wt = torch.from_numpy(W.copy())
+    upd = (sp * 0.5) * s_bar.item()
+    Wt.add_(-0.1 * upd)
+    assert np.array_equal(Wt.numpy(), W2)
+
+
+def test_get_my_slice():
+    for n, w in ((128, 8), (10, 3), (7, 7), (5, 8)):
+        got = []
+        for r in range(w):
+            got += list(range(n))[O.get_my_slice(n, w, r)]
+        assert got == list(range(n))
