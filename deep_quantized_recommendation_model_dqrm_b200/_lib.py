@@ -1,0 +1,100 @@
+"""ctypes binding of libdqrm_b200.so (the C ABI declared in include/dqrm_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing (or was
+not built for this tree) every entry point raises.  Build it with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C
+deep_quantized_recommendation_model_dqrm_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdqrm_b200.so")
+
+MAX_TABLES = 64
+BWD_CTA_MAX_LOOKUPS = 16384
+STATUS_INDEX_RANGE, STATUS_OFFSET_ORDER, STATUS_CAPACITY = 1, 2, 4
+
+_vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+_p = C.c_void_p          # every pointer (host arrays are passed as ctypes arrays, device ptrs as ints)
+
+# name -> (restype, argtypes); order and meaning follow include/dqrm_b200.h
+SIGNATURES = {
+    "dqrm_abi_version": (_i32, []),
+    "dqrm_last_error": (C.c_char_p, []),
+    "dqrm_scan_workspace_bytes": (_sz, [_i32]),
+    "dqrm_table_absmax_scale": (_i32, [_i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "dqrm_scale_from_absmax": (_i32, [_i32, _p, _i32, _p, _p, _p]),
+    "dqrm_embbag_fwd": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _p, _p, _i32, _p, _i64, _i64, _p, _p, _p]),
+    "dqrm_bwd_workspace_bytes": (_sz, [_i32, _i64, _i32]),
+    "dqrm_embbag_bwd": (_i32, [_i32, _p, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p, _i32, _p,
+                               _p, _p, _sz, _p]),
+    "dqrm_grad_absmax_scale": (_i32, [_i32, _i32, _p, _p, _i64, _i32, _p, _p]),
+    "dqrm_sgd_rows": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _f32, _f32, _p, _f32, _p]),
+    "dqrm_slot_bytes": (_sz, [_i32, _i64, _i32, _i32]),
+    "dqrm_slot_layout": (_i32, [_i32, _i64, _i32, _i32, C.POINTER(_sz), C.POINTER(_sz)]),
+    "dqrm_grad_pack": (_i32, [_i32, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _p, _p, _p]),
+    "dqrm_grad_topk": (_i32, [_i32, _i32, _p, _p, _p, _i64, _i64, _p]),
+    "dqrm_grad_merge_apply": (_i32, [_i32, _p, _p, _i32, _p, _i32, _i64, _i32, _p, _f32, _p, _p, _p, _p, _p]),
+    "dqrm_interact_fwd": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p]),
+    "dqrm_interact_bwd": (_i32, [_p, _p, _i64, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _i64, _i64, _p]),
+    "dqrm_linear_fakequant": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "dqrm_fake_quant": (_i32, [_p, _i64, _i64, _p, _i32, _i32, _p, _p, _p]),
+    "dqrm_dense_grad_scale": (_i32, [_p, _p, _i32, _i32, _p, _p]),
+    "dqrm_dense_grad_quant": (_i32, [_p, _p, _i32, _p, _f32, _i32, _p, _p, _p]),
+    "dqrm_dense_apply": (_i32, [_p, _p, _p, _i32, _p, _f32, _f32, _p]),
+}
+
+_lib = None
+
+
+class DqrmLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the in-tree library and bind every symbol; raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DqrmLibraryError(
+            f"{LIB_PATH} not found: the CUDA library has not been built. There is no CPU fallback; "
+            "run `make -C deep_quantized_recommendation_model_dqrm_b200/csrc` (needs nvcc, sm_100a).")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale
+        fn.restype, fn.argtypes = res, args
+    if lib.dqrm_abi_version() != 1:
+        raise DqrmLibraryError(f"{LIB_PATH}: ABI version {lib.dqrm_abi_version()} != 1 (stale build)")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().dqrm_last_error().decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise DqrmLibraryError(f"{what} failed with {rc} ({os.strerror(-rc) if rc < 0 else rc}): {last_error()}")
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, None -> NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def i64_array(values):
+    return (C.c_int64 * len(values))(*[int(v) for v in values])
+
+
+def ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

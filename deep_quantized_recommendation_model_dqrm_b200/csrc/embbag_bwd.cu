@@ -1,0 +1,390 @@
+// (a4 bwd, a5, a7 steps 1-2) sparse row gradient of the QAT EmbeddingBag, de-duplicated.
+// Reference: autograd of quantization_supp/quant_modules_not_quantize_grad.py:393 and
+//            SymmetricQuantFunction.backward (quantization_supp/quant_utils.py:348-363): dy = (g*s)/s;
+//            ATen sparse EmbeddingBag backward (dlrm_s_pytorch_comm_grad.py:1938): one value row per lookup;
+//            Tensor.coalesce + gradient scale (sgd_quantized_gradients_parallel_comm.py:859-861).
+//
+// One CTA per table.  The table's lookups become 64-bit keys (row << 32 | bag) in
+// shared memory; because a key carries its bag, equal rows are ordered by bag =
+// original lookup order, which makes the (unstable) bitonic network a stable
+// sort by row.  Head flags + a block scan give the ascending unique rows; a
+// dim/4-lane group then folds each row's duplicates left-to-right, reading
+// dy = (g*s)/s straight from dOut (the per-lookup [L,D] value matrix the
+// reference materialises never exists), and the CTA finishes with the table's
+// max|sum| -> 8-bit gradient scale.  Sort, unique, segmented sum and scale are
+// ONE launch for all tables (the reference: index_select, thrust sort,
+// coalesceValuesKernel, 4 reductions and a host sync per table).
+#include "common.cuh"
+
+namespace dqrm {
+
+constexpr unsigned long long kPadKey = ~0ull;
+constexpr int kBwdPrefetchRows = 8;   // float4 row loads in flight per lane group (divided by COLS)
+
+struct BwdArgs {
+  long long rows[DQRM_MAX_TABLES];
+  long long idx_begin[DQRM_MAX_TABLES + 1];
+};
+
+__device__ __forceinline__ float ste_dy(float g, float s, bool quant) {
+  return quant ? __fdiv_rn(__fmul_rn(g, s), s) : g;
+}
+
+template <int COLS>
+__global__ void __launch_bounds__(1024)
+embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
+                      const long long* __restrict__ indices, const long long* __restrict__ offsets, long long bags,
+                      const float* __restrict__ dout, long long dts, long long dbs,
+                      const float* __restrict__ fwd_scale, long long capacity,
+                      int* __restrict__ uniq_rows, int* __restrict__ uniq_count, float* __restrict__ grad_sums,
+                      int grad_bits, float* __restrict__ grad_scale_local, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_warp_tot[32];
+  __shared__ int s_nvalid, s_unique;
+  __shared__ unsigned s_max;
+
+  const int t = blockIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const long long L = a.idx_begin[t + 1] - a.idx_begin[t];
+  int n = 2;
+  while (n < L) n <<= 1;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  int* seg_start = reinterpret_cast<int*>(keys + n);
+  const long long* idx = indices + a.idx_begin[t];
+  const long long* off = offsets + (long long)t * bags;
+  const long long nrows = a.rows[t];
+  int bad = 0;
+
+  // 1. keys
+  for (int i = tid; i < n; i += nthr) keys[i] = kPadKey;
+  __syncthreads();
+  for (long long b = tid; b < bags; b += nthr) {
+    long long start = off[b];
+    long long end = (b + 1 < bags) ? off[b + 1] : L;
+    if (start < 0 || end > L || start > end) {
+      bad |= DQRM_STATUS_OFFSET_ORDER;
+      start = start < 0 ? 0 : (start > L ? L : start);
+      end = end > L ? L : (end < start ? start : end);
+    }
+    for (long long l = start; l < end; ++l) {
+      long long r = idx[l];
+      if (r < 0 || r >= nrows) { bad |= DQRM_STATUS_INDEX_RANGE; r = r < 0 ? 0 : nrows - 1; }
+      keys[l] = ((unsigned long long)r << 32) | (unsigned long long)(unsigned)b;
+    }
+  }
+  __syncthreads();
+
+  // 2. bitonic sort, ascending
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < (n >> 1); i += nthr) {
+        const int lo = 2 * i - (i & (j - 1));
+        const int hi = lo + j;
+        const unsigned long long x = keys[lo], y = keys[hi];
+        const bool up = (lo & k) == 0;
+        if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+
+  // 3. number of real keys (pads sort last)
+  if (tid == 0) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] == kPadKey) hi = mid; else lo = mid + 1; }
+    s_nvalid = lo;
+  }
+  __syncthreads();
+  const int nvalid = s_nvalid;
+
+  // 4. head flags -> exclusive scan -> seg_start[]
+  const int chunk = (nvalid + nthr - 1) / nthr;
+  const int c0 = min(tid * chunk, nvalid), c1 = min(c0 + chunk, nvalid);
+  int heads = 0;
+  for (int i = c0; i < c1; ++i)
+    heads += (i == 0) || ((unsigned)(keys[i] >> 32) != (unsigned)(keys[i - 1] >> 32));
+  int incl = heads;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((tid & 31) >= d) incl += v;
+  }
+  if ((tid & 31) == 31) s_warp_tot[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    const int nw = (nthr + 31) >> 5;
+    int v = tid < nw ? s_warp_tot[tid] : 0;
+    int w = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, w, d);
+      if (tid >= d) w += u;
+    }
+    s_warp_tot[tid] = w - v;                   // exclusive prefix of warp totals
+    if (tid == 31) s_unique = w;
+  }
+  __syncthreads();
+  int pos = s_warp_tot[tid >> 5] + incl - heads;
+  for (int i = c0; i < c1; ++i)
+    if ((i == 0) || ((unsigned)(keys[i] >> 32) != (unsigned)(keys[i - 1] >> 32))) seg_start[pos++] = i;
+  int U = s_unique;
+  if (tid == 0) {
+    seg_start[U] = nvalid;
+    if (U > capacity) bad |= DQRM_STATUS_CAPACITY;
+    uniq_count[t] = (int)(U > capacity ? capacity : U);
+  }
+  __syncthreads();
+  if (U > capacity) U = (int)capacity;
+
+  // 5. segmented left fold of dy over each unique row
+  const bool quant = fwd_scale != nullptr;
+  const float s = quant ? fwd_scale[t] : 1.0f;
+  const int lane = tid % group;
+  const float* dbase = dout + (long long)t * dts;
+  unsigned m = 0u;
+  for (int j = tid / group; j < U; j += nthr / group) {
+    const int p0 = seg_start[j], p1 = seg_start[j + 1];
+    constexpr int kBwdPrefetch = kBwdPrefetchRows / COLS;
+    float4 acc[COLS];
+    for (int p = p0; p < p1; p += kBwdPrefetch) {
+      float4 v[kBwdPrefetch][COLS];
+#pragma unroll
+      for (int u = 0; u < kBwdPrefetch; ++u) {
+        const bool live = p + u < p1;
+        const long long bag = live ? (long long)(unsigned)keys[p + u] : 0;
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+          const int col = lane + c * group;
+          v[u][c] = (live && col < dim4)
+                        ? __ldg(reinterpret_cast<const float4*>(dbase + bag * dbs) + col)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBwdPrefetch; ++u) {
+        if (p + u >= p1) break;
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+          const float4 d = make_float4(ste_dy(v[u][c].x, s, quant), ste_dy(v[u][c].y, s, quant),
+                                       ste_dy(v[u][c].z, s, quant), ste_dy(v[u][c].w, s, quant));
+          if (p + u == p0) {
+            acc[c] = d;
+          } else {
+            acc[c].x = __fadd_rn(acc[c].x, d.x); acc[c].y = __fadd_rn(acc[c].y, d.y);
+            acc[c].z = __fadd_rn(acc[c].z, d.z); acc[c].w = __fadd_rn(acc[c].w, d.w);
+          }
+        }
+      }
+    }
+    if (lane == 0) uniq_rows[(long long)t * capacity + j] = (int)(keys[p0] >> 32);
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int col = lane + c * group;
+      if (col >= dim4) continue;
+      reinterpret_cast<float4*>(grad_sums + ((long long)t * capacity + j) * dim4 * 4)[col] = acc[c];
+      m = max(m, abs_bits4(acc[c]));
+    }
+  }
+
+  // 6. per-table gradient scale
+  const unsigned bm = block_max_u32(m, &s_max);
+  if (tid == 0 && grad_scale_local) grad_scale_local[t] = scale_of(__uint_as_float(bm), grad_bits);
+  if (bad) atomicOr(status, bad);
+}
+
+__global__ void grad_absmax_scale_kernel(int dim, const float* __restrict__ grad_sums, const int* __restrict__ uniq_count,
+                                         long long capacity, int bits, float* __restrict__ scale_local) {
+  __shared__ unsigned s_max;
+  const int t = blockIdx.x;
+  const long long n = (long long)uniq_count[t] * dim;
+  const float* g = grad_sums + (long long)t * capacity * dim;
+  unsigned m = 0u;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) m = max(m, abs_bits(g[i]));
+  const unsigned bm = block_max_u32(m, &s_max);
+  if (threadIdx.x == 0) scale_local[t] = scale_of(__uint_as_float(bm), bits);
+}
+
+struct MomPtrs { float* p[DQRM_MAX_TABLES]; };
+
+// W[row] += (-lr) * (sum * inv_world)                       sgd_quantized_gradients_parallel_comm.py:626
+// or row-wise sparse Adagrad (USE_MOM):                      optim/rwsadagrad.py:97-113
+//   m[row] += mean_d(g^2);  W[row] += (-lr) * (g / (sqrt(m[row]) + eps))
+template <int COLS, bool USE_MOM>
+__global__ void __launch_bounds__(256)
+sgd_rows_kernel(const __grid_constant__ TableSet ts, const __grid_constant__ MomPtrs mom, int dim4, int group,
+                const int* __restrict__ uniq_rows, const int* __restrict__ uniq_count,
+                const float* __restrict__ grad_sums, long long capacity, float neg_lr, float inv_world, float eps) {
+  const int t = blockIdx.y;
+  const int U = uniq_count[t];
+  const int lane = threadIdx.x % group;
+  const int gpb = blockDim.x / group;
+  for (int jb = blockIdx.x * gpb; jb < U; jb += gridDim.x * gpb) {     // block-uniform trip count (shuffles below)
+    const int j = min(jb + (int)threadIdx.x / group, U - 1);
+    const bool live = jb + (int)threadIdx.x / group < U;
+    const long long row = uniq_rows[(long long)t * capacity + j];
+    const float4* g4 = reinterpret_cast<const float4*>(grad_sums + ((long long)t * capacity + j) * dim4 * 4);
+    float4* w4 = reinterpret_cast<float4*>(ts.w[t] + row * dim4 * 4);
+    float4 g[COLS];
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int col = lane + c * group;
+      g[c] = col < dim4 ? g4[col] : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[c].x = __fmul_rn(g[c].x, inv_world); g[c].y = __fmul_rn(g[c].y, inv_world);
+      g[c].z = __fmul_rn(g[c].z, inv_world); g[c].w = __fmul_rn(g[c].w, inv_world);
+      if (USE_MOM) sq += g[c].x * g[c].x + g[c].y * g[c].y + g[c].z * g[c].z + g[c].w * g[c].w;
+    }
+    float std = 1.0f;
+    if (USE_MOM) {
+      for (int d = group >> 1; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+      float* mrow = mom.p[t] + row;
+      float mval = 0.f;
+      if (lane == 0 && live) { mval = *mrow + sq / (float)(dim4 * 4); *mrow = mval; }
+      mval = __shfl_sync(0xffffffffu, mval, (threadIdx.x & 31) - lane);
+      std = sqrtf(mval) + eps;
+    }
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int col = lane + c * group;
+      if (col >= dim4 || !live) continue;
+      float4 w = w4[col];
+      float4 u = g[c];
+      if (USE_MOM) { u.x = __fdiv_rn(u.x, std); u.y = __fdiv_rn(u.y, std); u.z = __fdiv_rn(u.z, std); u.w = __fdiv_rn(u.w, std); }
+      w.x = __fadd_rn(w.x, __fmul_rn(neg_lr, u.x)); w.y = __fadd_rn(w.y, __fmul_rn(neg_lr, u.y));
+      w.z = __fadd_rn(w.z, __fmul_rn(neg_lr, u.z)); w.w = __fadd_rn(w.w, __fmul_rn(neg_lr, u.w));
+      w4[col] = w;
+    }
+  }
+}
+
+}  // namespace dqrm
+
+using namespace dqrm;
+
+namespace dqrm { size_t bwd_large_workspace_bytes(int64_t lookups); }   // embbag_bwd_large.cu
+
+extern "C" size_t dqrm_bwd_workspace_bytes(int num_tables, int64_t max_lookups_per_table, int dim) {
+  (void)num_tables; (void)dim;
+  if (max_lookups_per_table <= DQRM_BWD_CTA_MAX_LOOKUPS) return 0;
+  return dqrm::bwd_large_workspace_bytes(max_lookups_per_table);
+}
+
+namespace dqrm {
+int embbag_bwd_large(int t, long long rows, long long idx_begin, long long idx_end, int dim,
+                     const int64_t* indices, const int64_t* offsets, int64_t bags,
+                     const float* dout, int64_t dts, int64_t dbs, const float* fwd_scale,
+                     int64_t capacity, int32_t* uniq_rows, int32_t* uniq_count, float* grad_sums,
+                     int grad_bits, float* grad_scale_local, int32_t* status,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st);   // embbag_bwd_large.cu
+}
+
+extern "C" int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
+                               const int64_t* indices, const int64_t* offsets, const int64_t* idx_begin, int64_t bags,
+                               const float* dout, int64_t dout_table_stride, int64_t dout_bag_stride,
+                               const float* fwd_scale,
+                               int64_t capacity, int32_t* uniq_rows, int32_t* uniq_count, float* grad_sums,
+                               int grad_bits, float* grad_scale_local,
+                               int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  DQRM_REQUIRE(rows && indices && offsets && idx_begin && dout && uniq_rows && uniq_count && grad_sums && status,
+               -EINVAL, "embbag_bwd: null argument");
+  DQRM_REQUIRE(num_tables >= 1 && num_tables <= DQRM_MAX_TABLES, -E2BIG, "embbag_bwd: num_tables=%d", num_tables);
+  DQRM_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= 512, -EINVAL, "embbag_bwd: dim=%d must be a multiple of 4 in [4,512]", dim);
+  DQRM_REQUIRE(bags >= 1 && bags < (1ll << 31), -EINVAL, "embbag_bwd: bags=%lld", (long long)bags);
+  DQRM_REQUIRE(!grad_scale_local || (grad_bits >= 2 && grad_bits <= 16), -EINVAL, "embbag_bwd: grad_bits=%d", grad_bits);
+  DQRM_REQUIRE(dout_bag_stride % 4 == 0 && dout_table_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(dout) & 15u) == 0,
+               -EINVAL, "embbag_bwd: dout must be 16-byte aligned with strides multiple of 4");
+  DQRM_REQUIRE((reinterpret_cast<uintptr_t>(grad_sums) & 15u) == 0, -EINVAL, "embbag_bwd: grad_sums not 16-byte aligned");
+  BwdArgs a;
+  long long lmax = 0;
+  for (int k = 0; k < num_tables; ++k) {
+    DQRM_REQUIRE(rows[k] >= 1 && rows[k] < (1ll << 31), -EINVAL, "embbag_bwd: rows[%d]=%lld", k, (long long)rows[k]);
+    DQRM_REQUIRE(idx_begin[k + 1] >= idx_begin[k], -EINVAL, "embbag_bwd: idx_begin not monotone at %d", k);
+    a.rows[k] = rows[k];
+    a.idx_begin[k] = idx_begin[k];
+    const long long L = idx_begin[k + 1] - idx_begin[k];
+    DQRM_REQUIRE(L <= capacity, -EINVAL, "embbag_bwd: table %d has %lld lookups > capacity %lld", k, L, (long long)capacity);
+    if (L > lmax) lmax = L;
+  }
+  a.idx_begin[num_tables] = idx_begin[num_tables];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const RowLanes rl = row_lanes(dim);
+
+  if (lmax > DQRM_BWD_CTA_MAX_LOOKUPS) {
+    // large tables: one multi-block radix-sort pipeline per table
+    for (int k = 0; k < num_tables; ++k) {
+      int rc = embbag_bwd_large(k, rows[k], idx_begin[k], idx_begin[k + 1], dim, indices, offsets, bags, dout,
+                                dout_table_stride, dout_bag_stride, fwd_scale, capacity, uniq_rows, uniq_count,
+                                grad_sums, grad_bits, grad_scale_local, status, workspace, workspace_bytes, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+
+  int n = 2;
+  while (n < lmax) n <<= 1;
+  int threads = n / 2;
+  if (threads < 128) threads = 128;
+  if (threads > 1024) threads = 1024;
+  const size_t smem = (size_t)n * sizeof(unsigned long long) + ((size_t)n + 4) * sizeof(int);
+#define DQRM_BWD(COLS)                                                                                         \
+  do {                                                                                                         \
+    auto kern = embbag_bwd_cta_kernel<COLS>;                                                                   \
+    if (smem > 48 * 1024) {                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+      DQRM_REQUIRE(e == cudaSuccess, -EIO, "embbag_bwd: cannot opt in to %zu B shared memory: %s", smem,       \
+                   cudaGetErrorString(e));                                                                     \
+    }                                                                                                          \
+    kern<<<num_tables, threads, smem, st>>>(a, dim / 4, rl.group, reinterpret_cast<const long long*>(indices), \
+                                            reinterpret_cast<const long long*>(offsets), bags, dout,           \
+                                            dout_table_stride, dout_bag_stride, fwd_scale, capacity, uniq_rows, \
+                                            uniq_count, grad_sums, grad_bits, grad_scale_local, status);       \
+  } while (0)
+  if (rl.cols == 1) DQRM_BWD(1);
+  else if (rl.cols == 2) DQRM_BWD(2);
+  else DQRM_BWD(4);
+#undef DQRM_BWD
+  DQRM_LAUNCH_CHECK("embbag_bwd_cta_kernel");
+  return 0;
+}
+
+extern "C" int dqrm_grad_absmax_scale(int num_tables, int dim, const float* grad_sums, const int32_t* uniq_count,
+                                      int64_t capacity, int bits, float* scale_local, void* stream) {
+  DQRM_REQUIRE(grad_sums && uniq_count && scale_local, -EINVAL, "grad_absmax_scale: null argument");
+  DQRM_REQUIRE(num_tables >= 1 && bits >= 2 && bits <= 16, -EINVAL, "grad_absmax_scale: bad argument");
+  grad_absmax_scale_kernel<<<num_tables, 256, 0, static_cast<cudaStream_t>(stream)>>>(dim, grad_sums, uniq_count,
+                                                                                      capacity, bits, scale_local);
+  DQRM_LAUNCH_CHECK("grad_absmax_scale_kernel");
+  return 0;
+}
+
+extern "C" int dqrm_sgd_rows(int num_tables, float* const* weight, const int64_t* rows, int dim,
+                             const int32_t* uniq_rows, const int32_t* uniq_count, const float* grad_sums,
+                             int64_t capacity, float lr, float inv_world, float* const* momentum, float eps,
+                             void* stream) {
+  DQRM_REQUIRE(weight && rows && uniq_rows && uniq_count && grad_sums, -EINVAL, "sgd_rows: null argument");
+  DQRM_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= 512, -EINVAL, "sgd_rows: dim=%d", dim);
+  TableSet ts;
+  if (int rc = fill_tables(ts, num_tables, weight, rows, nullptr)) return rc;
+  const RowLanes rl = row_lanes(dim);
+  MomPtrs mom;
+  for (int k = 0; k < DQRM_MAX_TABLES; ++k) mom.p[k] = (momentum && k < num_tables) ? momentum[k] : nullptr;
+  long long blocks = ceil_div(capacity, 256 / rl.group);
+  if (blocks > 4 * kSMs) blocks = 4 * kSMs;
+  if (blocks < 1) blocks = 1;
+  dim3 grid((unsigned)blocks, num_tables);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float neg_lr = -lr;
+#define DQRM_SGD(COLS)                                                                                              \
+  do {                                                                                                              \
+    if (momentum) sgd_rows_kernel<COLS, true><<<grid, 256, 0, st>>>(ts, mom, dim / 4, rl.group, uniq_rows, uniq_count, \
+                                                                    grad_sums, capacity, neg_lr, inv_world, eps);   \
+    else sgd_rows_kernel<COLS, false><<<grid, 256, 0, st>>>(ts, mom, dim / 4, rl.group, uniq_rows, uniq_count,      \
+                                                            grad_sums, capacity, neg_lr, inv_world, eps);           \
+  } while (0)
+  if (rl.cols == 1) DQRM_SGD(1);
+  else if (rl.cols == 2) DQRM_SGD(2);
+  else DQRM_SGD(4);
+#undef DQRM_SGD
+  DQRM_LAUNCH_CHECK("sgd_rows_kernel");
+  return 0;
+}

@@ -1,0 +1,151 @@
+// (a15) QuantLinear weight/bias fake-quantisation and (a11) the 8-bit per-channel quantised exchange
+// of the dense (MLP) gradients.
+// Reference: QuantLinear.forward, quantization_supp/quant_modules_not_quantize_grad.py:125-154
+//            symmetric_linear_quantization_params, quantization_supp/quant_utils.py:196-220
+//            quantize_linear_grad / quantize_bias_grad, sgd_quantized_gradients_parallel_comm.py:892-961
+//            weight_update_parallel_comm (MLP part), sgd_quantized_gradients_parallel_comm.py:630-663
+//
+// Everything here is "one warp per quantisation channel" over a flat fp32 arena: a weight row is a
+// channel, a whole bias vector is one channel.  All 14 MLP tensors of the model are handled by ONE
+// launch per phase (scale / quantise / apply) instead of the reference's ~10 ATen launches and two
+// Gloo all-reduces per tensor.  The GEMMs themselves stay on cuBLAS (fp32, library call).
+#include "common.cuh"
+
+namespace dqrm {
+
+__global__ void __launch_bounds__(256)
+linear_fakequant_kernel(const float* __restrict__ W, const float* __restrict__ b, int out_f, int in_f, int bits,
+                        float* __restrict__ W_int, float* __restrict__ b_int, float* __restrict__ scale_row) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= out_f) return;
+  const float* w = W + (long long)row * in_f;
+  unsigned m = 0u;
+  for (int i = lane; i < in_f; i += 32) m = max(m, abs_bits(w[i]));
+  m = warp_max_u32(m);
+  const float s = scale_of(__uint_as_float(m), bits);
+  const float inv = __fdiv_rn(1.0f, s);
+  const float hi = qmax_of(bits), lo = -hi - 1.0f;
+  float* q = W_int + (long long)row * in_f;
+  for (int i = lane; i < in_f; i += 32) q[i] = quant_code(w[i], inv, lo, hi);
+  if (lane == 0) {
+    scale_row[row] = s;
+    if (b) b_int[row] = quant_code(b[row], inv, lo, hi);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dense_grad_scale_kernel(const float* __restrict__ grad, const long long* __restrict__ chan_begin, int num_chan,
+                        int bits, float* __restrict__ scale_local) {
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ch >= num_chan) return;
+  const long long a = chan_begin[ch], e = chan_begin[ch + 1];
+  unsigned m = 0u;
+  for (long long i = a + lane; i < e; i += 32) m = max(m, abs_bits(grad[i]));
+  m = warp_max_u32(m);
+  if (lane == 0) scale_local[ch] = scale_of(__uint_as_float(m), bits);
+}
+
+__global__ void __launch_bounds__(256)
+dense_grad_quant_kernel(const float* __restrict__ grad, const long long* __restrict__ chan_begin, int num_chan,
+                        const float* __restrict__ scale_sum, float inv_world, int bits,
+                        float* __restrict__ codes, float* __restrict__ scale_mean) {
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ch >= num_chan) return;
+  const long long a = chan_begin[ch], e = chan_begin[ch + 1];
+  const float s_bar = __fmul_rn(scale_sum[ch], inv_world);
+  const float inv = __fdiv_rn(1.0f, s_bar);
+  const float hi = qmax_of(bits), lo = -hi - 1.0f;
+  for (long long i = a + lane; i < e; i += 32) codes[i] = quant_code(grad[i], inv, lo, hi);
+  if (lane == 0) scale_mean[ch] = s_bar;
+}
+
+__global__ void __launch_bounds__(256)
+dense_apply_kernel(float* __restrict__ param, const float* __restrict__ code_sum, const long long* __restrict__ chan_begin,
+                   int num_chan, const float* __restrict__ scale_mean, float inv_world, float neg_lr) {
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ch >= num_chan) return;
+  const long long a = chan_begin[ch], e = chan_begin[ch + 1];
+  const float s = scale_mean ? scale_mean[ch] : 1.0f;
+  for (long long i = a + lane; i < e; i += 32) {
+    const float g = __fmul_rn(code_sum[i], inv_world);                    // all_reduce(SUM) * (1/N)
+    float u = __fmul_rn(neg_lr, g);                                       // (-lr * grad) ...
+    if (scale_mean) u = __fmul_rn(u, s);                                  // ... * s          (:642-643)
+    param[i] = __fadd_rn(param[i], u);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fake_quant_kernel(const float* __restrict__ x, long long rows, long long cols, const float* __restrict__ scale,
+                  int per_row, int bits, float* __restrict__ q, float* __restrict__ dq) {
+  const float hi = qmax_of(bits), lo = -hi - 1.0f;
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float s = per_row ? scale[i / cols] : scale[0];
+    const float c = quant_code(x[i], __fdiv_rn(1.0f, s), lo, hi);
+    q[i] = c;
+    if (dq) dq[i] = __fmul_rn(c, s);
+  }
+}
+
+}  // namespace dqrm
+
+using namespace dqrm;
+
+extern "C" int dqrm_fake_quant(const float* x, int64_t rows, int64_t cols, const float* scale, int scale_per_row,
+                               int bits, float* q, float* dequant, void* stream) {
+  DQRM_REQUIRE(x && scale && q && rows >= 0 && cols >= 0, -EINVAL, "fake_quant: bad argument");
+  DQRM_REQUIRE(bits >= 2 && bits <= 16, -EINVAL, "fake_quant: bits=%d outside [2,16]", bits);
+  if (rows * cols == 0) return 0;
+  long long blocks = ceil_div(rows * cols, 256);
+  if (blocks > 8 * kSMs) blocks = 8 * kSMs;
+  fake_quant_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, cols, scale, scale_per_row,
+                                                                                     bits, q, dequant);
+  DQRM_LAUNCH_CHECK("fake_quant_kernel");
+  return 0;
+}
+
+extern "C" int dqrm_linear_fakequant(const float* W, const float* b, int out_features, int in_features, int bits,
+                                     float* W_int, float* b_int, float* scale_row, void* stream) {
+  DQRM_REQUIRE(W && W_int && scale_row, -EINVAL, "linear_fakequant: null argument");
+  DQRM_REQUIRE((b == nullptr) == (b_int == nullptr), -EINVAL, "linear_fakequant: b and b_int must come together");
+  DQRM_REQUIRE(out_features >= 1 && in_features >= 1, -EINVAL, "linear_fakequant: bad shape");
+  DQRM_REQUIRE(bits >= 2 && bits <= 16, -EINVAL, "linear_fakequant: bits=%d outside [2,16]", bits);
+  linear_fakequant_kernel<<<(out_features + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      W, b, out_features, in_features, bits, W_int, b_int, scale_row);
+  DQRM_LAUNCH_CHECK("linear_fakequant_kernel");
+  return 0;
+}
+
+extern "C" int dqrm_dense_grad_scale(const float* grad, const int64_t* chan_begin, int num_chan, int bits,
+                                     float* scale_local, void* stream) {
+  DQRM_REQUIRE(grad && chan_begin && scale_local && num_chan >= 1, -EINVAL, "dense_grad_scale: bad argument");
+  DQRM_REQUIRE(bits >= 2 && bits <= 16, -EINVAL, "dense_grad_scale: bits=%d outside [2,16]", bits);
+  dense_grad_scale_kernel<<<(num_chan + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      grad, reinterpret_cast<const long long*>(chan_begin), num_chan, bits, scale_local);
+  DQRM_LAUNCH_CHECK("dense_grad_scale_kernel");
+  return 0;
+}
+
+extern "C" int dqrm_dense_grad_quant(const float* grad, const int64_t* chan_begin, int num_chan,
+                                     const float* scale_sum, float inv_world, int bits,
+                                     float* codes, float* scale_mean, void* stream) {
+  DQRM_REQUIRE(grad && chan_begin && scale_sum && codes && scale_mean && num_chan >= 1, -EINVAL, "dense_grad_quant: bad argument");
+  DQRM_REQUIRE(bits >= 2 && bits <= 16, -EINVAL, "dense_grad_quant: bits=%d outside [2,16]", bits);
+  dense_grad_quant_kernel<<<(num_chan + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      grad, reinterpret_cast<const long long*>(chan_begin), num_chan, scale_sum, inv_world, bits, codes, scale_mean);
+  DQRM_LAUNCH_CHECK("dense_grad_quant_kernel");
+  return 0;
+}
+
+extern "C" int dqrm_dense_apply(float* param, const float* code_sum, const int64_t* chan_begin, int num_chan,
+                                const float* scale_mean, float inv_world, float lr, void* stream) {
+  DQRM_REQUIRE(param && code_sum && chan_begin && num_chan >= 1, -EINVAL, "dense_apply: bad argument");
+  dense_apply_kernel<<<(num_chan + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, code_sum, reinterpret_cast<const long long*>(chan_begin), num_chan, scale_mean, inv_world, -lr);
+  DQRM_LAUNCH_CHECK("dense_apply_kernel");
+  return 0;
+}

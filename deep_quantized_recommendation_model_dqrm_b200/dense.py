@@ -1,0 +1,110 @@
+"""Flat arena for the dense (MLP) parameters and their 8-bit per-channel quantised gradient
+exchange.  All QuantLinear weights and biases of a model live in ONE fp32
+buffer (parameters are views), their gradients in a second one, so that scale / quantise / apply are
+one kernel launch each and the exchange is two all-reduces in total (the reference: 28 Gloo
+all-reduces per step, sgd_quantized_gradients_parallel_comm.py:341-394)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class DenseArena:
+    def __init__(self, layers, device):
+        """layers: QuantLinear modules in reference order (bot_l then top_l)."""
+        self.lib = _lib.load()
+        self.layers = list(layers)
+        self.device = device
+        params = []
+        for l in self.layers:
+            params.append(l.weight)
+            if l.bias is not None:
+                params.append(l.bias)
+        total = sum(p.numel() for p in params)
+        self.flat = torch.empty(total, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
+        chan = [0]
+        off = 0
+        for p in params:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + n].view(p.shape)
+            if p.grad is not None:                # adopt a gradient produced before the arena existed
+                self.flat_grad[off:off + n].copy_(p.grad.reshape(-1))
+            p.grad = self.flat_grad[off:off + n].view(p.shape)
+            if p.dim() == 2:                      # weight: one channel per output row  (sgd...:905-906)
+                for r in range(p.shape[0]):
+                    chan.append(off + (r + 1) * p.shape[1])
+            else:                                 # bias: one scalar scale for the vector (sgd...:945-947)
+                chan.append(off + n)
+            off += n
+        self.params = params
+        self.total = total
+        self.num_chan = len(chan) - 1
+        self.chan_begin = torch.tensor(chan, dtype=torch.int64, device=device)
+        self.scale_local = torch.zeros(self.num_chan, dtype=torch.float32, device=device)
+        self.scale_mean = torch.zeros(self.num_chan, dtype=torch.float32, device=device)
+        self.codes = torch.zeros(total, dtype=torch.float32, device=device)
+        self._bind_scale_views()
+
+    def _bind_scale_views(self):
+        """weight_scaling_factor / bias_scaling_factor of every layer = views of scale_mean (sgd...:343,352)."""
+        c = 0
+        for l in self.layers:
+            o = l.weight.shape[0]
+            l.weight_scaling_factor = self.scale_mean[c:c + o]
+            c += o
+            if l.bias is not None:
+                l.bias_scaling_factor = self.scale_mean[c]
+                c += 1
+
+    def intact(self):
+        """True while every parameter (and its grad) still aliases the arena."""
+        base, gbase = self.flat.data_ptr(), self.flat_grad.data_ptr()
+        off = 0
+        for p in self.params:
+            if p.data.data_ptr() != base + 4 * off or p.grad is None or p.grad.data_ptr() != gbase + 4 * off:
+                return False
+            off += p.numel()
+        return True
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def quantize_exchange(self, world=1, process_group=None, bits=8, quantized=True):
+        """quantize_linear_grad / quantize_bias_grad for every tensor at once
+        (sgd_quantized_gradients_parallel_comm.py:892-961): local scales -> SUM all-reduce ->
+        quantise with the mean scale -> SUM all-reduce of the codes."""
+        if world > 1:
+            import torch.distributed as dist
+        if not quantized:
+            self.codes.copy_(self.flat_grad)
+            if world > 1:
+                dist.all_reduce(self.codes, group=process_group)
+            return
+        self.local_scale(bits)
+        if world > 1:
+            dist.all_reduce(self.scale_local, group=process_group)
+        self.quantize(world, bits)
+        if world > 1:
+            dist.all_reduce(self.codes, group=process_group)
+
+    def local_scale(self, bits=8):
+        _lib.check(self.lib.dqrm_dense_grad_scale(self.flat_grad.data_ptr(), self.chan_begin.data_ptr(), self.num_chan,
+                                                  bits, self.scale_local.data_ptr(), _lib.stream_ptr()),
+                   "dqrm_dense_grad_scale")
+
+    def quantize(self, world=1, bits=8):
+        """scale_local must hold the SUM over ranks of the local scales."""
+        _lib.check(self.lib.dqrm_dense_grad_quant(self.flat_grad.data_ptr(), self.chan_begin.data_ptr(), self.num_chan,
+                                                  self.scale_local.data_ptr(), float(1.0 / world), bits,
+                                                  self.codes.data_ptr(), self.scale_mean.data_ptr(), _lib.stream_ptr()),
+                   "dqrm_dense_grad_quant")
+
+    def apply(self, lr, world=1, quantized=True):
+        """MLP half of weight_update_parallel_comm (sgd_quantized_gradients_parallel_comm.py:630-663)."""
+        st = _lib.stream_ptr()
+        _lib.check(self.lib.dqrm_dense_apply(self.flat.data_ptr(), self.codes.data_ptr(), self.chan_begin.data_ptr(),
+                                             self.num_chan, self.scale_mean.data_ptr() if quantized else None,
+                                             float(1.0 / world), float(lr), st), "dqrm_dense_apply")

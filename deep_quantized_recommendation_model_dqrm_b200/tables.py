@@ -1,0 +1,275 @@
+"""Host-side state of a group of QAT embedding tables on one GPU.
+
+`EmbeddingTableGroup` owns what the reference scatters over 26 module
+instances and their autograd/optimizer side effects: the per-table scales
+(``eb_scaling_factor``), the de-duplicated row gradients of the current step,
+the gradient scales (``emb_scaling_factor``) and the exchange slots.  Every
+method is a thin call into libdqrm_b200 on the current CUDA stream; nothing
+here computes on the host or synchronises the device, so a whole train step is
+CUDA-graph capturable.
+
+Data layout in HBM:
+  weights      T tables, fp32 [rows_k, D] row-major (optionally views of one arena)
+  scale/inv    fp32 [T]                         (a1)
+  out          fp32 [T, B, D]                   (a3)   codes int8/int16 [T, B, D]
+  uniq_rows    int32 [T, cap]; uniq_count int32 [T]; grad_sums fp32 [T, cap, D]     (a5/a7-1)
+  slot         count[T] | rows[T][cap] | codes[T][cap][D]   (a7-4), gathered = world slots
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class EmbeddingTableGroup:
+    def __init__(self, weights, embedding_bit=4, grad_bit=8):
+        lib = _lib.load()
+        assert len(weights) >= 1
+        w0 = weights[0]
+        if not w0.is_cuda:
+            raise _lib.DqrmLibraryError("EmbeddingTableGroup needs CUDA tensors: there is no CPU path")
+        self.lib = lib
+        self.weights = list(weights)                 # Parameters or tensors; .data re-read at every call
+        self.T = len(weights)
+        self.dim = int(w0.shape[1])
+        self.rows = [int(w.shape[0]) for w in weights]
+        self.device = w0.device
+        self.embedding_bit = int(embedding_bit)
+        self.grad_bit = int(grad_bit)
+        self._rows_arr = _lib.i64_array(self.rows)
+        dev = self.device
+        self.absmax = torch.zeros(self.T, dtype=torch.float32, device=dev)
+        self.scale = torch.zeros(self.T, dtype=torch.float32, device=dev)        # eb_scaling_factor per table
+        self.inv_scale = torch.zeros(self.T, dtype=torch.float32, device=dev)
+        self.scale_valid = False
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._scan_ws = torch.zeros(int(lib.dqrm_scan_workspace_bytes(self.T)), dtype=torch.uint8, device=dev)
+        # step state
+        self.capacity = 0
+        self.world = 1
+        self.bags = 0
+        self.uniq_rows = self.uniq_count = self.grad_sums = None
+        self.grad_scale_local = torch.zeros(self.T, dtype=torch.float32, device=dev)
+        self.grad_scale_mean = torch.zeros(self.T, dtype=torch.float32, device=dev)  # emb_scaling_factor per table
+        self.gathered_scales = None
+        self.slot = self.gathered = None
+        self.updated_rows = self.updated_count = self.qbar = None
+        self._bwd_ws = None
+        self.last = None          # (indices, offsets, idx_begin, idx_begin_arr, bags, full_precision)
+        self.keep_debug = False   # also emit updated_rows / qbar in merge (parity tests, .grad materialisation)
+
+    # ---- helpers --------------------------------------------------------
+    def _wptrs(self):
+        ws = []
+        for w in self.weights:
+            d = w.data
+            if d.dtype != torch.float32 or not d.is_contiguous() or d.device != self.device:
+                raise _lib.DqrmLibraryError("embedding weights must be contiguous fp32 on the group's device")
+            ws.append(d)
+        return _lib.ptr_array(ws)
+
+    def check_status(self):
+        """Device-side data errors (D2H sync). Raises on out-of-range indices etc."""
+        s = int(self.status.item())
+        if s:
+            self.status.zero_()
+            names = [n for b, n in ((1, "index out of range"), (2, "offsets not monotone"), (4, "capacity exceeded")) if s & b]
+            raise IndexError("dqrm kernel status: " + ", ".join(names))
+
+    @staticmethod
+    def pack_inputs(lS_i, lS_o, device):
+        """Reference batch formats -> (indices[L_total], offsets[T,B], idx_begin list, bags).
+        lS_i/lS_o are a [T,B] int64 tensor pair (Criteo) or lists of 1-D tensors
+        (random data); dlrm_data_pytorch.py:328-345, 1099-1157."""
+        if torch.is_tensor(lS_i):
+            T, B = lS_i.shape
+            idx = lS_i.to(device=device, dtype=torch.int64).contiguous().view(-1)
+            idx_begin = [k * B for k in range(T + 1)]
+        else:
+            lens = [int(t.shape[0]) for t in lS_i]
+            idx = torch.cat([t.to(device=device, dtype=torch.int64).view(-1) for t in lS_i])
+            idx_begin = [0]
+            for n in lens:
+                idx_begin.append(idx_begin[-1] + n)
+        if torch.is_tensor(lS_o):
+            off = lS_o.to(device=device, dtype=torch.int64).contiguous()
+        else:
+            off = torch.stack([t.to(device=device, dtype=torch.int64) for t in lS_o]).contiguous()
+        return idx, off, idx_begin, int(off.shape[1])
+
+    # ---- (a1) -----------------------------------------------------------
+    def scan_scales(self, shard_rank=0, shard_world=1, process_group=None):
+        """Recompute every table's scale from a full max-abs pass (one launch).
+        With shard_world > 1 each rank scans 1/world of the rows and the maxima
+        are combined with a MAX all-reduce (replicas are bit-identical)."""
+        lib, st = self.lib, _lib.stream_ptr()
+        sharded = shard_world > 1
+        rc = lib.dqrm_table_absmax_scale(self.T, self._wptrs(), self._rows_arr, self.dim, self.embedding_bit,
+                                         shard_rank, shard_world, self.absmax.data_ptr(),
+                                         None if sharded else self.scale.data_ptr(),
+                                         None if sharded else self.inv_scale.data_ptr(),
+                                         self._scan_ws.data_ptr(), st)
+        _lib.check(rc, "dqrm_table_absmax_scale")
+        if sharded:
+            import torch.distributed as dist
+            dist.all_reduce(self.absmax, op=dist.ReduceOp.MAX, group=process_group)
+            rc = lib.dqrm_scale_from_absmax(self.T, self.absmax.data_ptr(), self.embedding_bit,
+                                            self.scale.data_ptr(), self.inv_scale.data_ptr(), st)
+            _lib.check(rc, "dqrm_scale_from_absmax")
+        self.scale_valid = True
+
+    # ---- (a3) -----------------------------------------------------------
+    def forward(self, indices, offsets, idx_begin, bags, full_precision=False, want_codes=True, out=None):
+        lib, st = self.lib, _lib.stream_ptr()
+        dev = self.device
+        if out is None:
+            out = torch.empty((self.T, bags, self.dim), dtype=torch.float32, device=dev)
+        codes = None
+        if want_codes and not full_precision:
+            codes = torch.empty((self.T, bags, self.dim), dtype=torch.int8 if self.embedding_bit <= 8 else torch.int16,
+                                device=dev)
+        ib = _lib.i64_array(idx_begin)
+        rc = lib.dqrm_embbag_fwd(self.T, self._wptrs(), self._rows_arr, self.dim, indices.data_ptr(),
+                                 offsets.data_ptr(), ib, bags,
+                                 None if full_precision else self.scale.data_ptr(),
+                                 None if full_precision else self.inv_scale.data_ptr(), self.embedding_bit,
+                                 out.data_ptr(), out.stride(0), out.stride(1), _lib.ptr(codes),
+                                 self.status.data_ptr(), st)
+        _lib.check(rc, "dqrm_embbag_fwd")
+        self.last = (indices, offsets, idx_begin, ib, bags, full_precision)
+        self.codes = codes
+        return out
+
+    # ---- (a4 bwd, a5, a7-1/2) ---------------------------------------------
+    def _ensure_step_buffers(self, capacity, world):
+        if self.capacity == capacity and self.world == world and self.uniq_rows is not None:
+            return
+        dev, T, D = self.device, self.T, self.dim
+        self.capacity, self.world = capacity, world
+        self.uniq_rows = torch.zeros((T, capacity), dtype=torch.int32, device=dev)
+        self.uniq_count = torch.zeros(T, dtype=torch.int32, device=dev)
+        self.grad_sums = torch.zeros((T, capacity, D), dtype=torch.float32, device=dev)
+        self.gathered_scales = torch.zeros((world, T), dtype=torch.float32, device=dev)
+        sb = int(self.lib.dqrm_slot_bytes(T, capacity, D, self.grad_bit))
+        self.slot_bytes = sb
+        self.gathered = torch.zeros(world * sb, dtype=torch.uint8, device=dev)
+        self.slot = None   # view of this rank's slice of `gathered`, set by exchange()
+        self.updated_rows = self.updated_count = self.qbar = None
+        wsb = int(self.lib.dqrm_bwd_workspace_bytes(T, capacity, D))
+        self._bwd_ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+        self._bwd_ws_bytes = wsb
+
+    def backward(self, dout, world=1, last=None):
+        """De-duplicated row gradients of a forward (default: the last one) from dOut [T, B, D]-strided."""
+        lib, st = self.lib, _lib.stream_ptr()
+        indices, offsets, idx_begin, ib, bags, full_precision = last if last is not None else self.last
+        cap = max(idx_begin[k + 1] - idx_begin[k] for k in range(self.T))
+        cap = max(cap, 1)
+        self._ensure_step_buffers(cap, world)
+        rc = lib.dqrm_embbag_bwd(self.T, self._rows_arr, self.dim, indices.data_ptr(), offsets.data_ptr(), ib, bags,
+                                 dout.data_ptr(), dout.stride(0), dout.stride(1),
+                                 None if full_precision else self.scale.data_ptr(),
+                                 self.capacity, self.uniq_rows.data_ptr(), self.uniq_count.data_ptr(),
+                                 self.grad_sums.data_ptr(), self.grad_bit, self.grad_scale_local.data_ptr(),
+                                 self.status.data_ptr(), self._bwd_ws.data_ptr(), self._bwd_ws_bytes, st)
+        _lib.check(rc, "dqrm_embbag_bwd")
+
+    def set_grad_bit(self, bits):
+        """Change the gradient code width after a backward: re-size the slots, refresh the local scale."""
+        self.grad_bit = int(bits)
+        if self.uniq_rows is None:
+            return
+        sb = int(self.lib.dqrm_slot_bytes(self.T, self.capacity, self.dim, self.grad_bit))
+        self.slot_bytes = sb
+        self.gathered = torch.zeros(self.world * sb, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.dqrm_grad_absmax_scale(self.T, self.dim, self.grad_sums.data_ptr(),
+                                                   self.uniq_count.data_ptr(), self.capacity, self.grad_bit,
+                                                   self.grad_scale_local.data_ptr(), _lib.stream_ptr()),
+                   "dqrm_grad_absmax_scale")
+
+    def topk(self, k):
+        """(a8) keep the k highest-energy rows per table, then refresh the local scale."""
+        st = _lib.stream_ptr()
+        _lib.check(self.lib.dqrm_grad_topk(self.T, self.dim, self.grad_sums.data_ptr(), self.uniq_rows.data_ptr(),
+                                           self.uniq_count.data_ptr(), self.capacity, int(k), st), "dqrm_grad_topk")
+        _lib.check(self.lib.dqrm_grad_absmax_scale(self.T, self.dim, self.grad_sums.data_ptr(),
+                                                   self.uniq_count.data_ptr(), self.capacity, self.grad_bit,
+                                                   self.grad_scale_local.data_ptr(), st), "dqrm_grad_absmax_scale")
+
+    # ---- (a7-3..5) --------------------------------------------------------
+    def exchange(self, world=1, rank=0, process_group=None):
+        """Scale all-gather -> pack -> slot all-gather (the only two collectives of the
+        embedding exchange, replacing 52 Gloo calls).  Composed of the three phases below so that
+        tests can emulate several ranks on one GPU by copying between replicas' buffers."""
+        assert world == self.world, "backward() and exchange() must agree on world size"
+        self.stage_scale(rank)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.gathered_scales.view(-1), self.grad_scale_local, group=process_group)
+        self.pack(rank)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.gathered, self.slot, group=process_group)
+
+    def stage_scale(self, rank=0):
+        """Phase 1: this rank's 26 local gradient scales into row `rank` of gathered_scales."""
+        self.gathered_scales[rank].copy_(self.grad_scale_local)
+
+    def pack(self, rank=0):
+        """Phase 2 (after the scale all-gather): quantise with the rank-mean scale into slot `rank`."""
+        sb = self.slot_bytes
+        self.slot = self.gathered[rank * sb:(rank + 1) * sb]
+        rc = self.lib.dqrm_grad_pack(self.T, self.dim, self.grad_sums.data_ptr(), self.uniq_rows.data_ptr(),
+                                     self.uniq_count.data_ptr(), self.capacity, self.gathered_scales.data_ptr(),
+                                     self.world, self.grad_bit, self.slot.data_ptr(), self.grad_scale_mean.data_ptr(),
+                                     _lib.stream_ptr())
+        _lib.check(rc, "dqrm_grad_pack")
+
+    def merge_apply(self, lr):
+        """(a7-5, a9): W[row] += (-lr) * ((sum_r q_r * 1/N) * s_bar) on the union of rows."""
+        lib, st = self.lib, _lib.stream_ptr()
+        if self.keep_debug and self.updated_rows is None:
+            n = self.world * self.capacity
+            self.updated_rows = torch.zeros((self.T, n), dtype=torch.int32, device=self.device)
+            self.updated_count = torch.zeros(self.T, dtype=torch.int32, device=self.device)
+            self.qbar = torch.zeros((self.T, n, self.dim), dtype=torch.float32, device=self.device)
+        dbg = self.keep_debug
+        rc = lib.dqrm_grad_merge_apply(self.T, self._wptrs(), self._rows_arr, self.dim, self.gathered.data_ptr(),
+                                       self.world, self.capacity, self.grad_bit, self.grad_scale_mean.data_ptr(),
+                                       float(lr), _lib.ptr(self.updated_rows) if dbg else None,
+                                       _lib.ptr(self.updated_count) if dbg else None,
+                                       _lib.ptr(self.qbar) if dbg else None, self.status.data_ptr(), st)
+        _lib.check(rc, "dqrm_grad_merge_apply")
+
+    def sgd_apply(self, lr, inv_world=1.0, momentum=None, eps=1e-10):
+        """(a10) un-quantised row update from the local de-duplicated sums (optionally RW-Adagrad)."""
+        st = _lib.stream_ptr()
+        mom = _lib.ptr_array(momentum) if momentum is not None else None
+        rc = self.lib.dqrm_sgd_rows(self.T, self._wptrs(), self._rows_arr, self.dim, self.uniq_rows.data_ptr(),
+                                    self.uniq_count.data_ptr(), self.grad_sums.data_ptr(), self.capacity, float(lr),
+                                    float(inv_world), mom, float(eps), st)
+        _lib.check(rc, "dqrm_sgd_rows")
+
+    # ---- views for tests / API compatibility (these synchronise) ----------
+    def slot_views(self, rank=0):
+        """(count[T], rows[T,cap], codes[T,cap,D]) views of one gathered slot."""
+        ro, co = C.c_size_t(), C.c_size_t()
+        self.lib.dqrm_slot_layout(self.T, self.capacity, self.dim, self.grad_bit, C.byref(ro), C.byref(co))
+        sb = self.slot_bytes
+        s = self.gathered[rank * sb:(rank + 1) * sb]
+        cnt = s[:self.T * 4].view(torch.int32)
+        rows = s[ro.value:ro.value + self.T * self.capacity * 4].view(torch.int32).view(self.T, self.capacity)
+        cb = 1 if self.grad_bit <= 8 else 2
+        codes = s[co.value:co.value + self.T * self.capacity * self.dim * cb]
+        codes = codes.view(torch.int8 if cb == 1 else torch.int16).view(self.T, self.capacity, self.dim)
+        return cnt, rows, codes
+
+    def sparse_grad(self, t):
+        """Coalesced sparse COO gradient of table t (what the reference leaves in
+        ``embedding_bag.weight.grad`` after ``.coalesce()``, sgd...parallel_comm.py:859)."""
+        u = int(self.uniq_count[t].item())
+        return torch.sparse_coo_tensor(self.uniq_rows[t, :u].long()[None], self.grad_sums[t, :u].clone(),
+                                       size=(self.rows[t], self.dim))

@@ -1,0 +1,265 @@
+/*
+ * dqrm_b200.h -- C ABI of libdqrm_b200.so: the B200 (sm_100a) implementation of
+ * DQRM's data-parallel hot path.
+ *
+ * The reference (YangZhou08/Deep_Quantized_Recommendation_Model_DQRM) is pure
+ * Python over stock PyTorch ops: it has no FFI of its own, so each entry point
+ * below names the reference Python function (file:line under the reference
+ * tree) whose arithmetic it replaces.  The Python surface that binds these
+ * (ctypes) keeps the reference's module / function names.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in any signature.  `stream` is
+ *     a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - "dev" pointers are device memory owned by the caller; "host" pointers are
+ *     small per-table metadata arrays read synchronously during the call (they
+ *     are baked into the kernel parameters, so calls are CUDA-graph capturable).
+ *   - every call is asynchronous on `stream`, never synchronises the device,
+ *     and never allocates.  Workspaces are sized by the *_bytes queries.
+ *   - return value: 0 = launched; <0 = -errno style (-EINVAL bad shape / bits /
+ *     alignment, -E2BIG more than DQRM_MAX_TABLES tables or a table too large
+ *     for the fast path, -ENOMEM workspace too small, -EIO CUDA launch error).
+ *     dqrm_last_error() returns a thread-local description of the last failure.
+ *   - data-dependent errors (index out of range) cannot be reported
+ *     synchronously: kernels OR a DQRM_STATUS_* bit into the caller's `status`
+ *     word (dev int32, zero it once) and clamp the offending index.
+ *   - all floating point is IEEE fp32 with round-to-nearest-even, no FMA
+ *     contraction on the quantisation / update paths (bit-exact codes and
+ *     scales versus the reference); tables are fp32 [rows, dim] row-major with
+ *     16-byte aligned base and dim % 4 == 0.
+ *   - rows of a table are addressed by int64 on input (the reference's index
+ *     dtype) and stored as int32 in de-duplicated row lists (rows < 2^31).
+ */
+#ifndef DQRM_B200_H
+#define DQRM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DQRM_API __attribute__((visibility("default")))
+#else
+#define DQRM_API
+#endif
+
+#define DQRM_ABI_VERSION 1
+#define DQRM_MAX_TABLES 64           /* tables per call (kernel-parameter descriptor size) */
+#define DQRM_BWD_CTA_MAX_LOOKUPS 16384 /* per-table lookups handled by the single-CTA sort path */
+
+#define DQRM_STATUS_INDEX_RANGE 1    /* an index was <0 or >= rows (clamped) */
+#define DQRM_STATUS_OFFSET_ORDER 2   /* offsets not monotone / outside the index segment */
+#define DQRM_STATUS_CAPACITY 4       /* more unique rows than `capacity` */
+
+DQRM_API int dqrm_abi_version(void);
+DQRM_API const char* dqrm_last_error(void);
+
+/* ------------------------------------------------------------------ (a1) --
+ * Per-table symmetric scale: absmax = max|W| over the whole table, then
+ * s = max(absmax, 1e-8) / (2^(bits-1)-1) and inv_s = 1.0f / s.
+ * Replaces symmetric_linear_quantization_param_two
+ *   (quantization_supp/quant_utils.py:141-194), called once per table per
+ *   forward by QuantEmbeddingBagTwo.forward
+ *   (quantization_supp/quant_modules_not_quantize_grad.py:337).
+ * All tables are reduced by ONE launch.  `shard_world` > 1 restricts the scan
+ * to the `shard_rank`-th contiguous slice of every table's rows (replicas are
+ * identical, so max over ranks == full scan): then only `absmax` is meaningful
+ * and the caller combines ranks with a MAX all-reduce before
+ * dqrm_scale_from_absmax.
+ *   weight   host array [num_tables] of dev pointers (fp32 [rows_k, dim])
+ *   rows     host array [num_tables]
+ *   absmax   dev [num_tables] out
+ *   scale, inv_scale  dev [num_tables] out, or both NULL (absmax only)
+ *   workspace dev, dqrm_scan_workspace_bytes(); must be zero before first use,
+ *            every launch leaves it zero again.
+ */
+DQRM_API size_t dqrm_scan_workspace_bytes(int num_tables);
+DQRM_API int dqrm_table_absmax_scale(int num_tables, const float* const* weight, const int64_t* rows, int dim,
+                            int bits, int shard_rank, int shard_world,
+                            float* absmax, float* scale, float* inv_scale,
+                            void* workspace, void* stream);
+/* s = max(absmax,1e-8)/n ; inv = 1/s  for n_scales independent entries (quant_utils.py:189-192). */
+DQRM_API int dqrm_scale_from_absmax(int n_scales, const float* absmax, int bits, float* scale, float* inv_scale,
+                           void* stream);
+
+/* ------------------------------------------------------------------ (a3) --
+ * Fused gather + sum-pool + fake-quantise + dequantise for all tables in one
+ * launch.  Replaces QuantEmbeddingBagTwo.forward steps (ii)-(iv)
+ *   (quant_modules_not_quantize_grad.py:367,378,393) with SymmetricQuantFunction
+ *   (quant_utils.py:322-346, linear_quantize :75-101), as called per table by
+ *   DLRM_Net.apply_emb (dlrm_s_pytorch_comm_grad.py:614-679).
+ *   pooled = left fold of W[idx] over the bag, in index order
+ *   q   = clamp(rint(inv_s * pooled), -2^(bits-1), 2^(bits-1)-1)
+ *   out = q * s                       (scale == NULL: out = pooled, qm:395)
+ *   indices  dev int64, all tables' lookups concatenated
+ *   idx_begin host [num_tables+1]: table k owns indices[idx_begin[k] .. idx_begin[k+1])
+ *   offsets  dev int64 [num_tables, bags]: bag starts RELATIVE to the table's
+ *            segment (nn.EmbeddingBag offsets, no trailing end)
+ *   out      dev fp32; element (k, b, d) at out[k*out_table_stride + b*out_bag_stride + d]
+ *   codes    NULL, or dev [num_tables, bags, dim] int8 (bits<=8) / int16 (bits<=16)
+ */
+DQRM_API int dqrm_embbag_fwd(int num_tables, const float* const* weight, const int64_t* rows, int dim,
+                    const int64_t* indices, const int64_t* offsets, const int64_t* idx_begin, int64_t bags,
+                    const float* scale, const float* inv_scale, int bits,
+                    float* out, int64_t out_table_stride, int64_t out_bag_stride,
+                    void* codes, int32_t* status, void* stream);
+
+/* ------------------------------------------------- (a4 bwd, a5, a7 step 1-2) --
+ * Sparse row gradient of (a3), de-duplicated: dy = (g*s)/s (autograd of
+ * qm:393 then SymmetricQuantFunction.backward, quant_utils.py:348-363; no clip
+ * mask), one value row per lookup (ATen sparse EmbeddingBag backward,
+ * triggered at dlrm_s_pytorch_comm_grad.py:1938), then Tensor.coalesce
+ * (sgd_quantized_gradients_parallel_comm.py:859): rows sorted ascending and
+ * unique, duplicates summed as a left fold in original lookup order.
+ * Optionally also the per-table gradient scale of quantize_emb_grad step 2
+ * (sgd...parallel_comm.py:861): s_local = max(max|sums|,1e-8)/(2^(grad_bits-1)-1).
+ *   dout       dev fp32, element (k,b,d) at dout[k*dout_table_stride + b*dout_bag_stride + d]
+ *   fwd_scale  dev [num_tables] (the forward's s) or NULL for the full-precision forward (dy = g)
+ *   capacity   slots per table in the outputs (>= lookups of the largest table)
+ *   uniq_rows  dev int32 [num_tables, capacity]; uniq_count dev int32 [num_tables]
+ *   grad_sums  dev fp32 [num_tables, capacity, dim]
+ *   grad_scale_local dev [num_tables] or NULL (then grad_bits is ignored)
+ * One CTA per table sorts (row, bag) keys in shared memory; tables with more
+ * than DQRM_BWD_CTA_MAX_LOOKUPS lookups take the multi-block radix-sort path,
+ * which needs `workspace` (dqrm_bwd_workspace_bytes, 0 when not needed).
+ */
+DQRM_API size_t dqrm_bwd_workspace_bytes(int num_tables, int64_t max_lookups_per_table, int dim);
+DQRM_API int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
+                    const int64_t* indices, const int64_t* offsets, const int64_t* idx_begin, int64_t bags,
+                    const float* dout, int64_t dout_table_stride, int64_t dout_bag_stride,
+                    const float* fwd_scale,
+                    int64_t capacity, int32_t* uniq_rows, int32_t* uniq_count, float* grad_sums,
+                    int grad_bits, float* grad_scale_local,
+                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stand-alone (a7 step 2): s_local[k] from grad_sums / uniq_count. */
+DQRM_API int dqrm_grad_absmax_scale(int num_tables, int dim, const float* grad_sums, const int32_t* uniq_count,
+                           int64_t capacity, int bits, float* scale_local, void* stream);
+
+/* ----------------------------------------------------------------- (a10) --
+ * Un-quantised row update  W[row] += (-lr) * (sum * inv_world)
+ * (weight_update_parallel_comm with emb_grad_quantized=False,
+ *  sgd...parallel_comm.py:626; single process: torch.optim.SGD on the sparse grad).
+ * With `momentum` != NULL applies row-wise sparse Adagrad instead
+ * (optim/rwsadagrad.py:97-113): m[row] += mean(g^2); W[row] -= lr * g / (sqrt(m[row]) + eps).
+ *   momentum  NULL, or host array [num_tables] of dev fp32 [rows_k] accumulators
+ */
+DQRM_API int dqrm_sgd_rows(int num_tables, float* const* weight, const int64_t* rows, int dim,
+                  const int32_t* uniq_rows, const int32_t* uniq_count, const float* grad_sums, int64_t capacity,
+                  float lr, float inv_world, float* const* momentum, float eps, void* stream);
+
+/* ----------------------------------------------------------- (a7 steps 3-4) --
+ * Quantise this rank's de-duplicated row gradients into its exchange slot.
+ *   s_bar[k] = (sum_r gathered_scales[r][k]) * (1/world), summed in rank order
+ *              (all_reduce(SUM) then mul_(1./N), sgd...parallel_comm.py:865-866)
+ *   q        = clamp(rint((1/s_bar) * sums), -2^(bits-1), 2^(bits-1)-1)   (:869)
+ * Slot layout (dqrm_slot_bytes; offsets from dqrm_slot_layout), fixed capacity
+ * so one all-gather of `slot_bytes` per rank replaces the reference's Gloo
+ * sparse all-reduce (:878):
+ *   int32 count[num_tables] | int32 rows[num_tables][capacity] |
+ *   int8 (bits<=8) or int16 codes[num_tables][capacity][dim]
+ *   gathered_scales dev [world, num_tables];  scale_mean dev [num_tables] out
+ */
+DQRM_API size_t dqrm_slot_bytes(int num_tables, int64_t capacity, int dim, int bits);
+DQRM_API int dqrm_slot_layout(int num_tables, int64_t capacity, int dim, int bits,
+                     size_t* rows_offset, size_t* codes_offset);
+DQRM_API int dqrm_grad_pack(int num_tables, int dim, const float* grad_sums, const int32_t* uniq_rows,
+                   const int32_t* uniq_count, int64_t capacity,
+                   const float* gathered_scales, int world, int bits,
+                   void* slot, float* scale_mean, void* stream);
+
+/* ------------------------------------------------------------------ (a8) --
+ * Top-k row sparsification of the de-duplicated gradients, in place, between
+ * coalesce and the gradient scale: per table keep the `topk` rows of largest
+ * score ||g_row||^2 / dim (ties: lower row id); survivors stay in ascending row
+ * order, uniq_count becomes min(count, topk), dropped rows are discarded.
+ * north_star extension: the DQRM path itself only has "specified" sparsity
+ * (rows touched by the batch); the only top-k in the reference tree is
+ * training_imagenet_speedup.py:138,149 whose score/selection this follows.
+ * Parity unpinned; topk >= count is the identity =
+ * reference behaviour.  Recompute the scale afterwards with
+ * dqrm_grad_absmax_scale.  Tables with more than DQRM_BWD_CTA_MAX_LOOKUPS
+ * unique rows are rejected (-E2BIG).
+ */
+DQRM_API int dqrm_grad_topk(int num_tables, int dim, float* grad_sums, int32_t* uniq_rows, int32_t* uniq_count,
+                   int64_t capacity, int64_t topk, void* stream);
+
+/* ---------------------------------------------------- (a7 step 5, a9) --
+ * Merge the `world` gathered slots and apply the SGD row update in place:
+ *   for every row in the union of the ranks' row lists
+ *     W[row] += (-lr) * ((float(sum_r q_r[row]) * (1/world)) * s_bar)
+ * (sparse all-reduce + mul_(1./N), sgd...parallel_comm.py:878,885; update
+ *  weight_update_parallel_comm :618,622).  Integer codes of coinciding rows are
+ * summed exactly; each row is updated once.  Every rank runs this on the same
+ * gathered bytes, so replicas stay bit-identical.
+ *   gathered   dev, `world` slots back to back (all-gather output)
+ *   updated_rows  NULL or dev int32 [num_tables, world*capacity]: union rows
+ *                 (unordered); updated_count dev int32 [num_tables] (zeroed by the call)
+ *   qbar       NULL or dev fp32 [num_tables, world*capacity, dim]: (sum q)*(1/world)
+ *              aligned with updated_rows (the reference's .grad values after :885)
+ */
+DQRM_API int dqrm_grad_merge_apply(int num_tables, float* const* weight, const int64_t* rows, int dim,
+                          const void* gathered, int world, int64_t capacity, int bits,
+                          const float* scale_mean, float lr,
+                          int32_t* updated_rows, int32_t* updated_count, float* qbar,
+                          int32_t* status, void* stream);
+
+/* ----------------------------------------------------------------- (a14) --
+ * Dot interaction: T = [x | ly_0 .. ly_{F-1}] per sample ([F+1, dim]),
+ * Z = T T^t, R = [x | strict lower triangle of Z] (with `itself`, the diagonal too).
+ * Replaces DLRM_Net.interact_features (dlrm_s_pytorch_comm_grad.py:701-725).
+ *   ly   dev fp32, element (k,b,d) at ly[k*table_stride + b*bag_stride + d]
+ *   R    dev fp32 [batch, dim + npairs]
+ * Backward: dx, dly from dR (autograd of the same expression).
+ */
+DQRM_API int dqrm_interact_fwd(const float* x, const float* ly, int64_t ly_table_stride, int64_t ly_bag_stride,
+                      int64_t batch, int num_tables, int dim, int itself, float* R, void* stream);
+DQRM_API int dqrm_interact_bwd(const float* x, const float* ly, int64_t ly_table_stride, int64_t ly_bag_stride,
+                      const float* dR, int64_t batch, int num_tables, int dim, int itself,
+                      float* dx, float* dly, int64_t dly_table_stride, int64_t dly_bag_stride, void* stream);
+
+/* ----------------------------------------------------------------- (a15) --
+ * QuantLinear weight/bias fake-quantisation, per output channel:
+ *   s_row = max(max|W_row|,1e-8)/(2^(bits-1)-1); W_int = clamp(rint((1/s_row) W));
+ *   b_int = clamp(rint((1/s_row) b))  -- bias uses the WEIGHT's scale and bits
+ * (quant_modules_not_quantize_grad.py:125-154, quant_utils.py:196-220).
+ */
+DQRM_API int dqrm_linear_fakequant(const float* W, const float* b, int out_features, int in_features, int bits,
+                          float* W_int, float* b_int, float* scale_row, void* stream);
+
+/* ------------------------------------------------------------------ (a4) --
+ * Stand-alone SymmetricQuantFunction.forward on a [rows, cols] fp32 matrix
+ * (quant_utils.py:322-346): q = clamp(rint((1/s) * x), -2^(bits-1), 2^(bits-1)-1),
+ * integer-valued fp32.  scale is dev [1] (scale_per_row = 0) or dev [rows]
+ * (scale.view(-1,1), quant_utils.py:90-93).  `dequant` != NULL also writes q * s.
+ */
+DQRM_API int dqrm_fake_quant(const float* x, int64_t rows, int64_t cols, const float* scale, int scale_per_row,
+                             int bits, float* q, float* dequant, void* stream);
+
+/* ----------------------------------------------------------------- (a11) --
+ * 8-bit per-channel quantised exchange of dense (MLP) gradients laid out in one
+ * flat fp32 arena split into `num_chan` channels [chan_begin[c], chan_begin[c+1])
+ * (a weight row is a channel; a whole bias vector is one channel):
+ *   dqrm_dense_grad_scale : s_local[c] = max(max|g_c|,1e-8)/(2^(bits-1)-1)
+ *        (quantize_linear_grad / quantize_bias_grad, sgd...parallel_comm.py:905-910, 945-947)
+ *   dqrm_dense_grad_quant : s_bar = scale_sum * inv_world ; q = clamp(rint((1/s_bar) g))   (:912-919)
+ *   dqrm_dense_apply      : p += ((-lr) * (code_sum * inv_world)) * s_bar
+ *        (weight_update_parallel_comm :642-643 -- note the association differs from (a9))
+ * chan_begin is dev int64 [num_chan+1]; codes are integer-valued fp32 so one
+ * SUM all-reduce between quant and apply adds them exactly.
+ */
+DQRM_API int dqrm_dense_grad_scale(const float* grad, const int64_t* chan_begin, int num_chan, int bits,
+                          float* scale_local, void* stream);
+DQRM_API int dqrm_dense_grad_quant(const float* grad, const int64_t* chan_begin, int num_chan,
+                          const float* scale_sum, float inv_world, int bits,
+                          float* codes, float* scale_mean, void* stream);
+DQRM_API int dqrm_dense_apply(float* param, const float* code_sum, const int64_t* chan_begin, int num_chan,
+                     const float* scale_mean, float inv_world, float lr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQRM_B200_H */

@@ -1,0 +1,369 @@
+"""GPU parity: the CUDA path (through the C ABI, via the reference-shaped Python surface) against the
+oracle on identical seeded inputs, and against the golden vectors produced by the reference.
+
+Bars (north_star): INT4/INT8 codes, scales, de-duplicated row sets and updated-row sets bit-exact;
+pooled fp32 outputs and updated weights within 1e-5 relative (they are in fact bit-exact against the
+oracle's explicit-order spec, which is asserted where the order is a contract)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import dqrm_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _mods():
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib, synthetic, tables
+    from deep_quantized_recommendation_model_dqrm_b200.quantization_supp import quant_modules as qm
+    from deep_quantized_recommendation_model_dqrm_b200.quantization_supp import quant_utils as qu
+    return _lib, synthetic, tables, qm, qu
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    b = np.ascontiguousarray(np.asarray(b, dtype=np.float32))
+    return a.shape == b.shape and a.tobytes() == b.tobytes()
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------ (a1)
+@pytest.mark.parametrize("rows,dim", [(3, 16), (1000, 16), (4097, 16), (100003, 16), (257, 64), (70001, 128), (5, 20)])
+def test_table_scale_bit_exact(rows, dim):
+    _lib, synthetic, tables, qm, qu = _mods()
+    rng = np.random.RandomState(rows)
+    W = synthetic.table_weights_numpy(rows, dim, rng)
+    W[rng.randint(rows), rng.randint(dim)] *= -3.0           # a negative extreme decides the scale
+    Wd = torch.tensor(W, device="cuda")
+    for bits in (4, 8):
+        s = qu.symmetric_linear_quantization_param_two(bits, Wd, None, None, None)
+        assert s.dim() == 0 and s.is_cuda
+        assert bits_equal(cpu(s), O.table_scale_spec(W, bits))
+
+
+def test_table_scale_many_tables_one_launch_and_sharded():
+    _lib, synthetic, tables, qm, qu = _mods()
+    rows = [1460, 583, 101227, 22608, 305, 24, 12517, 633, 3, 93145, 5683, 83593, 3194, 27]
+    rng = np.random.RandomState(1)
+    Ws = [synthetic.table_weights_numpy(n, 16, rng) for n in rows]
+    g = tables.EmbeddingTableGroup([torch.tensor(w, device="cuda") for w in Ws], embedding_bit=4)
+    for _ in range(2):                                        # second launch checks the workspace reset
+        g.scan_scales()
+        want = np.array([O.table_scale_spec(w, 4) for w in Ws], dtype=np.float32)
+        assert bits_equal(cpu(g.scale), want)
+        assert bits_equal(cpu(g.inv_scale), (np.float32(1.0) / want).astype(np.float32))
+    full = cpu(g.absmax).copy()
+    for world in (2, 3, 8):                                   # row-sharded scan: max over shards == full scan
+        acc = np.zeros_like(full)
+        for r in range(world):
+            rc = g.lib.dqrm_table_absmax_scale(g.T, g._wptrs(), g._rows_arr, g.dim, 4, r, world, g.absmax.data_ptr(),
+                                               None, None, g._scan_ws.data_ptr(), _lib.stream_ptr())
+            assert rc == 0
+            acc = np.maximum(acc, cpu(g.absmax))
+        assert bits_equal(acc, full)
+
+
+# ------------------------------------------------------------------------------------ (a3), (a4), (a5)
+EMB_CASES = ["emb_multihot_d16", "emb_multihot_d64_b8", "emb_onehot_zipf_d16", "emb_onehot_tiny_d16", "emb_ragged_d16"]
+
+
+@pytest.mark.parametrize("name", EMB_CASES)
+def test_emb_module_forward_backward_vs_golden_and_oracle(name):
+    _lib, synthetic, tables, qm, qu = _mods()
+    g = load_golden(name)
+    bits = int(g["bits"])
+    E = qm.QuantEmbeddingBagTwo(int(g["rows"]), int(g["dim"]), bits, embedding_id=0,
+                                _weight=torch.tensor(g["W"], device="cuda"))
+    idx, off = torch.tensor(g["idx"], device="cuda"), torch.tensor(g["off"], device="cuda")
+    out = E(idx, off)
+    # reference-produced vectors: scale + codes bit-exact, output 1e-5
+    assert bits_equal(cpu(E.eb_scaling_factor), g["scale"])
+    assert np.array_equal(cpu(E.output_integer), g["codes"])
+    np.testing.assert_allclose(cpu(out), g["out"], rtol=RTOL, atol=0)
+    # oracle spec: everything bit-exact
+    s, codes, want = O.embbag_forward_spec(g["W"], g["idx"], g["off"], bits)
+    assert bits_equal(cpu(out), want)
+    out.backward(torch.tensor(g["dout"], device="cuda"))
+    grp = E._group
+    grp.check_status()
+    sp = grp.sparse_grad(0)
+    rows = cpu(sp._indices()[0])
+    assert np.array_equal(rows, g["co_rows"])                                  # de-duplicated row set
+    np.testing.assert_allclose(cpu(sp._values()), g["co_vals"], rtol=RTOL, atol=1e-5 * np.abs(g["dout"]).max())
+    r0, v0 = O.embbag_backward_spec(g["dout"], g["idx"], g["off"], g["scale"])
+    urows, sums = O.coalesce_spec(r0, v0)
+    assert np.array_equal(rows, urows) and bits_equal(cpu(sp._values()), sums)   # original-order left fold
+    assert bits_equal(cpu(grp.grad_scale_local[0]), O.grad_scale_spec(sums, 8))
+    # full-precision branch (qm:395)
+    pooled = E(idx, off, full_precision_flag=True)
+    assert bits_equal(cpu(pooled), O.pool_sum_spec(g["W"], g["idx"], g["off"]))
+    np.testing.assert_allclose(cpu(pooled), g["pooled"], rtol=RTOL, atol=1e-9)
+
+
+def _c1_group(B=128, P=10, seed=7, dim=16, rows=None, bits=4):
+    _lib, synthetic, tables, qm, qu = _mods()
+    rows = rows or [10000] * 8
+    rng = np.random.RandomState(seed)
+    Ws = [synthetic.table_weights_numpy(n, dim, rng) for n in rows]
+    X, lS_o, lS_i, T = synthetic.random_batch(rows, B, P, seed=seed + 1)
+    g = tables.EmbeddingTableGroup([torch.tensor(w, device="cuda") for w in Ws], embedding_bit=bits)
+    idx, off, idx_begin, bags = tables.EmbeddingTableGroup.pack_inputs(lS_i, lS_o, "cuda")
+    return g, Ws, lS_i, lS_o, (idx, off, idx_begin, bags), rng
+
+
+@pytest.mark.parametrize("dim,P", [(16, 10), (64, 4), (128, 3), (32, 1)])
+def test_group_fwd_bwd_exchange_update_world1(dim, P):
+    """Config C1 shape: 8 tables x 10k rows, multi-hot bags; the whole (a1..a9) chain for one rank."""
+    g, Ws, lS_i, lS_o, (idx, off, idx_begin, bags), rng = _c1_group(P=P, dim=dim)
+    g.scan_scales()
+    out = g.forward(idx, off, idx_begin, bags)
+    dout = rng.randn(g.T, bags, dim).astype(np.float32)
+    g.backward(torch.tensor(dout, device="cuda"), world=1)
+    g.keep_debug = True
+    g.exchange(world=1, rank=0)
+    g.merge_apply(0.1)
+    g.check_status()
+    cnt, srows, scodes = g.slot_views(0)
+    for t in range(g.T):
+        i_t, o_t = lS_i[t].numpy(), lS_o[t].numpy()
+        s, codes, want = O.embbag_forward_spec(Ws[t], i_t, o_t, 4)
+        assert bits_equal(cpu(g.scale[t]), s) and bits_equal(cpu(out[t]), want)
+        assert np.array_equal(cpu(g.codes[t]).astype(np.float32), codes)
+        r0, v0 = O.embbag_backward_spec(dout[t], i_t, o_t, s)
+        urows, sums = O.coalesce_spec(r0, v0)
+        ex = O.exchange_emb_grad_spec([(urows, sums)], 8, Ws[t].shape[0])
+        U = int(cnt[t])
+        assert U == len(urows) and np.array_equal(cpu(srows[t, :U]), urows)
+        assert bits_equal(cpu(g.grad_scale_mean[t]), ex["s_bar"])
+        assert np.array_equal(cpu(scodes[t, :U]).astype(np.float32), ex["codes"][0])          # INT8 codes
+        Wn = Ws[t].copy()
+        O.weight_update_emb_spec(Wn, ex["union_rows"], ex["qbar"], ex["s_bar"], 0.1)
+        assert bits_equal(cpu(g.weights[t]), Wn)                                             # updated table
+        nu = int(g.updated_count[t])
+        order = np.argsort(cpu(g.updated_rows[t, :nu]))
+        assert np.array_equal(cpu(g.updated_rows[t, :nu])[order], ex["union_rows"])           # updated-row set
+        assert bits_equal(cpu(g.qbar[t, :nu])[order], ex["qbar"])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_exchange_emulated_ranks(world):
+    """N ranks' slots merged on one GPU (each 'rank' is a replica group over its own copy of the tables)."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    rows = [50, 3, 1000, 20000]
+    dim, B = 16, 64
+    rng = np.random.RandomState(world)
+    Ws = [synthetic.table_weights_numpy(n, dim, rng) for n in rows]
+    groups, per_rank = [], []
+    for r in range(world):
+        g = tables.EmbeddingTableGroup([torch.tensor(w, device="cuda") for w in Ws], embedding_bit=4)
+        X, lS_o, lS_i, T = synthetic.criteo_batch(rows, B, seed=50 + r, zipf=1.2 if r % 2 else None)
+        idx, off, idx_begin, bags = tables.EmbeddingTableGroup.pack_inputs(lS_i, lS_o, "cuda")
+        g.scan_scales()
+        g.forward(idx, off, idx_begin, bags)
+        dout = (rng.randn(g.T, bags, dim) * 0.01).astype(np.float32)
+        g.backward(torch.tensor(dout, device="cuda"), world=world)
+        g.keep_debug = True
+        groups.append(g)
+        per_rank.append((lS_i.numpy(), lS_o.numpy(), dout))
+    for r, g in enumerate(groups):
+        g.stage_scale(r)
+    allsc = torch.stack([g.grad_scale_local for g in groups])
+    for g in groups:
+        g.gathered_scales.copy_(allsc)
+    for r, g in enumerate(groups):
+        g.pack(r)
+    sb = groups[0].slot_bytes
+    for g in groups:
+        for r2, g2 in enumerate(groups):
+            if g2 is not g:
+                g.gathered[r2 * sb:(r2 + 1) * sb].copy_(g2.gathered[r2 * sb:(r2 + 1) * sb])
+    for g in groups:
+        g.merge_apply(0.1)
+        g.check_status()
+    for t in range(len(rows)):
+        s = O.table_scale_spec(Ws[t], 4)
+        pr = []
+        for (li, lo, dout) in per_rank:
+            r0, v0 = O.embbag_backward_spec(dout[t], li[t], lo[t], s)
+            pr.append(O.coalesce_spec(r0, v0))
+        ex = O.exchange_emb_grad_spec(pr, 8, rows[t])
+        Wn = Ws[t].copy()
+        O.weight_update_emb_spec(Wn, ex["union_rows"], ex["qbar"], ex["s_bar"], 0.1)
+        for r, g in enumerate(groups):
+            assert bits_equal(cpu(g.grad_scale_mean[t]), ex["s_bar"])
+            cnt, srows, scodes = g.slot_views(r)
+            U = int(cnt[t])
+            assert np.array_equal(cpu(srows[t, :U]), pr[r][0])
+            assert np.array_equal(cpu(scodes[t, :U]).astype(np.float32), ex["codes"][r])
+            nu = int(g.updated_count[t])
+            order = np.argsort(cpu(g.updated_rows[t, :nu]))
+            assert np.array_equal(cpu(g.updated_rows[t, :nu])[order], ex["union_rows"])
+            assert bits_equal(cpu(g.qbar[t, :nu])[order], ex["qbar"])
+            assert bits_equal(cpu(g.weights[t]), Wn)                    # replicas bit-identical to the oracle
+
+
+def test_large_table_path_matches_oracle():
+    """> DQRM_BWD_CTA_MAX_LOOKUPS lookups on one table: multi-block radix-sort path."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    rows, dim, B, P = 5000, 16, 4096, 8
+    rng = np.random.RandomState(3)
+    W = synthetic.table_weights_numpy(rows, dim, rng)
+    idx, off = synthetic.random_bags(rows, B, P, rng, fixed=True)
+    assert idx.numel() > _lib.BWD_CTA_MAX_LOOKUPS
+    g = tables.EmbeddingTableGroup([torch.tensor(W, device="cuda")], embedding_bit=4)
+    i2, o2, ib, bags = tables.EmbeddingTableGroup.pack_inputs([idx], [off], "cuda")
+    g.scan_scales()
+    out = g.forward(i2, o2, ib, bags)
+    s, codes, want = O.embbag_forward_spec(W, idx.numpy(), off.numpy(), 4)
+    assert bits_equal(cpu(out[0]), want)
+    dout = rng.randn(1, bags, dim).astype(np.float32)
+    g.backward(torch.tensor(dout, device="cuda"), world=1)
+    g.check_status()
+    sp = g.sparse_grad(0)
+    r0, v0 = O.embbag_backward_spec(dout[0], idx.numpy(), off.numpy(), s)
+    urows, sums = O.coalesce_spec(r0, v0)
+    assert np.array_equal(cpu(sp._indices()[0]), urows)
+    assert bits_equal(cpu(sp._values()), sums)
+    assert bits_equal(cpu(g.grad_scale_local[0]), O.grad_scale_spec(sums, 8))
+
+
+def test_max_cta_lookups_boundary():
+    """Exactly DQRM_BWD_CTA_MAX_LOOKUPS lookups (largest single-CTA sort) with heavy duplication."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    rows, dim, B = 300, 16, _lib.BWD_CTA_MAX_LOOKUPS
+    rng = np.random.RandomState(4)
+    W = synthetic.table_weights_numpy(rows, dim, rng)
+    idx = torch.from_numpy(np.minimum(rng.zipf(1.1, size=B) - 1, rows - 1).astype(np.int64))
+    off = torch.arange(B, dtype=torch.int64)
+    g = tables.EmbeddingTableGroup([torch.tensor(W, device="cuda")], embedding_bit=4)
+    i2, o2, ib, bags = tables.EmbeddingTableGroup.pack_inputs([idx], [off], "cuda")
+    g.scan_scales()
+    g.forward(i2, o2, ib, bags)
+    dout = rng.randn(1, bags, dim).astype(np.float32)
+    g.backward(torch.tensor(dout, device="cuda"), world=1)
+    g.check_status()
+    sp = g.sparse_grad(0)
+    r0, v0 = O.embbag_backward_spec(dout[0], idx.numpy(), off.numpy(), O.table_scale_spec(W, 4))
+    urows, sums = O.coalesce_spec(r0, v0)
+    assert np.array_equal(cpu(sp._indices()[0]), urows) and bits_equal(cpu(sp._values()), sums)
+
+
+def test_out_of_range_index_is_flagged():
+    _lib, synthetic, tables, qm, qu = _mods()
+    E = qm.QuantEmbeddingBagTwo(10, 16, 4, _weight=torch.zeros(10, 16, device="cuda"))
+    E(torch.tensor([1, 10, 2], device="cuda"), torch.tensor([0, 1, 2], device="cuda"))
+    with pytest.raises(IndexError):
+        E._group.check_status()
+    E._group.check_status()        # flag is cleared after being reported
+
+
+# ------------------------------------------------------------------------------------------ (a8)
+def test_topk_rows():
+    g, Ws, lS_i, lS_o, (idx, off, idx_begin, bags), rng = _c1_group(B=256, P=1, seed=11)
+    g.scan_scales()
+    g.forward(idx, off, idx_begin, bags)
+    dout = rng.randn(g.T, bags, 16).astype(np.float32)
+    g.backward(torch.tensor(dout, device="cuda"), world=1)
+    before = [(cpu(g.uniq_rows[t, :int(g.uniq_count[t])]).copy(), cpu(g.grad_sums[t, :int(g.uniq_count[t])]).copy())
+              for t in range(g.T)]
+    k = 50
+    g.topk(k)
+    for t in range(g.T):
+        rows, sums, _ = O.topk_rows_spec(before[t][0], before[t][1], k)
+        U = int(g.uniq_count[t])
+        assert U == min(k, len(before[t][0]))
+        assert np.array_equal(cpu(g.uniq_rows[t, :U]), rows)
+        assert bits_equal(cpu(g.grad_sums[t, :U]), sums)
+        assert bits_equal(cpu(g.grad_scale_local[t]), O.grad_scale_spec(sums, 8))
+    g.topk(10 ** 6)                                    # k >= count: identity
+    assert int(g.uniq_count[0]) == min(k, len(before[0][0]))
+
+
+# ----------------------------------------------------------------------------------------- (a10)
+def test_sgd_rows_and_rwsadagrad():
+    g, Ws, lS_i, lS_o, (idx, off, idx_begin, bags), rng = _c1_group(B=64, P=3, seed=13)
+    g.scan_scales()
+    g.forward(idx, off, idx_begin, bags)
+    dout = rng.randn(g.T, bags, 16).astype(np.float32)
+    g.backward(torch.tensor(dout, device="cuda"), world=1)
+    sums = [(cpu(g.uniq_rows[t, :int(g.uniq_count[t])]).astype(np.int64), cpu(g.grad_sums[t, :int(g.uniq_count[t])]).copy())
+            for t in range(g.T)]
+    g.sgd_apply(0.1)
+    for t in range(g.T):
+        Wn = Ws[t].copy()
+        O.weight_update_emb_unquantized_spec(Wn, sums[t][0], sums[t][1], 0.1)
+        assert bits_equal(cpu(g.weights[t]), Wn)
+    # row-wise sparse Adagrad (optim/rwsadagrad.py:97-113) against the same formula in torch
+    mom = [torch.zeros(w.shape[0], device="cuda") for w in g.weights]
+    W0 = [cpu(w).copy() for w in g.weights]
+    g.sgd_apply(0.05, momentum=mom, eps=1e-10)
+    for t in range(g.T):
+        r, v = sums[t]
+        m = np.zeros(W0[t].shape[0], dtype=np.float32)
+        m[r] += (v ** 2).mean(axis=1)
+        Wn = W0[t].copy()
+        Wn[r] += -0.05 * (v / (np.sqrt(m[r]) + 1e-10)[:, None])
+        np.testing.assert_allclose(cpu(mom[t]), m, rtol=1e-5, atol=1e-12)
+        np.testing.assert_allclose(cpu(g.weights[t]), Wn, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------ (a14)
+@pytest.mark.parametrize("name", ["interact_kaggle", "interact_tb", "interact_small"])
+def test_interact_vs_golden(name):
+    from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
+    g = load_golden(name)
+    x = torch.tensor(g["x"], device="cuda", requires_grad=True)
+    ly = torch.tensor(g["ly"], device="cuda", requires_grad=True)          # [T, B, D]
+    m = drv.DLRM_Net()
+    m.arch_interaction_op, m.arch_interaction_itself, m.quantization_flag, m.quantize_activation = "dot", False, True, False
+    R, none = m.interact_features(x, list(ly.unbind(0)))
+    assert none is None
+    np.testing.assert_allclose(cpu(R), g["R"], rtol=RTOL, atol=1e-5)
+    R.backward(torch.tensor(g["dR"], device="cuda"))
+    np.testing.assert_allclose(cpu(x.grad), g["dx"], rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(cpu(ly.grad), g["dly"], rtol=RTOL, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ (a15)
+@pytest.mark.parametrize("name", ["linear_13_64", "linear_367_32", "linear_64_1"])
+def test_quant_linear_vs_golden(name):
+    _lib, synthetic, tables, qm, qu = _mods()
+    g = load_golden(name)
+    LL = torch.nn.Linear(g["W"].shape[1], g["W"].shape[0])
+    LL.weight.data, LL.bias.data = torch.tensor(g["W"]), torch.tensor(g["b"])
+    Q = qm.QuantLinear(weight_bit=int(g["bits"]), bias_bit=int(g["bits"]), per_channel=True)
+    Q.set_param(LL)
+    Q = Q.cuda()
+    x = torch.tensor(g["x"], device="cuda", requires_grad=True)
+    y, none = Q(x)
+    assert none is None
+    assert bits_equal(cpu(Q.fc_scaling_factor), g["scale"])
+    assert np.array_equal(cpu(Q.weight_integer), g["W_int"]) and np.array_equal(cpu(Q.bias_integer), g["b_int"])
+    np.testing.assert_allclose(cpu(y), g["y"], rtol=RTOL, atol=1e-5)
+    y.backward(torch.tensor(g["dy"], device="cuda"))
+    np.testing.assert_allclose(cpu(x.grad), g["dx"], rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(cpu(Q.weight.grad), g["dW"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(cpu(Q.bias.grad), g["db"], rtol=1e-4, atol=1e-4)
+
+
+def test_symmetric_quant_function_api():
+    _lib, synthetic, tables, qm, qu = _mods()
+    rng = np.random.RandomState(0)
+    x = rng.randn(37, 16).astype(np.float32)
+    s = np.float32(0.05)
+    xd = torch.tensor(x, device="cuda", requires_grad=True)
+    sd = torch.tensor(s, device="cuda")
+    q = qu.SymmetricQuantFunction.apply(xd, 4, sd)
+    assert np.array_equal(cpu(q), O.quantize_spec(x, 4, s))
+    q.sum().backward()
+    assert bits_equal(cpu(xd.grad), (np.ones_like(x) / s).astype(np.float32))
+    srow = np.abs(rng.randn(37)).astype(np.float32) + 0.01
+    q = qu.SymmetricQuantFunction.apply(xd, 8, torch.tensor(srow, device="cuda"))
+    assert np.array_equal(cpu(q), O.quantize_spec(x, 8, srow))
+    with pytest.raises(ValueError):
+        qu.SymmetricQuantFunction.apply(xd, 4, None)
