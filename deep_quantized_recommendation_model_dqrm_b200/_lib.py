@@ -49,9 +49,40 @@ SIGNATURES = {
 
 _lib = None
 
+# entry points that enqueue at least one of OUR kernels per call (bench.py's gpu_launches claim)
+LAUNCHING = ("dqrm_table_absmax_scale", "dqrm_scale_from_absmax", "dqrm_embbag_fwd", "dqrm_embbag_bwd",
+             "dqrm_grad_absmax_scale", "dqrm_sgd_rows", "dqrm_grad_pack", "dqrm_grad_topk", "dqrm_grad_merge_apply",
+             "dqrm_interact_fwd", "dqrm_interact_bwd", "dqrm_linear_fakequant", "dqrm_fake_quant",
+             "dqrm_dense_grad_scale", "dqrm_dense_grad_quant", "dqrm_dense_apply")
+launch_counts = {}
+
 
 class DqrmLibraryError(RuntimeError):
     pass
+
+
+class _Counted:
+    """The CDLL with every kernel-launching entry point wrapped by a call counter."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        for name in SIGNATURES:
+            fn = getattr(lib, name)
+            if name in LAUNCHING:
+                launch_counts[name] = 0
+                fn = self._wrap(name, fn)
+            setattr(self, name, fn)
+
+    @staticmethod
+    def _wrap(name, fn):
+        def call(*a):
+            launch_counts[name] += 1
+            return fn(*a)
+        return call
+
+
+def total_launches() -> int:
+    return sum(launch_counts.values())
 
 
 def load():
@@ -69,8 +100,8 @@ def load():
         fn.restype, fn.argtypes = res, args
     if lib.dqrm_abi_version() != 1:
         raise DqrmLibraryError(f"{LIB_PATH}: ABI version {lib.dqrm_abi_version()} != 1 (stale build)")
-    _lib = lib
-    return lib
+    _lib = _Counted(lib)
+    return _lib
 
 
 def last_error() -> str:

@@ -59,6 +59,7 @@ class EmbeddingTableGroup:
         self.updated_rows = self.updated_count = self.qbar = None
         self._bwd_ws = None
         self.last = None          # (indices, offsets, idx_begin, idx_begin_arr, bags, full_precision)
+        self.fixed_capacity = None  # rows per table in the exchange slots (default: this step's largest table)
         self.keep_debug = False   # also emit updated_rows / qbar in merge (parity tests, .grad materialisation)
 
     # ---- helpers --------------------------------------------------------
@@ -168,6 +169,12 @@ class EmbeddingTableGroup:
         indices, offsets, idx_begin, ib, bags, full_precision = last if last is not None else self.last
         cap = max(idx_begin[k + 1] - idx_begin[k] for k in range(self.T))
         cap = max(cap, 1)
+        if self.fixed_capacity is not None:
+            # all ranks must agree on the slot capacity; with one index per bag (Criteo) it is simply the
+            # local batch, with ragged multi-hot bags the caller fixes a common upper bound
+            if cap > self.fixed_capacity:
+                raise _lib.DqrmLibraryError(f"{cap} lookups on one table exceed fixed_capacity={self.fixed_capacity}")
+            cap = self.fixed_capacity
         self._ensure_step_buffers(cap, world)
         rc = lib.dqrm_embbag_bwd(self.T, self._rows_arr, self.dim, indices.data_ptr(), offsets.data_ptr(), ib, bags,
                                  dout.data_ptr(), dout.stride(0), dout.stride(1),

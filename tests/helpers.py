@@ -66,9 +66,13 @@ def emulated_dp_step(models, batches, lr, device="cuda", keep_debug=True):
     """One iteration of the custom-DP loop over `len(models)` replicas living on ONE GPU."""
     world = len(models)
     losses = []
+    cap = 1                       # common slot capacity: the largest per-table lookup count of any rank
+    for (_, _, lS_i, _) in batches:
+        cap = max(cap, max(int(t.shape[0]) for t in lS_i) if not torch.is_tensor(lS_i) else int(lS_i.shape[1]))
     for r, (m, (X, lS_o, lS_i, T)) in enumerate(zip(models, batches)):
         g = m._ensure_group()
         g.dp_world, g.dp_rank = world, r
+        g.fixed_capacity = cap
         g.keep_debug = keep_debug
         Z = drv.dlrm_wrap(m, X, lS_o, lS_i, True, device)
         E = drv.loss_fn_wrap(Z, T, True, device)
