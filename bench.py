@@ -231,9 +231,7 @@ def run_ours(args):
         e0.record()
         for i in range(K):
             step.load(*src[(W + i) % pool])
-            ev_scan[i][0].record()
-            step.scan()
-            ev_scan[i][1].record()
+            step.scan(events=ev_scan[i])
             if step.graph is not None:
                 step.graph.replay()
             else:
@@ -271,6 +269,7 @@ def run_ours(args):
     algo_bytes = table_bytes / world if dlrm.shard_scan else table_bytes
     achieved = algo_bytes / (scan_ms / 1000.0) / 1e9
     if rank != 0:
+        dist.destroy_process_group()
         return
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -288,7 +287,8 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"kernel": "table_absmax_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_SCAN_TRAFFIC.get((args.workload, world)),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": scan_ms,
                      "share_of_step": scan_ms / (ms_dev / args.steps)},
@@ -303,6 +303,13 @@ def run_ours(args):
                                 "sample": f"{args.cpu_steps} full train steps after 1 warm-up, batch {B}, same "
                                           f"{args.workload}-shape model on the host ({build_s:.0f}s to build tables)"}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# DRAM traffic of one table_absmax_kernel launch from `ncu --set full` (dram__bytes_read.sum +
+# dram__bytes_write.sum, profiles/r01_scan_kernel_ncu_full.txt); valid for the full (unsharded) Kaggle scan.
+NCU_SCAN_TRAFFIC = {("kaggle", 1): 2.1647e9 + 3.9e6}
 
 
 def main():

@@ -45,11 +45,12 @@ class GraphedTrainStep:
                 self._body()
             torch.cuda.synchronize()
 
-    def scan(self):
+    def scan(self, events=None):
         """(a1) one launch for all tables; with world > 1 each rank scans 1/world of the rows."""
         g = self.group
         sharded = self.world > 1 and self.dlrm.shard_scan
-        g.scan_scales(shard_rank=self.rank if sharded else 0, shard_world=self.world if sharded else 1)
+        g.scan_scales(shard_rank=self.rank if sharded else 0, shard_world=self.world if sharded else 1,
+                      events=events)
 
     def _body(self):
         d = self.dlrm

@@ -102,17 +102,21 @@ class EmbeddingTableGroup:
         return idx, off, idx_begin, int(off.shape[1])
 
     # ---- (a1) -----------------------------------------------------------
-    def scan_scales(self, shard_rank=0, shard_world=1, process_group=None):
+    def scan_scales(self, shard_rank=0, shard_world=1, process_group=None, events=None):
         """Recompute every table's scale from a full max-abs pass (one launch).
         With shard_world > 1 each rank scans 1/world of the rows and the maxima
         are combined with a MAX all-reduce (replicas are bit-identical)."""
         lib, st = self.lib, _lib.stream_ptr()
         sharded = shard_world > 1
+        if events is not None:            # (start, end) CUDA events bracketing exactly the scan kernel
+            events[0].record()
         rc = lib.dqrm_table_absmax_scale(self.T, self._wptrs(), self._rows_arr, self.dim, self.embedding_bit,
                                          shard_rank, shard_world, self.absmax.data_ptr(),
                                          None if sharded else self.scale.data_ptr(),
                                          None if sharded else self.inv_scale.data_ptr(),
                                          self._scan_ws.data_ptr(), st)
+        if events is not None:
+            events[1].record()
         _lib.check(rc, "dqrm_table_absmax_scale")
         if sharded:
             import torch.distributed as dist

@@ -1,0 +1,150 @@
+"""CPU (no GPU): the C-ABI library loads and exports every symbol include/dqrm_b200.h declares, argument
+validation works without a device, host-side logic (input packing, shard, arena channel table, flag
+parsing), and the world_size-2 gloo path of extend_distributed / weight_syncc."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dqrm_b200.h")).read()
+    declared = set(re.findall(r"DQRM_API\s+[\w\s\*]+?\b(dqrm_\w+)\s*\(", hdr))
+    assert len(declared) >= 22
+    lib = _lib.load()
+    import ctypes
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+        assert name in _lib.SIGNATURES, f"{name} declared in the header but not bound in _lib.SIGNATURES"
+    assert set(_lib.SIGNATURES) == declared
+    assert lib.dqrm_abi_version() == 1
+
+
+def test_argument_validation_without_a_device():
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    lib = _lib.load()
+    assert lib.dqrm_scan_workspace_bytes(26) == 27 * 4
+    assert lib.dqrm_slot_bytes(26, 128, 16, 8) == 112 + 26 * 128 * 4 + 26 * 128 * 16
+    assert lib.dqrm_slot_bytes(26, 128, 16, 16) == 112 + 26 * 128 * 4 + 26 * 128 * 16 * 2
+    assert lib.dqrm_bwd_workspace_bytes(26, 128, 16) == 0
+    assert lib.dqrm_bwd_workspace_bytes(1, 1 << 20, 16) > 4 * (1 << 20) * 4
+    # errors are returned, not thrown, and carry a message (no kernel is launched on these paths)
+    rc = lib.dqrm_table_absmax_scale(0, None, None, 16, 4, 0, 1, None, None, None, None, None)
+    assert rc < 0 and "num_tables" in _lib.last_error()
+    rc = lib.dqrm_embbag_fwd(1, None, None, 18, None, None, None, 4, None, None, 4, None, 0, 0, None, None, None)
+    assert rc < 0
+    rc = lib.dqrm_scale_from_absmax(1, 1, 40, 1, None, None)
+    assert rc == -22 and "bits" in _lib.last_error()
+    with pytest.raises(_lib.DqrmLibraryError):
+        _lib.check(rc, "dqrm_scale_from_absmax")
+
+
+def test_no_cpu_fallback():
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    from deep_quantized_recommendation_model_dqrm_b200.quantization_supp import quant_modules as qm
+    from deep_quantized_recommendation_model_dqrm_b200.quantization_supp import quant_utils as qu
+    E = qm.QuantEmbeddingBagTwo(10, 16, 4)
+    with pytest.raises(_lib.DqrmLibraryError):
+        E(torch.tensor([1, 2]), torch.tensor([0, 1]))
+    with pytest.raises(_lib.DqrmLibraryError):
+        qu.symmetric_linear_quantization_param_two(4, torch.zeros(4, 16), None, None, None)
+    # nothing in the product package imports the oracle
+    pkg = os.path.join(ROOT, "deep_quantized_recommendation_model_dqrm_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_pack_inputs_and_shard():
+    from deep_quantized_recommendation_model_dqrm_b200 import synthetic
+    from deep_quantized_recommendation_model_dqrm_b200.tables import EmbeddingTableGroup
+    from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
+    X, lS_o, lS_i, T = synthetic.criteo_batch([10, 20, 30], 8, seed=1)
+    idx, off, ib, bags = EmbeddingTableGroup.pack_inputs(lS_i, lS_o, "cpu")
+    assert bags == 8 and ib == [0, 8, 16, 24] and idx.numel() == 24 and off.shape == (3, 8)
+    X, lS_o, lS_i, T = synthetic.random_batch([10, 20, 30], 5, 4, seed=2)
+    idx, off, ib, bags = EmbeddingTableGroup.pack_inputs(lS_i, lS_o, "cpu")
+    assert bags == 5 and ib[-1] == sum(t.numel() for t in lS_i) and torch.equal(idx[ib[1]:ib[2]], lS_i[1])
+    for n, w in ((128, 8), (10, 3), (5, 8)):
+        got = []
+        for r in range(w):
+            got += list(range(n))[drv.get_my_slice(n, w, r)]
+        assert got == list(range(n))
+    assert synthetic.top_mlp_sizes(26, 16, [512, 256, 1]) == [367, 512, 256, 1]
+    assert synthetic.top_mlp_sizes(26, 64, [512, 512, 256, 1])[0] == 415
+
+
+def test_flags_match_reference_defaults():
+    from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
+    a = drv.parse_args(["--quantization_flag", "--quantize_act_and_lin", "--embedding_bit=4", "--weight_bit=4",
+                        "--linear_channel", "--quantize_activation", "--quantize_embedding_bag_gradient",
+                        "--embedding_bag_gradient_bit_num=8", "-n", "1", "-g", "4", "-nr", "0"])
+    assert a.quantize_activation is False           # --linear_channel forces it off (drv:1155-1156)
+    assert a.world_size == 4 and a.embedding_bag_gradient_bit_num == 8
+    assert drv.parse_args([]).embedding_bag_gradient_bit_num == 16
+
+
+def test_dense_arena_channel_table_cpu():
+    from deep_quantized_recommendation_model_dqrm_b200.dense import DenseArena
+    from deep_quantized_recommendation_model_dqrm_b200.quantization_supp import quant_modules as qm
+    layers = []
+    for n_in, n_out in ((13, 8), (8, 4)):
+        q = qm.QuantLinear(weight_bit=4, bias_bit=4, per_channel=True)
+        q.set_param(torch.nn.Linear(n_in, n_out))
+        layers.append(q)
+    w0 = layers[0].weight.data.clone()
+    a = DenseArena(layers, torch.device("cpu"))
+    assert a.total == 13 * 8 + 8 + 8 * 4 + 4 and a.num_chan == 8 + 1 + 4 + 1
+    cb = a.chan_begin.tolist()
+    assert cb[:3] == [0, 13, 26] and cb[8] == 104 and cb[9] == 112 and cb[-1] == a.total
+    assert torch.equal(layers[0].weight.data, w0) and a.intact()
+    layers[0].weight.grad.add_(1.0)
+    assert a.flat_grad[:104].eq(1.0).all() and a.flat_grad[104:].eq(0.0).all()
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    sys.path.insert(0, ROOT)
+    from deep_quantized_recommendation_model_dqrm_b200 import extend_distributed as ext
+    from deep_quantized_recommendation_model_dqrm_b200 import sgd_quantized_gradients_parallel_comm as sgd
+    ext.init_distributed(rank=rank, local_rank=rank, size=world, use_gpu=False, backend="gloo")
+    assert ext.my_rank == rank and ext.my_size == world
+    sl = ext.get_my_slice(10)
+    ln, splits = ext.get_split_lengths(7)
+    lin = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        lin.weight.fill_(float(rank + 1))
+        lin.bias.fill_(float(10 * (rank + 1)))
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l = lin
+    m = M()
+    sgd.weight_syncc(m, world)                       # all-reduce-average of every parameter (sgd:963-970)
+    g = ext.all_gather(torch.full((2,), float(rank)), None)
+    ext.barrier()
+    torch.save({"slice": (sl.start, sl.stop), "split": (ln, splits), "w": m.l.weight.data.clone(),
+                "b": m.l.bias.data.clone(), "g": g}, out.format(rank=rank))
+    torch.distributed.destroy_process_group()
+
+
+def test_world2_gloo_host_logic(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r{rank}.pt")
+    mp.spawn(_gloo_worker, args=(2, 29741, out), nprocs=2, join=True)
+    r0, r1 = torch.load(out.format(rank=0)), torch.load(out.format(rank=1))
+    assert r0["slice"] == (0, 5) and r1["slice"] == (5, 10)
+    assert r0["split"] == (4, [4, 3]) and r1["split"] == (3, [4, 3])
+    for r in (r0, r1):
+        assert torch.all(r["w"] == 1.5) and torch.all(r["b"] == 15.0)
+        assert r["g"].tolist() == [0.0, 0.0, 1.0, 1.0]
