@@ -39,8 +39,11 @@ SIGNATURES = {
     "dqrm_grad_topk": (_i32, [_i32, _i32, _p, _p, _p, _i64, _i64, _p]),
     "dqrm_grad_merge_apply": (_i32, [_i32, _p, _p, _i32, _p, _i32, _i64, _i32, _p, _f32, _p, _p, _p, _p, _p]),
     "dqrm_interact_fwd": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p]),
-    "dqrm_interact_bwd": (_i32, [_p, _p, _i64, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _i64, _i64, _p]),
+    "dqrm_interact_bwd": (_i32, [_p, _p, _i64, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _i64, _i64, _p, _p]),
     "dqrm_linear_fakequant": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "dqrm_mlp_fakequant_all": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    "dqrm_linear_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
+    "dqrm_linear_bwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "dqrm_fake_quant": (_i32, [_p, _i64, _i64, _p, _i32, _i32, _p, _p, _p]),
     "dqrm_dense_grad_scale": (_i32, [_p, _p, _i32, _i32, _p, _p]),
     "dqrm_dense_grad_quant": (_i32, [_p, _p, _i32, _p, _f32, _i32, _p, _p, _p]),
@@ -53,6 +56,7 @@ _lib = None
 LAUNCHING = ("dqrm_table_absmax_scale", "dqrm_scale_from_absmax", "dqrm_embbag_fwd", "dqrm_embbag_bwd",
              "dqrm_grad_absmax_scale", "dqrm_sgd_rows", "dqrm_grad_pack", "dqrm_grad_topk", "dqrm_grad_merge_apply",
              "dqrm_interact_fwd", "dqrm_interact_bwd", "dqrm_linear_fakequant", "dqrm_fake_quant",
+             "dqrm_mlp_fakequant_all", "dqrm_linear_fwd", "dqrm_linear_bwd",
              "dqrm_dense_grad_scale", "dqrm_dense_grad_quant", "dqrm_dense_apply")
 launch_counts = {}
 

@@ -1,0 +1,322 @@
+// (a15) fused QuantLinear layers: one fake-quant launch for ALL layers of the model, then one kernel per
+// layer forward and two per layer backward, each with its prologue / epilogue fused:
+//   fwd : out = act((x W_int^t + b_int) * s_row)                       qm:209 + the ReLU / Sigmoid that follows
+//   dx  : dx  = g W_int,      g = dout * act'(out) * s_row             autograd of qm:209
+//   dw  : dW += (g^t x) / s_row ;  db += (sum_b g) / s_row             STE of SymmetricQuantFunction (qu:363)
+// Reference: QuantLinear.forward, quantization_supp/quant_modules_not_quantize_grad.py:105-211.
+//
+// The reference step spends ~95 launches here (per layer: 4 reductions, 6 pointwise, addmm, mul, relu;
+// backward: 3 GEMM/GEMV, 5 pointwise, a column reduction, 2 AccumulateGrad adds).  These layers are tiny
+// (batch 128: 33 MFLOP for the largest, 0.95 MFLOP/sample in total) -- launch latency, not FLOPs, so the
+// win is the launch count: 1 + 7 + 13 launches.  fp32 FFMA on purpose: parity is 1e-5 against an fp32
+// reference (allow_tf32 = False there) and one layer is far below a tcgen05 tile per SM.  No atomics and
+// no split-K: the summation order is fixed, so data-parallel replicas stay bit-identical.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace dqrm {
+
+constexpr int kMaxLayers = 16;
+
+struct MlpLayers {
+  const float* W[kMaxLayers];
+  const float* b[kMaxLayers];
+  float* W_int[kMaxLayers];
+  float* b_int[kMaxLayers];
+  float* s[kMaxLayers];
+  int out_f[kMaxLayers];
+  int in_f[kMaxLayers];
+  int row_begin[kMaxLayers + 1];
+  int num_layers;
+};
+
+// one warp per weight row over all layers
+__global__ void __launch_bounds__(256)
+mlp_fakequant_all_kernel(const __grid_constant__ MlpLayers L, int bits) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= L.row_begin[L.num_layers]) return;
+  int l = 0;
+  while (row >= L.row_begin[l + 1]) ++l;
+  const int r = row - L.row_begin[l];
+  const int in_f = L.in_f[l];
+  const float* w = L.W[l] + (long long)r * in_f;
+  unsigned m = 0u;
+  for (int i = lane; i < in_f; i += 32) m = max(m, abs_bits(w[i]));
+  m = warp_max_u32(m);
+  const float s = scale_of(__uint_as_float(m), bits);
+  const float inv = __fdiv_rn(1.0f, s);
+  const float hi = qmax_of(bits), lo = -hi - 1.0f;
+  float* q = L.W_int[l] + (long long)r * in_f;
+  for (int i = lane; i < in_f; i += 32) q[i] = quant_code(w[i], inv, lo, hi);
+  if (lane == 0) {
+    L.s[l][r] = s;
+    if (L.b[l]) L.b_int[l][r] = quant_code(L.b[l][r], inv, lo, hi);
+  }
+}
+
+enum Act { kActNone = 0, kActRelu = 1, kActSigmoid = 2 };
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == kActRelu) return fmaxf(z, 0.0f);                           // torch.relu == clamp_min(0)
+  if (act == kActSigmoid) return 1.0f / (1.0f + expf(-z));
+  return z;
+}
+__device__ __forceinline__ float act_bwd(float dout, float out, int act) {
+  if (act == kActRelu) return out > 0.0f ? dout : 0.0f;                 // threshold_backward
+  if (act == kActSigmoid) return dout * ((1.0f - out) * out);           // sigmoid_backward
+  return dout;
+}
+
+// Small fp32 GEMM, C[M,N] = sum_k A(m,k) B(k,n):  CTA tile 32 x 64, 128 threads, 4 x 4 outputs per thread.
+// MODE 0 (fwd): A = x[M=batch, K=in] (k contiguous)         B(k,n) = W_int[n][k]
+// MODE 1 (dx) : A(m,k) = g(batch m, out k)                   B(k,n) = W_int[k][n]   (N = in)
+// MODE 2 (dw) : A(m,k) = g(batch k, out m)                   B(k,n) = x[k][n]       (M = out, N = in, K = batch)
+//
+// At batch 128 a layer has only 16-96 output tiles, far fewer than 148 SMs, and its K loop is the whole
+// latency.  So K is split across a THREAD-BLOCK CLUSTER (1,1,S), S <= 8: CTA r of the cluster multiplies
+// its K-slice, parks the partial tile in its shared memory, and after a cluster barrier every CTA sums
+// one row-slice of the tile over ranks 0..S-1 through distributed shared memory -- a fixed order, so the
+// result is deterministic (no atomics, no workspace; replicas stay bit-identical) -- and applies the
+// epilogue for that slice.  Inside a CTA the K loop is a register-prefetch double buffer.
+constexpr int BM = 32, BN = 64, BK = 16, TM = 4, TN = 4, kGemmThreads = 128;
+constexpr int A_PER_THR = BM * BK / kGemmThreads, B_PER_THR = BK * BN / kGemmThreads;    // 4, 8
+constexpr int APAD = BM + 4, BPAD = BN + 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads)
+linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int, const float* __restrict__ b_int,
+                   const float* __restrict__ s_row, const float* __restrict__ dout, const float* __restrict__ out,
+                   float* __restrict__ C, float* __restrict__ db, int batch, int out_f, int in_f, int act, int kc) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  __shared__ __align__(16) float As[2][BK][APAD];
+  __shared__ __align__(16) float Bs[2][BK][BPAD];                       // also the partial tile red[BM][BN]
+  static_assert(2 * BK * BPAD >= BM * BN, "partial tile must fit in Bs");
+  const int M = MODE == 2 ? out_f : batch;
+  const int N = MODE == 0 ? out_f : in_f;
+  const int K = MODE == 0 ? in_f : (MODE == 1 ? out_f : batch);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;                               // thread tile rows ty*4.., cols tx*4..
+  const int kbeg = rank * kc, kend = min(K, kbeg + kc);
+
+  auto g_at = [&](int bi, int oi) -> float {                            // g = dout * act'(out) * s_row
+    const long long e = (long long)bi * out_f + oi;
+    return __fmul_rn(act_bwd(__ldg(dout + e), __ldg(out + e), act), __ldg(s_row + oi));
+  };
+  auto A_at = [&](int m, int k) -> float {
+    if (m >= M || k >= kend) return 0.0f;
+    if (MODE == 0) return __ldg(x + (long long)m * in_f + k);
+    if (MODE == 1) return g_at(m, k);
+    return g_at(k, m);
+  };
+  auto B_at = [&](int k, int n) -> float {
+    if (k >= kend || n >= N) return 0.0f;
+    if (MODE == 0) return __ldg(W_int + (long long)n * in_f + k);
+    if (MODE == 1) return __ldg(W_int + (long long)k * in_f + n);
+    return __ldg(x + (long long)k * in_f + n);
+  };
+  // element -> (row, k) mappings chosen so that consecutive threads read consecutive addresses
+  auto a_coord = [&](int e, int& am, int& ak) {
+    if (MODE == 2) { am = e & (BM - 1); ak = e / BM; }                  // g(k, m): contiguous along m (out)
+    else           { ak = e & (BK - 1); am = e / BK; }                  // contiguous along k
+  };
+  auto b_coord = [&](int e, int& bk, int& bn) {
+    if (MODE == 0) { bk = e & (BK - 1); bn = e / BK; }                  // W_int[n][k]: contiguous along k
+    else           { bn = e & (BN - 1); bk = e / BN; }                  // contiguous along n
+  };
+
+  // MODE 2: the A tiles ARE g, so the bias gradient (column sums of g over the batch) is accumulated for
+  // free from the elements each thread stages; only the first column of tiles needs it
+  const bool do_db = MODE == 2 && db != nullptr && blockIdx.x == 0;
+  float db_part = 0.0f;
+  float a_reg[A_PER_THR], b_reg[B_PER_THR];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_PER_THR; ++i) { int am, ak; a_coord(tid + i * kGemmThreads, am, ak); a_reg[i] = A_at(m0 + am, k0 + ak); }
+#pragma unroll
+    for (int i = 0; i < B_PER_THR; ++i) { int bk, bn; b_coord(tid + i * kGemmThreads, bk, bn); b_reg[i] = B_at(k0 + bk, n0 + bn); }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_PER_THR; ++i) {
+      int am, ak; a_coord(tid + i * kGemmThreads, am, ak); As[buf][ak][am] = a_reg[i];
+      if (MODE == 2) db_part = __fadd_rn(db_part, a_reg[i]);            // row am == tid & 31 for every i
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER_THR; ++i) { int bk, bn; b_coord(tid + i * kGemmThreads, bk, bn); Bs[buf][bk][bn] = b_reg[i]; }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+  if (kbeg < kend) {
+    fetch(kbeg);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+      const bool more = k0 + BK < kend;
+      if (more) fetch(k0 + BK);                                         // loads in flight during the FMAs below
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
+        const float a[TM] = {av.x, av.y, av.z, av.w}, b[TN] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      if (more) stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  float* red = &Bs[0][0][0];                                            // [BM][BN]
+  __shared__ float db_slice[kGemmThreads / BM][BM];
+  __shared__ float db_cta[BM];
+  if (do_db) {                                                           // CTA-level: 4 k-interleaved partials per row
+    db_slice[tid / BM][tid & (BM - 1)] = db_part;
+    __syncthreads();
+    if (tid < BM) {
+      float t = db_slice[0][tid];
+#pragma unroll
+      for (int sl = 1; sl < kGemmThreads / BM; ++sl) t = __fadd_rn(t, db_slice[sl][tid]);
+      db_cta[tid] = t;
+    }
+  }
+  auto epilogue = [&](int m, int n, float v) {
+    if (m >= M || n >= N) return;
+    if (MODE == 0) {
+      const float z = __fmul_rn(__fadd_rn(v, b_int ? b_int[n] : 0.0f), s_row[n]);
+      C[(long long)m * out_f + n] = act_fwd(z, act);
+    } else if (MODE == 1) {
+      C[(long long)m * in_f + n] = v;
+    } else {
+      float* dst = C + (long long)m * in_f + n;                          // accumulate into the grad arena
+      *dst = __fadd_rn(*dst, __fdiv_rn(v, s_row[m]));
+    }
+  };
+  if (S == 1) {
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) epilogue(m0 + ty * TM + i, n0 + tx * TN + j, acc[i][j]);
+    if (do_db) {
+      __syncthreads();
+      if (tid < BM && m0 + tid < M) db[m0 + tid] = __fadd_rn(db[m0 + tid], __fdiv_rn(db_cta[tid], s_row[m0 + tid]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+      *reinterpret_cast<float4*>(&red[(ty * TM + i) * BN + tx * TN]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    cluster.sync();
+    const int rows_per = BM / S;                                        // S in {2,4,8}
+    for (int e = tid; e < rows_per * BN; e += kGemmThreads) {
+      const int r = rank * rows_per + e / BN, c = e % BN;
+      float part[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)                                        // all DSMEM loads in flight, then a fixed-order sum
+        part[q] = q < S ? cluster.map_shared_rank(red, q)[r * BN + c] : 0.0f;
+      float v = part[0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) if (q < S) v = __fadd_rn(v, part[q]);
+      epilogue(m0 + r, n0 + c, v);
+    }
+    if (do_db && rank == 0 && tid < BM && m0 + tid < M) {
+      float t = db_cta[tid];
+      for (int q = 1; q < S; ++q) t = __fadd_rn(t, cluster.map_shared_rank(db_cta, q)[tid]);
+      db[m0 + tid] = __fadd_rn(db[m0 + tid], __fdiv_rn(t, s_row[m0 + tid]));
+    }
+    cluster.sync();                                                      // peers must not exit while being read
+  }
+}
+
+// cluster size: enough K-slices to put >= ~128 CTAs on the chip, each slice >= 2 K-tiles
+static int pick_split(int tiles, int K) {
+  int S = 1;
+  while (S < 8 && tiles * S < 128 && K / (S * 2) >= 2 * BK) S *= 2;
+  return S;
+}
+
+template <int MODE>
+static int launch_gemm(const float* x, const float* W_int, const float* b_int, const float* s_row, const float* dout,
+                       const float* out, float* C, float* db, int batch, int out_f, int in_f, int act, cudaStream_t st) {
+  const int M = MODE == 2 ? out_f : batch;
+  const int N = MODE == 0 ? out_f : in_f;
+  const int K = MODE == 0 ? in_f : (MODE == 1 ? out_f : batch);
+  const int gx = (N + BN - 1) / BN, gy = (M + BM - 1) / BM;
+  const int S = pick_split(gx * gy, K);
+  int kc = (K + S - 1) / S;
+  kc = ((kc + BK - 1) / BK) * BK;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, gy, S);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, linear_gemm_kernel<MODE>, x, W_int, b_int, s_row, dout, out, C, db, batch,
+                                     out_f, in_f, act, kc);
+  if (e != cudaSuccess) { set_error("linear_gemm_kernel<%d>: %s", MODE, cudaGetErrorString(e)); return -EIO; }
+  return 0;
+}
+
+}  // namespace dqrm
+
+using namespace dqrm;
+
+extern "C" int dqrm_mlp_fakequant_all(int num_layers, const float* const* W, const float* const* b,
+                                      const int32_t* out_features, const int32_t* in_features, int bits,
+                                      float* const* W_int, float* const* b_int, float* const* scale_row, void* stream) {
+  DQRM_REQUIRE(num_layers >= 1 && num_layers <= kMaxLayers, -E2BIG, "mlp_fakequant_all: num_layers=%d (max %d)", num_layers, kMaxLayers);
+  DQRM_REQUIRE(W && out_features && in_features && W_int && scale_row, -EINVAL, "mlp_fakequant_all: null argument");
+  DQRM_REQUIRE(bits >= 2 && bits <= 16, -EINVAL, "mlp_fakequant_all: bits=%d outside [2,16]", bits);
+  MlpLayers L;
+  L.num_layers = num_layers;
+  int rows = 0;
+  for (int l = 0; l < num_layers; ++l) {
+    DQRM_REQUIRE(W[l] && W_int[l] && scale_row[l] && out_features[l] >= 1 && in_features[l] >= 1, -EINVAL,
+                 "mlp_fakequant_all: layer %d malformed", l);
+    L.W[l] = W[l]; L.b[l] = b ? b[l] : nullptr; L.W_int[l] = W_int[l]; L.b_int[l] = b_int ? b_int[l] : nullptr;
+    DQRM_REQUIRE((L.b[l] == nullptr) == (L.b_int[l] == nullptr), -EINVAL, "mlp_fakequant_all: layer %d b/b_int mismatch", l);
+    L.s[l] = scale_row[l]; L.out_f[l] = out_features[l]; L.in_f[l] = in_features[l];
+    L.row_begin[l] = rows;
+    rows += out_features[l];
+  }
+  L.row_begin[num_layers] = rows;
+  mlp_fakequant_all_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, bits);
+  DQRM_LAUNCH_CHECK("mlp_fakequant_all_kernel");
+  return 0;
+}
+
+extern "C" int dqrm_linear_fwd(const float* x, const float* W_int, const float* b_int, const float* scale_row,
+                               int batch, int out_features, int in_features, int act, float* out, void* stream) {
+  DQRM_REQUIRE(x && W_int && scale_row && out, -EINVAL, "linear_fwd: null argument");
+  DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_fwd: bad shape/act");
+  return launch_gemm<0>(x, W_int, b_int, scale_row, nullptr, nullptr, out, nullptr, batch, out_features, in_features, act,
+                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dqrm_linear_bwd(const float* x, const float* W_int, const float* scale_row, const float* dout,
+                               const float* out, int batch, int out_features, int in_features, int act,
+                               float* dx, float* dW_accum, float* db_accum, void* stream) {
+  DQRM_REQUIRE(x && W_int && scale_row && dout && out && dW_accum, -EINVAL, "linear_bwd: null argument");
+  DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_bwd: bad shape/act");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dx)
+    if (int rc = launch_gemm<1>(x, W_int, nullptr, scale_row, dout, out, dx, nullptr, batch, out_features, in_features, act, st))
+      return rc;
+  return launch_gemm<2>(x, W_int, nullptr, scale_row, dout, out, dW_accum, db_accum, batch, out_features, in_features, act, st);
+}

@@ -43,6 +43,34 @@ class DenseArena:
         self.total = total
         self.num_chan = len(chan) - 1
         self.chan_begin = torch.tensor(chan, dtype=torch.int64, device=device)
+        # fake-quantised copies (same layout as `flat`) + per-output-row scales, refreshed by fakequant_all()
+        self.flat_int = torch.zeros(total, dtype=torch.float32, device=device)
+        nrows = sum(l.weight.shape[0] for l in self.layers)
+        self.fc_scale = torch.zeros(nrows, dtype=torch.float32, device=device)
+        off, r0 = 0, 0
+        Wp, bp, Wi, bi, sp, outs, ins = [], [], [], [], [], [], []
+        for l in self.layers:
+            o, i = l.weight.shape
+            l._w_int = self.flat_int[off:off + o * i].view(o, i)
+            Wp.append(l.weight.data.data_ptr()); Wi.append(l._w_int.data_ptr())
+            off += o * i
+            if l.bias is not None:
+                l._b_int = self.flat_int[off:off + o]
+                bp.append(l.bias.data.data_ptr()); bi.append(l._b_int.data_ptr())
+                off += o
+            else:
+                l._b_int = None
+                bp.append(None); bi.append(None)
+            l._fc_scale = self.fc_scale[r0:r0 + o]
+            sp.append(l._fc_scale.data_ptr())
+            r0 += o
+            outs.append(o); ins.append(i)
+        import ctypes as C
+        n = len(self.layers)
+        mk = lambda vals: (C.c_void_p * n)(*vals)
+        self._fq_args = (mk(Wp), mk(bp), (C.c_int32 * n)(*outs), (C.c_int32 * n)(*ins), mk(Wi), mk(bi), mk(sp))
+        self.fused_ok = n <= 16 and len({l.weight_bit for l in self.layers}) == 1 and \
+            all((l.bias is None) or (l.quantize_bias and l.bias_bit == l.weight_bit) for l in self.layers)
         self.scale_local = torch.zeros(self.num_chan, dtype=torch.float32, device=device)
         self.scale_mean = torch.zeros(self.num_chan, dtype=torch.float32, device=device)
         self.codes = torch.zeros(total, dtype=torch.float32, device=device)
@@ -68,6 +96,18 @@ class DenseArena:
                 return False
             off += p.numel()
         return True
+
+    def fakequant_all(self):
+        """Fake-quantise every layer's weight and bias in ONE launch (qm:125-154 for all layers); binds the
+        results to the modules' ``weight_integer / bias_integer / fc_scaling_factor`` attributes."""
+        Wp, bp, outs, ins, Wi, bi, sp = self._fq_args
+        rc = self.lib.dqrm_mlp_fakequant_all(len(self.layers), Wp, bp, outs, ins, int(self.layers[0].weight_bit),
+                                             Wi, bi, sp, _lib.stream_ptr())
+        _lib.check(rc, "dqrm_mlp_fakequant_all")
+        if not getattr(self, "_int_views_bound", False):
+            for l in self.layers:
+                l.weight_integer, l.bias_integer, l.fc_scaling_factor = l._w_int, l._b_int, l._fc_scale
+            self._int_views_bound = True
 
     def zero_grad(self):
         self.flat_grad.zero_()

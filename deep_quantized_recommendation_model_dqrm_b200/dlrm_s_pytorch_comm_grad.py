@@ -42,13 +42,16 @@ class EmbOutputs(list):
     """``ly``: list of per-table [B, D] tensors (the reference's return type) that also carries the
     [T, B, D] tensor they are views of, so interact_features can skip the concatenation."""
     stacked = None
+    group = None
 
 
 class _InteractFunction(torch.autograd.Function):
-    """Fused dot interaction (a14), forward and backward in one kernel each."""
+    """Fused dot interaction (a14), forward and backward in one kernel each.  When `ly` is the output of the
+    fused QAT EmbeddingBag (`group` given) the backward also applies that op's straight-through estimator
+    (g*s)/s in its epilogue and tells the group, so the de-duplicating backward skips it."""
 
     @staticmethod
-    def forward(ctx, x, ly, itself):
+    def forward(ctx, x, ly, itself, group):
         lib = _lib.load()
         T, B, D = ly.shape
         nf = T + 1
@@ -60,6 +63,8 @@ class _InteractFunction(torch.autograd.Function):
         _lib.check(rc, "dqrm_interact_fwd")
         ctx.save_for_backward(x, ly)
         ctx.itself = itself
+        ctx.group = group
+        ctx.ste = group is not None and group.last is not None and not group.last[5]    # quantised forward
         return R
 
     @staticmethod
@@ -70,11 +75,14 @@ class _InteractFunction(torch.autograd.Function):
         dR = dR.contiguous()
         dx = torch.empty_like(x)
         dly = torch.empty((T, B, D), dtype=torch.float32, device=x.device)
+        g = ctx.group
         rc = lib.dqrm_interact_bwd(x.data_ptr(), ly.data_ptr(), ly.stride(0), ly.stride(1), dR.data_ptr(), B, T, D,
                                    int(ctx.itself), dx.data_ptr(), dly.data_ptr(), dly.stride(0), dly.stride(1),
-                                   _lib.stream_ptr())
+                                   g.scale.data_ptr() if ctx.ste else None, _lib.stream_ptr())
         _lib.check(rc, "dqrm_interact_bwd")
-        return dx, dly, None
+        if ctx.ste:
+            g.ste_done_for = dly.data_ptr()      # the gradient tensor that already carries (g*s)/s
+        return dx, dly, None, None
 
 
 class DLRM_Net(nn.Module):
@@ -212,13 +220,35 @@ class DLRM_Net(nn.Module):
             g.dp_world, g.dp_rank = ext_dist.my_size, ext_dist.my_rank
         return g
 
+    fuse_mlp = True               # fused QuantLinear+activation kernels over the dense arena (a15)
+
+    def _fused_mlp_arena(self):
+        """The dense arena if the fused MLP path applies (all layers quantised per channel on CUDA)."""
+        if not self.fuse_mlp or not self.quantize_act_and_lin or not self.channelwise_lin:
+            return None
+        from .sgd_quantized_gradients_parallel_comm import _dense_arena
+        arena = _dense_arena(self)
+        return arena if (arena.fused_ok and arena.flat.is_cuda) else None
+
     def apply_mlp(self, x, layers, prev_act_scaling_factor=None):
-        for layer in layers:
+        fused = self._mlp_arena is not None
+        i, n = 0, len(layers)
+        while i < n:
+            layer = layers[i]
             if isinstance(layer, QuantLinear):
+                if fused and not layer.full_precision_flag and prev_act_scaling_factor is None:
+                    nxt = layers[i + 1] if i + 1 < n else None
+                    act = 1 if isinstance(nxt, nn.ReLU) else (2 if isinstance(nxt, nn.Sigmoid) else 0)
+                    x = layer.forward_fused(x, act)
+                    i += 2 if act else 1
+                    continue
                 x, prev_act_scaling_factor = layer(x, prev_act_scaling_factor)
             else:
                 x = layer(x)
+            i += 1
         return x
+
+    _mlp_arena = None
 
     def apply_emb(self, lS_o, lS_i, emb_l, v_W_l, test_mode=False):
         """All tables in two launches (scale scan + fused forward) instead of a Python loop over
@@ -238,7 +268,7 @@ class DLRM_Net(nn.Module):
             self._scale_views_bound = True
         out = EmbBagGroupFunction.apply(g, idx, off, idx_begin, bags, fp, *[e.embedding_bag.weight for e in self.emb_l])
         ly = EmbOutputs(out.unbind(0))
-        ly.stacked = out
+        ly.stacked, ly.group = out, g
         return ly
 
     shard_scan = False            # multi-GPU: scan 1/world of every table per rank + MAX all-reduce
@@ -249,9 +279,10 @@ class DLRM_Net(nn.Module):
         if self.arch_interaction_op != "dot":
             sys.exit("ERROR: --arch-interaction-op=" + self.arch_interaction_op + " is not supported")
         stacked = getattr(ly, "stacked", None)
+        group = getattr(ly, "group", None)
         if stacked is None:
-            stacked = torch.stack(list(ly), dim=0)
-        R = _InteractFunction.apply(x, stacked, bool(self.arch_interaction_itself))
+            stacked, group = torch.stack(list(ly), dim=0), None
+        R = _InteractFunction.apply(x, stacked, bool(self.arch_interaction_itself), group)
         if not self.quantization_flag:
             return R
         if self.quantize_activation:
@@ -262,6 +293,9 @@ class DLRM_Net(nn.Module):
         if not self.quantization_flag or self.quantize_activation:
             raise NotImplementedError("only the --quantization_flag --linear_channel flow is built "
                                       "(dlrm_s_pytorch_comm_grad.py:855-859)")
+        self._mlp_arena = self._fused_mlp_arena()
+        if self._mlp_arena is not None:
+            self._mlp_arena.fakequant_all()          # all 7 layers' weights + biases, one launch
         x = self.apply_mlp(dense_x, self.bot_l, prev_act_scaling_factor=None)
         ly = self.apply_emb(lS_o, lS_i, self.emb_l, self.v_W_l, test_mode=test_mode)
         z, feature_scaling_factor = self.interact_features(x, ly)

@@ -45,7 +45,9 @@ class EmbBagGroupFunction(Function):
         g = ctx.group
         if dout.stride(2) != 1 or dout.stride(0) % 4 or dout.stride(1) % 4 or dout.data_ptr() % 16:
             dout = dout.contiguous()
-        g.backward(dout, world=g.dp_world, last=ctx.last)
+        ste_done = getattr(g, "ste_done_for", None) == dout.data_ptr()      # fused into the interaction backward
+        g.ste_done_for = None
+        g.backward(dout, world=g.dp_world, last=ctx.last, ste_done=ste_done)
         if g.materialize_grads:
             grads = tuple(g.sparse_grad(t) for t in range(g.T))
         else:
@@ -192,6 +194,40 @@ class _QuantLinearFunction(Function):
         return dx, dW, db, None, None
 
 
+class _FusedQuantLinearFunction(Function):
+    """One kernel forward (GEMM + bias + per-row scale + activation), two backward (dx; dW/db accumulated
+    straight into the gradient arena) on the weights fake-quantised by DenseArena.fakequant_all()."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, module, act):
+        lib = _lib.load()
+        x = x.contiguous()
+        B = x.shape[0]
+        out_f, in_f = weight.shape
+        out = torch.empty((B, out_f), dtype=torch.float32, device=x.device)
+        rc = lib.dqrm_linear_fwd(x.data_ptr(), module._w_int.data_ptr(), _lib.ptr(module._b_int),
+                                 module._fc_scale.data_ptr(), B, out_f, in_f, act, out.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "dqrm_linear_fwd")
+        ctx.save_for_backward(x, out)
+        ctx.module, ctx.act = module, act
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, out = ctx.saved_tensors
+        m = ctx.module
+        dout = dout.contiguous()
+        B = x.shape[0]
+        out_f, in_f = m.weight.shape
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        rc = lib.dqrm_linear_bwd(x.data_ptr(), m._w_int.data_ptr(), m._fc_scale.data_ptr(), dout.data_ptr(),
+                                 out.data_ptr(), B, out_f, in_f, ctx.act, _lib.ptr(dx), m.weight.grad.data_ptr(),
+                                 _lib.ptr(m.bias.grad if m.bias is not None else None), _lib.stream_ptr())
+        _lib.check(rc, "dqrm_linear_bwd")
+        return dx, None, None, None, None
+
+
 class QuantLinear(Module):
     """Per-channel INT-k weight + bias QAT linear layer (quant_modules_not_quantize_grad.py:20-211).
     Returns a tuple ``(y, None)`` like the reference (quantize_activation=False path)."""
@@ -235,6 +271,11 @@ class QuantLinear(Module):
 
     def unfix(self):
         self.fix_flag = False
+
+    def forward_fused(self, x, act):
+        """Fused layer + activation (act: 0 none, 1 relu, 2 sigmoid).  Requires the model's DenseArena
+        (weights / grads are arena views) and a DenseArena.fakequant_all() since the last weight update."""
+        return _FusedQuantLinearFunction.apply(x, self.weight, self.bias, self, act)
 
     def forward(self, x, prev_act_scaling_factor=None):
         if self.full_precision_flag:

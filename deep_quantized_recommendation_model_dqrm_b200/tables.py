@@ -167,7 +167,7 @@ class EmbeddingTableGroup:
         self._bwd_ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
         self._bwd_ws_bytes = wsb
 
-    def backward(self, dout, world=1, last=None):
+    def backward(self, dout, world=1, last=None, ste_done=False):
         """De-duplicated row gradients of a forward (default: the last one) from dOut [T, B, D]-strided."""
         lib, st = self.lib, _lib.stream_ptr()
         indices, offsets, idx_begin, ib, bags, full_precision = last if last is not None else self.last
@@ -182,7 +182,7 @@ class EmbeddingTableGroup:
         self._ensure_step_buffers(cap, world)
         rc = lib.dqrm_embbag_bwd(self.T, self._rows_arr, self.dim, indices.data_ptr(), offsets.data_ptr(), ib, bags,
                                  dout.data_ptr(), dout.stride(0), dout.stride(1),
-                                 None if full_precision else self.scale.data_ptr(),
+                                 None if (full_precision or ste_done) else self.scale.data_ptr(),
                                  self.capacity, self.uniq_rows.data_ptr(), self.uniq_count.data_ptr(),
                                  self.grad_sums.data_ptr(), self.grad_bit, self.grad_scale_local.data_ptr(),
                                  self.status.data_ptr(), self._bwd_ws.data_ptr(), self._bwd_ws_bytes, st)

@@ -213,13 +213,16 @@ DQRM_API int dqrm_grad_merge_apply(int num_tables, float* const* weight, const i
  * Replaces DLRM_Net.interact_features (dlrm_s_pytorch_comm_grad.py:701-725).
  *   ly   dev fp32, element (k,b,d) at ly[k*table_stride + b*bag_stride + d]
  *   R    dev fp32 [batch, dim + npairs]
- * Backward: dx, dly from dR (autograd of the same expression).
+ * Backward: dx, dly from dR (autograd of the same expression).  `ste_scale` (NULL or dev [num_tables]) fuses
+ * the QAT EmbeddingBag's straight-through estimator into the epilogue: dly <- (dly * s_k) / s_k (autograd of
+ * qm:393 then quant_utils.py:363); dqrm_embbag_bwd is then called with fwd_scale = NULL.
  */
 DQRM_API int dqrm_interact_fwd(const float* x, const float* ly, int64_t ly_table_stride, int64_t ly_bag_stride,
                       int64_t batch, int num_tables, int dim, int itself, float* R, void* stream);
 DQRM_API int dqrm_interact_bwd(const float* x, const float* ly, int64_t ly_table_stride, int64_t ly_bag_stride,
                       const float* dR, int64_t batch, int num_tables, int dim, int itself,
-                      float* dx, float* dly, int64_t dly_table_stride, int64_t dly_bag_stride, void* stream);
+                      float* dx, float* dly, int64_t dly_table_stride, int64_t dly_bag_stride,
+                      const float* ste_scale, void* stream);
 
 /* ----------------------------------------------------------------- (a15) --
  * QuantLinear weight/bias fake-quantisation, per output channel:
@@ -229,6 +232,25 @@ DQRM_API int dqrm_interact_bwd(const float* x, const float* ly, int64_t ly_table
  */
 DQRM_API int dqrm_linear_fakequant(const float* W, const float* b, int out_features, int in_features, int bits,
                           float* W_int, float* b_int, float* scale_row, void* stream);
+
+/* Fused QuantLinear layers (same arithmetic as dqrm_linear_fakequant + F.linear + the activation
+ * module that follows each layer in DLRM_Net.create_mlp, dlrm_s_pytorch_comm_grad.py:279-325):
+ *   dqrm_mlp_fakequant_all : dqrm_linear_fakequant for every layer of the model in ONE launch; all array
+ *                            arguments are host arrays [num_layers] (of dev pointers / sizes).
+ *   dqrm_linear_fwd        : out = act((x W_int^t + b_int) * s_row)        act: 0 none, 1 relu, 2 sigmoid
+ *   dqrm_linear_bwd        : g = dout * act'(out) * s_row ; dx = g W_int (dx may be NULL) ;
+ *                            dW_accum += (g^t x) / s_row ; db_accum += (sum_batch g) / s_row
+ *                            (straight-through estimator, quant_utils.py:348-363).
+ * fp32 FFMA with a fixed summation order (no split-K, no atomics): replicas stay bit-identical.
+ */
+DQRM_API int dqrm_mlp_fakequant_all(int num_layers, const float* const* W, const float* const* b,
+                                    const int32_t* out_features, const int32_t* in_features, int bits,
+                                    float* const* W_int, float* const* b_int, float* const* scale_row, void* stream);
+DQRM_API int dqrm_linear_fwd(const float* x, const float* W_int, const float* b_int, const float* scale_row,
+                             int batch, int out_features, int in_features, int act, float* out, void* stream);
+DQRM_API int dqrm_linear_bwd(const float* x, const float* W_int, const float* scale_row, const float* dout,
+                             const float* out, int batch, int out_features, int in_features, int act,
+                             float* dx, float* dW_accum, float* db_accum, void* stream);
 
 /* ------------------------------------------------------------------ (a4) --
  * Stand-alone SymmetricQuantFunction.forward on a [rows, cols] fp32 matrix
