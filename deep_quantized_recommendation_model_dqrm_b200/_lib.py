@@ -43,7 +43,7 @@ SIGNATURES = {
     "dqrm_linear_fakequant": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "dqrm_mlp_fakequant_all": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p]),
     "dqrm_linear_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
-    "dqrm_linear_bwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "dqrm_linear_bwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p]),
     "dqrm_fake_quant": (_i32, [_p, _i64, _i64, _p, _i32, _i32, _p, _p, _p]),
     "dqrm_dense_grad_scale": (_i32, [_p, _p, _i32, _i32, _p, _p]),
     "dqrm_dense_grad_quant": (_i32, [_p, _p, _i32, _p, _f32, _i32, _p, _p, _p]),

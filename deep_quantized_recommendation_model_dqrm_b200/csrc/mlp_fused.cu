@@ -88,7 +88,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads)
 linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int, const float* __restrict__ b_int,
                    const float* __restrict__ s_row, const float* __restrict__ dout, const float* __restrict__ out,
-                   float* __restrict__ C, float* __restrict__ db, int batch, int out_f, int in_f, int act, int kc) {
+                   float* __restrict__ C, float* __restrict__ db, int batch, int out_f, int in_f, int act, int kc,
+                   int accumulate) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
@@ -201,8 +202,9 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
     } else if (MODE == 1) {
       C[(long long)m * in_f + n] = v;
     } else {
-      float* dst = C + (long long)m * in_f + n;                          // accumulate into the grad arena
-      *dst = __fadd_rn(*dst, __fdiv_rn(v, s_row[m]));
+      float* dst = C + (long long)m * in_f + n;                          // straight into the grad arena
+      const float gq = __fdiv_rn(v, s_row[m]);
+      *dst = accumulate ? __fadd_rn(*dst, gq) : gq;
     }
   };
   if (S == 1) {
@@ -212,7 +214,10 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
       for (int j = 0; j < TN; ++j) epilogue(m0 + ty * TM + i, n0 + tx * TN + j, acc[i][j]);
     if (do_db) {
       __syncthreads();
-      if (tid < BM && m0 + tid < M) db[m0 + tid] = __fadd_rn(db[m0 + tid], __fdiv_rn(db_cta[tid], s_row[m0 + tid]));
+      if (tid < BM && m0 + tid < M) {
+        const float gq = __fdiv_rn(db_cta[tid], s_row[m0 + tid]);
+        db[m0 + tid] = accumulate ? __fadd_rn(db[m0 + tid], gq) : gq;
+      }
     }
   } else {
 #pragma unroll
@@ -234,7 +239,8 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
     if (do_db && rank == 0 && tid < BM && m0 + tid < M) {
       float t = db_cta[tid];
       for (int q = 1; q < S; ++q) t = __fadd_rn(t, cluster.map_shared_rank(db_cta, q)[tid]);
-      db[m0 + tid] = __fadd_rn(db[m0 + tid], __fdiv_rn(t, s_row[m0 + tid]));
+      const float gq = __fdiv_rn(t, s_row[m0 + tid]);
+      db[m0 + tid] = accumulate ? __fadd_rn(db[m0 + tid], gq) : gq;
     }
     cluster.sync();                                                      // peers must not exit while being read
   }
@@ -249,7 +255,8 @@ static int pick_split(int tiles, int K) {
 
 template <int MODE>
 static int launch_gemm(const float* x, const float* W_int, const float* b_int, const float* s_row, const float* dout,
-                       const float* out, float* C, float* db, int batch, int out_f, int in_f, int act, cudaStream_t st) {
+                       const float* out, float* C, float* db, int batch, int out_f, int in_f, int act, int accumulate,
+                       cudaStream_t st) {
   const int M = MODE == 2 ? out_f : batch;
   const int N = MODE == 0 ? out_f : in_f;
   const int K = MODE == 0 ? in_f : (MODE == 1 ? out_f : batch);
@@ -268,7 +275,7 @@ static int launch_gemm(const float* x, const float* W_int, const float* b_int, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, linear_gemm_kernel<MODE>, x, W_int, b_int, s_row, dout, out, C, db, batch,
-                                     out_f, in_f, act, kc);
+                                     out_f, in_f, act, kc, accumulate);
   if (e != cudaSuccess) { set_error("linear_gemm_kernel<%d>: %s", MODE, cudaGetErrorString(e)); return -EIO; }
   return 0;
 }
@@ -306,17 +313,18 @@ extern "C" int dqrm_linear_fwd(const float* x, const float* W_int, const float* 
   DQRM_REQUIRE(x && W_int && scale_row && out, -EINVAL, "linear_fwd: null argument");
   DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_fwd: bad shape/act");
   return launch_gemm<0>(x, W_int, b_int, scale_row, nullptr, nullptr, out, nullptr, batch, out_features, in_features, act,
-                        static_cast<cudaStream_t>(stream));
+                        0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dqrm_linear_bwd(const float* x, const float* W_int, const float* scale_row, const float* dout,
                                const float* out, int batch, int out_features, int in_features, int act,
-                               float* dx, float* dW_accum, float* db_accum, void* stream) {
-  DQRM_REQUIRE(x && W_int && scale_row && dout && out && dW_accum, -EINVAL, "linear_bwd: null argument");
+                               float* dx, float* dW, float* db, int accumulate, void* stream) {
+  DQRM_REQUIRE(x && W_int && scale_row && dout && out && dW, -EINVAL, "linear_bwd: null argument");
   DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_bwd: bad shape/act");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dx)
-    if (int rc = launch_gemm<1>(x, W_int, nullptr, scale_row, dout, out, dx, nullptr, batch, out_features, in_features, act, st))
+    if (int rc = launch_gemm<1>(x, W_int, nullptr, scale_row, dout, out, dx, nullptr, batch, out_features, in_features, act, 0, st))
       return rc;
-  return launch_gemm<2>(x, W_int, nullptr, scale_row, dout, out, dW_accum, db_accum, batch, out_features, in_features, act, st);
+  return launch_gemm<2>(x, W_int, nullptr, scale_row, dout, out, dW, db, batch, out_features, in_features, act,
+                        accumulate ? 1 : 0, st);
 }

@@ -111,6 +111,8 @@ class DenseArena:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+        for l in self.layers:
+            l._grad_dirty = False
 
     def quantize_exchange(self, world=1, process_group=None, bits=8, quantized=True):
         """quantize_linear_grad / quantize_bias_grad for every tensor at once

@@ -221,10 +221,14 @@ class _FusedQuantLinearFunction(Function):
         B = x.shape[0]
         out_f, in_f = m.weight.shape
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        # grads cleared since the last write (clear_gradients) are overwritten, otherwise accumulated
+        accumulate = 1 if getattr(m, "_grad_dirty", True) else 0
         rc = lib.dqrm_linear_bwd(x.data_ptr(), m._w_int.data_ptr(), m._fc_scale.data_ptr(), dout.data_ptr(),
                                  out.data_ptr(), B, out_f, in_f, ctx.act, _lib.ptr(dx), m.weight.grad.data_ptr(),
-                                 _lib.ptr(m.bias.grad if m.bias is not None else None), _lib.stream_ptr())
+                                 _lib.ptr(m.bias.grad if m.bias is not None else None), accumulate,
+                                 _lib.stream_ptr())
         _lib.check(rc, "dqrm_linear_bwd")
+        m._grad_dirty = True
         return dx, None, None, None, None
 
 

@@ -239,8 +239,9 @@ DQRM_API int dqrm_linear_fakequant(const float* W, const float* b, int out_featu
  *                            arguments are host arrays [num_layers] (of dev pointers / sizes).
  *   dqrm_linear_fwd        : out = act((x W_int^t + b_int) * s_row)        act: 0 none, 1 relu, 2 sigmoid
  *   dqrm_linear_bwd        : g = dout * act'(out) * s_row ; dx = g W_int (dx may be NULL) ;
- *                            dW_accum += (g^t x) / s_row ; db_accum += (sum_batch g) / s_row
- *                            (straight-through estimator, quant_utils.py:348-363).
+ *                            dW (+)= (g^t x) / s_row ; db (+)= (sum_batch g) / s_row
+ *                            (straight-through estimator, quant_utils.py:348-363); `accumulate` = 0 overwrites
+ *                            (gradients freshly cleared, clear_gradients sgd:714), 1 adds to what is there.
  * fp32 FFMA with a fixed summation order (no split-K, no atomics): replicas stay bit-identical.
  */
 DQRM_API int dqrm_mlp_fakequant_all(int num_layers, const float* const* W, const float* const* b,
@@ -250,7 +251,7 @@ DQRM_API int dqrm_linear_fwd(const float* x, const float* W_int, const float* b_
                              int batch, int out_features, int in_features, int act, float* out, void* stream);
 DQRM_API int dqrm_linear_bwd(const float* x, const float* W_int, const float* scale_row, const float* dout,
                              const float* out, int batch, int out_features, int in_features, int act,
-                             float* dx, float* dW_accum, float* db_accum, void* stream);
+                             float* dx, float* dW, float* db, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------ (a4) --
  * Stand-alone SymmetricQuantFunction.forward on a [rows, cols] fp32 matrix
