@@ -69,51 +69,63 @@ def mlp_sizes(cfg):
 
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  The timed region is tens
+    of milliseconds, too short for `nvidia-smi -lms`, so NVML is polled from a thread every ~2 ms."""
 
     def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.rows, self.proc, self.th = [], None, None
+        self.gpu, self.samples, self.stop_flag, self.th, self.err = gpu_index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES if it remaps them
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                                    # pragma: no cover
+            self.nv, self.err = None, repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        if self.nv is None:
             return
+        nv = self.nv
+
         def pump():
-            for line in self.proc.stdout:
-                self.rows.append(line.strip())
+            while not self.stop_flag:
+                try:
+                    mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    self.samples.append((time.perf_counter(), float(mhz), int(reasons)))
+                except Exception as e:                            # pragma: no cover
+                    self.err = repr(e)
+                    return
+                time.sleep(0.002)
         self.th = threading.Thread(target=pump, daemon=True)
         self.th.start()
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.th is not None:
+            self.th.join(timeout=1.0)
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable: %s" % self.err]}
+        nv = self.nv
+        sel = [s for s in self.samples if (t0 is None or s[0] >= t0) and (t1 is None or s[0] <= t1)] or self.samples
+        bits = 0
+        for s in sel:
+            bits |= s[2]
+        names = []
+        for nm, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                         ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                         ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                         ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            flag = getattr(nv, attr, None)
+            if flag is None:
+                flag = getattr(nv, attr.replace("ClocksEventReason", "ClocksThrottleReason"), 0)
+            if bits & flag:
+                names.append(nm)
+        return {"sm_mhz": float(np.median([s[1] for s in sel])), "sm_max_mhz": self.max_mhz, "reasons": names,
+                "samples": len(sel)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -169,6 +181,19 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
+def finish(world):
+    """Multi-rank exit.  destroy_process_group() with NCCL collectives captured in live CUDA graphs was seen
+    to hang at N=8 (the processes never exited); leave the communicator to process teardown and exit hard
+    once every rank has passed the last barrier."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_ours(args):
     import torch.distributed as dist
     from deep_quantized_recommendation_model_dqrm_b200 import _lib, synthetic
@@ -251,9 +276,10 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    t_begin = time.perf_counter()
     ms_dev, scan_ms = timed(args.steps, args.warmup, from_host=False)
     ms_e2e, _ = timed(args.steps, args.warmup, from_host=True)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     dlrm.emb_group.check_status()
     final_loss = float(step.loss.item())
 
@@ -269,7 +295,7 @@ def run_ours(args):
     algo_bytes = table_bytes / world if dlrm.shard_scan else table_bytes
     achieved = algo_bytes / (scan_ms / 1000.0) / 1e9
     if rank != 0:
-        dist.destroy_process_group()
+        finish(world)
         return
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -303,8 +329,7 @@ def run_ours(args):
                                 "sample": f"{args.cpu_steps} full train steps after 1 warm-up, batch {B}, same "
                                           f"{args.workload}-shape model on the host ({build_s:.0f}s to build tables)"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 # DRAM traffic of one table_absmax_kernel launch from `ncu --set full` (dram__bytes_read.sum +

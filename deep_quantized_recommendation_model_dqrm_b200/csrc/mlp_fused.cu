@@ -319,12 +319,13 @@ extern "C" int dqrm_linear_fwd(const float* x, const float* W_int, const float* 
 extern "C" int dqrm_linear_bwd(const float* x, const float* W_int, const float* scale_row, const float* dout,
                                const float* out, int batch, int out_features, int in_features, int act,
                                float* dx, float* dW, float* db, int accumulate, void* stream) {
-  DQRM_REQUIRE(x && W_int && scale_row && dout && out && dW, -EINVAL, "linear_bwd: null argument");
+  DQRM_REQUIRE(x && W_int && scale_row && dout && out && (dW || dx), -EINVAL, "linear_bwd: null argument");
   DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_bwd: bad shape/act");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dx)
     if (int rc = launch_gemm<1>(x, W_int, nullptr, scale_row, dout, out, dx, nullptr, batch, out_features, in_features, act, 0, st))
       return rc;
+  if (!dW) return 0;                                      // dx only (the caller runs dW on another stream)
   return launch_gemm<2>(x, W_int, nullptr, scale_row, dout, out, dW, db, batch, out_features, in_features, act,
                         accumulate ? 1 : 0, st);
 }

@@ -71,6 +71,11 @@ class DenseArena:
         self._fq_args = (mk(Wp), mk(bp), (C.c_int32 * n)(*outs), (C.c_int32 * n)(*ins), mk(Wi), mk(bi), mk(sp))
         self.fused_ok = n <= 16 and len({l.weight_bit for l in self.layers}) == 1 and \
             all((l.bias is None) or (l.quantize_bias and l.bias_bit == l.weight_bit) for l in self.layers)
+        # weight-gradient GEMMs run on a side stream, off the critical dx chain (None = same stream)
+        self.side_stream = torch.cuda.Stream(device=device) if self.flat.is_cuda else None
+        self.keepalive = []
+        for l in self.layers:
+            l._arena = self
         self.scale_local = torch.zeros(self.num_chan, dtype=torch.float32, device=device)
         self.scale_mean = torch.zeros(self.num_chan, dtype=torch.float32, device=device)
         self.codes = torch.zeros(total, dtype=torch.float32, device=device)
@@ -109,7 +114,14 @@ class DenseArena:
                 l.weight_integer, l.bias_integer, l.fc_scaling_factor = l._w_int, l._b_int, l._fc_scale
             self._int_views_bound = True
 
+    def join(self):
+        """Make the current stream wait for the side-stream weight-gradient kernels of this step."""
+        if self.side_stream is not None and self.keepalive:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+            self.keepalive.clear()
+
     def zero_grad(self):
+        self.join()
         self.flat_grad.zero_()
         for l in self.layers:
             l._grad_dirty = False
@@ -120,6 +132,7 @@ class DenseArena:
         quantise with the mean scale -> SUM all-reduce of the codes."""
         if world > 1:
             import torch.distributed as dist
+        self.join()
         if not quantized:
             self.codes.copy_(self.flat_grad)
             if world > 1:
@@ -133,6 +146,7 @@ class DenseArena:
             dist.all_reduce(self.codes, group=process_group)
 
     def local_scale(self, bits=8):
+        self.join()
         _lib.check(self.lib.dqrm_dense_grad_scale(self.flat_grad.data_ptr(), self.chan_begin.data_ptr(), self.num_chan,
                                                   bits, self.scale_local.data_ptr(), _lib.stream_ptr()),
                    "dqrm_dense_grad_scale")

@@ -223,11 +223,23 @@ class _FusedQuantLinearFunction(Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         # grads cleared since the last write (clear_gradients) are overwritten, otherwise accumulated
         accumulate = 1 if getattr(m, "_grad_dirty", True) else 0
-        rc = lib.dqrm_linear_bwd(x.data_ptr(), m._w_int.data_ptr(), m._fc_scale.data_ptr(), dout.data_ptr(),
-                                 out.data_ptr(), B, out_f, in_f, ctx.act, _lib.ptr(dx), m.weight.grad.data_ptr(),
-                                 _lib.ptr(m.bias.grad if m.bias is not None else None), accumulate,
-                                 _lib.stream_ptr())
-        _lib.check(rc, "dqrm_linear_bwd")
+        args = (x.data_ptr(), m._w_int.data_ptr(), m._fc_scale.data_ptr(), dout.data_ptr(), out.data_ptr(), B, out_f,
+                in_f, ctx.act)
+        wg, bg = m.weight.grad.data_ptr(), _lib.ptr(m.bias.grad if m.bias is not None else None)
+        arena = getattr(m, "_arena", None)
+        side = arena.side_stream if arena is not None else None
+        if side is None:
+            rc = lib.dqrm_linear_bwd(*args, _lib.ptr(dx), wg, bg, accumulate, _lib.stream_ptr())
+            _lib.check(rc, "dqrm_linear_bwd")
+        else:
+            # dx is on the critical path of the backward chain; dW/db only feed the optimizer, so they run
+            # on the arena's side stream and are joined in DenseArena.join() before the gradients are used
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            if dx is not None:
+                _lib.check(lib.dqrm_linear_bwd(*args, dx.data_ptr(), None, None, 0, main.cuda_stream), "dqrm_linear_bwd")
+            _lib.check(lib.dqrm_linear_bwd(*args, None, wg, bg, accumulate, side.cuda_stream), "dqrm_linear_bwd")
+            arena.keepalive.append((x, out, dout))        # these must outlive the side-stream kernel
         m._grad_dirty = True
         return dx, None, None, None, None
 

@@ -238,7 +238,8 @@ DQRM_API int dqrm_linear_fakequant(const float* W, const float* b, int out_featu
  *   dqrm_mlp_fakequant_all : dqrm_linear_fakequant for every layer of the model in ONE launch; all array
  *                            arguments are host arrays [num_layers] (of dev pointers / sizes).
  *   dqrm_linear_fwd        : out = act((x W_int^t + b_int) * s_row)        act: 0 none, 1 relu, 2 sigmoid
- *   dqrm_linear_bwd        : g = dout * act'(out) * s_row ; dx = g W_int (dx may be NULL) ;
+ *   dqrm_linear_bwd        : g = dout * act'(out) * s_row ; dx = g W_int (dx may be NULL; dW/db may be NULL
+ *                            so the two products can be issued on different streams) ;
  *                            dW (+)= (g^t x) / s_row ; db (+)= (sum_batch g) / s_row
  *                            (straight-through estimator, quant_utils.py:348-363); `accumulate` = 0 overwrites
  *                            (gradients freshly cleared, clear_gradients sgd:714), 1 adds to what is there.
