@@ -54,6 +54,10 @@ def parse():
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-steps", type=int, default=5)
+    p.add_argument("--scale-policy", type=str, default="full", choices=["full", "incremental"],
+                   help="full = rescan all tables every step (reference semantics); incremental = exact block-max tracker")
+    p.add_argument("--no-incremental-extra", action="store_true",
+                   help="skip the additional measurement of the incremental tracker reported beside the headline")
     return p.parse_args()
 
 
@@ -232,6 +236,7 @@ def run_ours(args):
         hb = tuple(t.pin_memory() for t in (X, lS_o, lS_i, T))
         host.append(hb)
         devb.append(tuple(t.to(dev) for t in hb))
+    dlrm._ensure_group().scale_policy = args.scale_policy
     step = GraphedTrainStep(dlrm, *devb[0], lr=LR, world_size=world, rank=rank, grad_bits=8, warmup=3,
                             use_graph=not args.no_graph)
     n0 = _lib.total_launches()                                # count OUR kernel launches of one step: one more
@@ -244,7 +249,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(K, W, from_host):
+    def timed(step, K, W, from_host):
         ev_scan = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         src = host if from_host else devb
@@ -277,11 +282,29 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     t_begin = time.perf_counter()
-    ms_dev, scan_ms = timed(args.steps, args.warmup, from_host=False)
-    ms_e2e, _ = timed(args.steps, args.warmup, from_host=True)
+    ms_dev, scan_ms = timed(step, args.steps, args.warmup, from_host=False)
+    ms_e2e, _ = timed(step, args.steps, args.warmup, from_host=True)
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     dlrm.emb_group.check_status()
     final_loss = float(step.loss.item())
+    extra = None
+    if args.scale_policy == "full" and not args.no_incremental_extra:
+        # the same step with the exact incremental scale tracker (bit-identical scales,
+        # tests/test_gpu_tracker.py): reported beside the headline, never instead of it
+        dlrm.emb_group.scale_policy = "incremental"
+        step2 = GraphedTrainStep(dlrm, *devb[0], lr=LR, world_size=world, rank=rank, grad_bits=8, warmup=3,
+                                 use_graph=not args.no_graph)
+        ms_inc, red_ms = timed(step2, args.steps, args.warmup, from_host=False)
+        ms_inc_e2e, _ = timed(step2, args.steps, args.warmup, from_host=True)
+        dlrm.emb_group.check_status()
+        extra = {"value": B * world * args.steps / (ms_inc / 1000.0), "unit": "samples/s",
+                 "ms_per_step": ms_inc / args.steps,
+                 "e2e_value": B * world * args.steps / (ms_inc_e2e / 1000.0),
+                 "blockmax_reduce_ms": red_ms,
+                 "note": "exact block-max tracker instead of the full rescan: scales bit-identical to the rescan "
+                         "(SURVEY.md 8 f-1); not the headline because the reference rescans every step"}
+        dlrm.emb_group.scale_policy = "full"
+        del step2
 
     gbatch = B * world
     value = gbatch * args.steps / (ms_dev / 1000.0)
@@ -304,8 +327,9 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}-shape DQRM: {len(cfg['rows'])} tables ({sum(cfg['rows'])} rows, "
                                f"{table_bytes / 1e9:.3f} GB fp32), dim {cfg['dim']}, INT4 emb+MLP QAT, INT8 grad exchange, "
                                f"batch {B}/GPU", "global_batch": gbatch, "parallelism": f"dp{world}",
-                   "scale_scan": "full rescan every step (reference period-1 semantics)" +
-                                 (", row-sharded 1/N + MAX all-reduce" if dlrm.shard_scan else ""),
+                   "scale_scan": ("exact incremental block-max tracker" if args.scale_policy == "incremental" else
+                                  "full rescan every step (reference period-1 semantics)" +
+                                  (", row-sharded 1/N + MAX all-reduce" if dlrm.shard_scan else "")),
                    "l2": "table arena (2.16 GB) is 17x the 126 MB L2: inputs larger than L2, no flush needed",
                    "cuda_graph": step.graph is not None, "final_loss": final_loss},
         "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
@@ -320,6 +344,8 @@ def run_ours(args):
                      "share_of_step": scan_ms / (ms_dev / args.steps)},
         "clocks": clocks,
     }
+    if extra is not None:
+        line["incremental_scale_tracker"] = extra
     if world == 1 and not args.no_cpu_baseline:
         del step, dlrm
         torch.cuda.empty_cache()

@@ -59,6 +59,13 @@ class EmbeddingTableGroup:
         self.updated_rows = self.updated_count = self.qbar = None
         self._bwd_ws = None
         self.last = None          # (indices, offsets, idx_begin, idx_begin_arr, bags, full_precision)
+        # (a1) scale policy: "full" = rescan every table on every call (reference semantics, HBM-bound);
+        # "incremental" = exact block-max tracker (bit-identical scales, O(touched rows) per step)
+        self.scale_policy = "full"
+        self.block_rows = 64
+        self._bm_buf = None
+        self._bm_valid = False
+        self._bm_wptrs = None
         self.fixed_capacity = None  # rows per table in the exchange slots (default: this step's largest table)
         self.keep_debug = False   # also emit updated_rows / qbar in merge (parity tests, .grad materialisation)
 
@@ -101,11 +108,67 @@ class EmbeddingTableGroup:
             off = torch.stack([t.to(device=device, dtype=torch.int64) for t in lS_o]).contiguous()
         return idx, off, idx_begin, int(off.shape[1])
 
+    # ---- (a1) incremental tracker ------------------------------------------
+    def _ensure_blockmax(self):
+        if self._bm_buf is not None:
+            return
+        ent = [int(self.lib.dqrm_blockmax_entries(n, self.block_rows)) for n in self.rows]
+        pad = [(e + 3) // 4 * 4 for e in ent]                       # keep every table's segment 16-byte aligned
+        self._bm_buf = torch.zeros(max(sum(pad), 4), dtype=torch.float32, device=self.device)
+        views, off = [], 0
+        for p_ in pad:
+            views.append(self._bm_buf[off:off + p_])
+            off += p_
+        self._bm_views = views
+        self._bm_ptrs = _lib.ptr_array(views)
+        self._bm_entries = _lib.i64_array(ent)
+
+    def invalidate_tracker(self):
+        """Call after mutating a table outside merge_apply / sgd_apply (e.g. loading a checkpoint)."""
+        self._bm_valid = False
+
+    def _tracker_scan(self, events=None):
+        lib, st = self.lib, _lib.stream_ptr()
+        self._ensure_blockmax()
+        wp = self._wptrs()
+        cur = tuple(wp)
+        if self._bm_wptrs != cur:                                  # a table's storage was replaced
+            self._bm_valid, self._bm_wptrs = False, cur
+        if not self._bm_valid:
+            _lib.check(lib.dqrm_blockmax_build(self.T, wp, self._rows_arr, self.dim, self.block_rows, self._bm_ptrs, st),
+                       "dqrm_blockmax_build")
+            self._bm_valid = True
+        if events is not None:
+            events[0].record()
+        rc = lib.dqrm_table_absmax_scale(self.T, self._bm_ptrs, self._bm_entries, 1, self.embedding_bit, 0, 1,
+                                         self.absmax.data_ptr(), self.scale.data_ptr(), self.inv_scale.data_ptr(),
+                                         self._scan_ws.data_ptr(), st)
+        if events is not None:
+            events[1].record()
+        _lib.check(rc, "dqrm_table_absmax_scale(blockmax)")
+        self.scale_valid = True
+
+    def _tracker_update(self, from_slots):
+        if self.scale_policy != "incremental" or not self._bm_valid:
+            return
+        st = _lib.stream_ptr()
+        if from_slots:
+            rc = self.lib.dqrm_blockmax_update(self.T, self._wptrs(), self._rows_arr, self.dim, self.block_rows,
+                                               self._bm_ptrs, self.gathered.data_ptr(), self.world, self.capacity,
+                                               self.grad_bit, None, None, st)
+        else:
+            rc = self.lib.dqrm_blockmax_update(self.T, self._wptrs(), self._rows_arr, self.dim, self.block_rows,
+                                               self._bm_ptrs, None, 0, self.capacity, self.grad_bit,
+                                               self.uniq_rows.data_ptr(), self.uniq_count.data_ptr(), st)
+        _lib.check(rc, "dqrm_blockmax_update")
+
     # ---- (a1) -----------------------------------------------------------
     def scan_scales(self, shard_rank=0, shard_world=1, process_group=None, events=None):
         """Recompute every table's scale from a full max-abs pass (one launch).
         With shard_world > 1 each rank scans 1/world of the rows and the maxima
         are combined with a MAX all-reduce (replicas are bit-identical)."""
+        if self.scale_policy == "incremental":
+            return self._tracker_scan(events)
         lib, st = self.lib, _lib.stream_ptr()
         sharded = shard_world > 1
         if events is not None:            # (start, end) CUDA events bracketing exactly the scan kernel
@@ -254,6 +317,7 @@ class EmbeddingTableGroup:
                                        _lib.ptr(self.updated_count) if dbg else None,
                                        _lib.ptr(self.qbar) if dbg else None, self.status.data_ptr(), st)
         _lib.check(rc, "dqrm_grad_merge_apply")
+        self._tracker_update(from_slots=True)
 
     def sgd_apply(self, lr, inv_world=1.0, momentum=None, eps=1e-10):
         """(a10) un-quantised row update from the local de-duplicated sums (optionally RW-Adagrad)."""
@@ -263,6 +327,7 @@ class EmbeddingTableGroup:
                                     self.uniq_count.data_ptr(), self.grad_sums.data_ptr(), self.capacity, float(lr),
                                     float(inv_world), mom, float(eps), st)
         _lib.check(rc, "dqrm_sgd_rows")
+        self._tracker_update(from_slots=False)
 
     # ---- views for tests / API compatibility (these synchronise) ----------
     def slot_views(self, rank=0):

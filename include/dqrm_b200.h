@@ -85,6 +85,24 @@ DQRM_API int dqrm_table_absmax_scale(int num_tables, const float* const* weight,
 DQRM_API int dqrm_scale_from_absmax(int n_scales, const float* absmax, int bits, float* scale, float* inv_scale,
                            void* stream);
 
+/* Exact incremental form of (a1) -- SURVEY.md section 8 (f-1).  max|W| is maintained per block of
+ * `block_rows` rows; after an update only the blocks holding an updated row are recomputed (from the table,
+ * so decreases are exact), and the per-table scale is the reduction of the block maxima: run
+ * dqrm_table_absmax_scale over the block-max arrays (each viewed as a [entries, 1] fp32 table).  The result
+ * is bit-identical to a full rescan.  The caller must route every table mutation through
+ * dqrm_grad_merge_apply / dqrm_sgd_rows + dqrm_blockmax_update, or rebuild.
+ *   blockmax   host array [num_tables] of dev fp32 [dqrm_blockmax_entries(rows_k, block_rows)] (16-byte aligned)
+ *   update     from the gathered exchange slots (gathered != NULL: world, capacity, bits as in
+ *              dqrm_grad_merge_apply) or from a local row list (uniq_rows / uniq_count, gathered == NULL)
+ */
+DQRM_API int64_t dqrm_blockmax_entries(int64_t rows, int block_rows);
+DQRM_API int dqrm_blockmax_build(int num_tables, const float* const* weight, const int64_t* rows, int dim,
+                                 int block_rows, float* const* blockmax, void* stream);
+DQRM_API int dqrm_blockmax_update(int num_tables, const float* const* weight, const int64_t* rows, int dim,
+                                  int block_rows, float* const* blockmax,
+                                  const void* gathered, int world, int64_t capacity, int bits,
+                                  const int32_t* uniq_rows, const int32_t* uniq_count, void* stream);
+
 /* ------------------------------------------------------------------ (a3) --
  * Fused gather + sum-pool + fake-quantise + dequantise for all tables in one
  * launch.  Replaces QuantEmbeddingBagTwo.forward steps (ii)-(iv)
