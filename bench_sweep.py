@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: INT4 QAT EmbeddingBag fwd+bwd micro-benchmark sweep on ONE table, 1 B200,
+against the CPU oracle (the reference's path restated, all host threads).
+
+    python bench_sweep.py [--quick] [--cpu] [--out profiles/rNN_sweep.jsonl]
+
+Per grid point (rows N, dim D, pooling P, batch B) it times, with CUDA events after warm-up:
+  scan      dqrm_table_absmax_scale                          bytes N*D*4
+  fwd       dqrm_embbag_fwd (scale given)                    bytes L(4D+8) + B(8+4D) + B*D (int8 codes)
+  bwd       dqrm_embbag_bwd + grad_pack + grad_merge_apply   bytes B*4D + L*8 + U*8D   
+and reports achieved GB/s on those ALGORITHMIC bytes (U = unique rows, counted on the device).
+Tables are larger than the 126 MB L2 for N >= 4M (D=16) so no flush is needed there; for smaller tables a
+256 MB buffer is written between iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def gpu_point(N, D, P, B, iters=5, flush=None):
+    from deep_quantized_recommendation_model_dqrm_b200 import synthetic, tables
+    dev = "cuda"
+    W = torch.empty((N, D), dtype=torch.float32, device=dev)
+    synthetic.table_weights_(W, 0, 99)
+    g = tables.EmbeddingTableGroup([W], embedding_bit=4)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    idx = torch.randint(0, N, (B * P,), device=dev, generator=gen, dtype=torch.int64)
+    off = (torch.arange(B, device=dev, dtype=torch.int64) * P).view(1, B)
+    ib = [0, B * P]
+    dout = torch.randn((1, B, D), device=dev, generator=gen)
+    out = torch.empty((1, B, D), device=dev)
+    L = B * P
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    t = {"scan": [], "fwd": [], "bwd": []}
+    for it in range(iters + 2):
+        if flush is not None:
+            flush.add_(1.0)
+        e = [ev() for _ in range(4)]
+        e[0].record(); g.scan_scales()
+        e[1].record(); g.forward(idx, off, ib, B, out=out)
+        e[2].record(); g.backward(dout, world=1); g.exchange(world=1, rank=0); g.merge_apply(0.1)
+        e[3].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            t["scan"].append(e[0].elapsed_time(e[1])); t["fwd"].append(e[1].elapsed_time(e[2])); t["bwd"].append(e[2].elapsed_time(e[3]))
+    g.check_status()
+    U = int(g.uniq_count[0].item())
+    ms = {k: float(np.median(v)) for k, v in t.items()}
+    by = {"scan": N * D * 4, "fwd": L * (4 * D + 8) + B * (8 + 4 * D) + B * D, "bwd": B * 4 * D + L * 8 + U * 8 * D}
+    res = {"rows": N, "dim": D, "pooling": P, "batch": B, "lookups": L, "unique_rows": U, "ms": ms, "bytes": by,
+           "GBps": {k: by[k] / (ms[k] * 1e-3) / 1e9 for k in ms},
+           "fwd_bwd_GBps_with_scan": sum(by.values()) / (sum(ms.values()) * 1e-3) / 1e9,
+           "fwd_bwd_GBps_gather_only": (by["fwd"] + by["bwd"]) / ((ms["fwd"] + ms["bwd"]) * 1e-3) / 1e9}
+    del g, W
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_point(N, D, P, B):
+    """Reference path on the host (oracle torch layer): scan + EmbeddingBag fwd + quant + bwd + coalesce +
+    8-bit quantise + SGD row update, one iteration after one warm-up."""
+    from oracle import dqrm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(5)
+    W = (torch.rand((N, D), generator=g) * 2 - 1) * float(np.sqrt(1 / N))
+    E = O.OracleEmbeddingBag(N, D, 4, weight=W)
+    idx = torch.randint(0, N, (B * P,), generator=g)
+    off = torch.arange(B) * P
+    dout = torch.randn((B, D), generator=g)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        y = E(idx, off)
+        E.embedding_bag.weight.grad = None
+        y.backward(dout)
+        co = E.embedding_bag.weight.grad.coalesce()
+        s = O.table_scale_torch(co.values(), 8).view(-1)
+        q = O.quantize_torch(co.values(), 8, s)
+        with torch.no_grad():
+            E.embedding_bag.weight.data[co.indices()[0]] += -0.1 * (q * s.item())
+        best = time.perf_counter() - t0
+    return {"ms_total": best * 1e3, "cores": torch.get_num_threads()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on the points with rows <= 4M")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    a = ap.parse_args()
+    if a.quick:
+        grid = [(1_000_000, 16, 1, 65536), (10_000_000, 16, 1, 65536), (10_000_000, 64, 16, 8192), (40_000_000, 128, 4, 8192)]
+    else:
+        grid = [(N, D, P, B) for N in (1_000_000, 10_000_000, 40_000_000) for D in (16, 64, 128)
+                for (P, B) in ((1, 65536), (16, 8192), (64, 1024))]
+    flush = torch.zeros(64 * 1024 * 1024, device="cuda")          # 256 MB > L2
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    with open(a.out, "w") as f:
+        for (N, D, P, B) in grid:
+            r = gpu_point(N, D, P, B, flush=flush if N * D * 4 < 512 * 1024 * 1024 else None)
+            if a.cpu and N <= 4_000_000:
+                r["cpu"] = cpu_point(N, D, P, B)
+                r["speedup_vs_cpu"] = r["cpu"]["ms_total"] / sum(r["ms"].values())
+            f.write(json.dumps(r) + "\n")
+            f.flush()
+            print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -20,7 +20,7 @@ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 struct SlotLayout { size_t rows_off, codes_off, bytes; int code_bytes; };
 inline SlotLayout slot_layout(int num_tables, int64_t capacity, int dim, int bits) {
   SlotLayout l;
-  l.code_bytes = bits > 8 ? 2 : 1;
+  l.code_bytes = bits == 32 ? 4 : (bits > 8 ? 2 : 1);   // 32 = un-quantised fp32 payload
   l.rows_off = align16((size_t)num_tables * 4);
   l.codes_off = l.rows_off + align16((size_t)num_tables * capacity * 4);
   l.bytes = l.codes_off + align16((size_t)num_tables * capacity * dim * l.code_bytes);
@@ -30,6 +30,9 @@ inline SlotLayout slot_layout(int num_tables, int64_t capacity, int dim, int bit
 template <typename CodeT> struct Code4;
 template <> struct Code4<int8_t> { using type = char4; };
 template <> struct Code4<int16_t> { using type = short4; };
+template <> struct Code4<float> { using type = float4; };        // un-quantised exchange (emb_grad_quantized=False)
+template <typename CodeT> struct AccOf { using type = int; };
+template <> struct AccOf<float> { using type = float; };
 
 // s_bar = (sum_r s_r) * (1/N) in rank order
 __device__ __forceinline__ float mean_scale(const float* __restrict__ gathered, int world, int T, int t, float inv_world) {
@@ -65,8 +68,12 @@ grad_pack_kernel(int T, int dim4, int group, const float* __restrict__ grad_sums
       if (col >= dim4) continue;
       const float4 g = g4[col];
       C4 q;
-      q.x = (CodeT)quant_code(g.x, inv, lo, hi); q.y = (CodeT)quant_code(g.y, inv, lo, hi);
-      q.z = (CodeT)quant_code(g.z, inv, lo, hi); q.w = (CodeT)quant_code(g.w, inv, lo, hi);
+      if constexpr (sizeof(CodeT) == 4) {
+        q.x = g.x; q.y = g.y; q.z = g.z; q.w = g.w;                      // fp32 sums travel as they are
+      } else {
+        q.x = (CodeT)quant_code(g.x, inv, lo, hi); q.y = (CodeT)quant_code(g.y, inv, lo, hi);
+        q.z = (CodeT)quant_code(g.z, inv, lo, hi); q.w = (CodeT)quant_code(g.w, inv, lo, hi);
+      }
       codes[e * dim4 + col] = q;
     }
   }
@@ -110,7 +117,7 @@ grad_merge_apply_kernel(const __grid_constant__ TableSet ts, int dim4, int group
       const int n2 = reinterpret_cast<const int*>(o)[t];
       if (find_row(reinterpret_cast<const int*>(o + lay.rows_off) + (long long)t * capacity, n2, x) >= 0) live = false;
     }
-    int q[COLS][4];
+    typename AccOf<CodeT>::type q[COLS][4];
     if (live) {
       const C4* mc = reinterpret_cast<const C4*>(my + lay.codes_off) + ((long long)t * capacity + j) * dim4;
 #pragma unroll
@@ -150,14 +157,19 @@ grad_merge_apply_kernel(const __grid_constant__ TableSet ts, int dim4, int group
       if (col >= dim4) continue;
       float qb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qb[i] = __fmul_rn((float)q[c][i], inv_world);       // (sum q) * (1/N)   :885
+      for (int i = 0; i < 4; ++i) qb[i] = __fmul_rn((float)q[c][i], inv_world);       // (sum q) * (1/N)   :885 / :322
       if (qbar) reinterpret_cast<float4*>(qbar + ((long long)t * world * capacity + slot_pos) * dim4 * 4)[col] =
                     make_float4(qb[0], qb[1], qb[2], qb[3]);
       float4 w = w4[col];
-      w.x = __fadd_rn(w.x, __fmul_rn(neg_lr, __fmul_rn(qb[0], s_bar)));               // :618, :622
-      w.y = __fadd_rn(w.y, __fmul_rn(neg_lr, __fmul_rn(qb[1], s_bar)));
-      w.z = __fadd_rn(w.z, __fmul_rn(neg_lr, __fmul_rn(qb[2], s_bar)));
-      w.w = __fadd_rn(w.w, __fmul_rn(neg_lr, __fmul_rn(qb[3], s_bar)));
+      if constexpr (sizeof(CodeT) == 4) {                                             // W += -lr * grad   :626
+        w.x = __fadd_rn(w.x, __fmul_rn(neg_lr, qb[0])); w.y = __fadd_rn(w.y, __fmul_rn(neg_lr, qb[1]));
+        w.z = __fadd_rn(w.z, __fmul_rn(neg_lr, qb[2])); w.w = __fadd_rn(w.w, __fmul_rn(neg_lr, qb[3]));
+      } else {                                                                         // :618, :622
+        w.x = __fadd_rn(w.x, __fmul_rn(neg_lr, __fmul_rn(qb[0], s_bar)));
+        w.y = __fadd_rn(w.y, __fmul_rn(neg_lr, __fmul_rn(qb[1], s_bar)));
+        w.z = __fadd_rn(w.z, __fmul_rn(neg_lr, __fmul_rn(qb[2], s_bar)));
+        w.w = __fadd_rn(w.w, __fmul_rn(neg_lr, __fmul_rn(qb[3], s_bar)));
+      }
       w4[col] = w;
     }
   }
@@ -188,7 +200,7 @@ extern "C" int dqrm_grad_pack(int num_tables, int dim, const float* grad_sums, c
   DQRM_REQUIRE(grad_sums && uniq_rows && uniq_count && gathered_scales && slot && scale_mean, -EINVAL, "grad_pack: null argument");
   DQRM_REQUIRE(num_tables >= 1 && num_tables <= DQRM_MAX_TABLES, -E2BIG, "grad_pack: num_tables=%d", num_tables);
   DQRM_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= 512, -EINVAL, "grad_pack: dim=%d", dim);
-  DQRM_REQUIRE(bits >= 2 && bits <= 16, -EINVAL, "grad_pack: bits=%d outside [2,16]", bits);
+  DQRM_REQUIRE((bits >= 2 && bits <= 16) || bits == 32, -EINVAL, "grad_pack: bits=%d outside [2,16] and != 32", bits);
   DQRM_REQUIRE(world >= 1 && capacity >= 1, -EINVAL, "grad_pack: world=%d capacity=%lld", world, (long long)capacity);
   DQRM_REQUIRE((reinterpret_cast<uintptr_t>(slot) & 15u) == 0, -EINVAL, "grad_pack: slot not 16-byte aligned");
   const SlotLayout lay = slot_layout(num_tables, capacity, dim, bits);
@@ -202,7 +214,8 @@ extern "C" int dqrm_grad_pack(int num_tables, int dim, const float* grad_sums, c
   grad_pack_kernel<COLS, CT><<<grid, 256, 0, st>>>(num_tables, dim / 4, rl.group, grad_sums, uniq_rows, uniq_count, \
                                                    capacity, gathered_scales, world, inv_world, bits,              \
                                                    static_cast<unsigned char*>(slot), lay, scale_mean)
-  if (bits <= 8) { if (rl.cols == 1) DQRM_PACK(1, int8_t); else if (rl.cols == 2) DQRM_PACK(2, int8_t); else DQRM_PACK(4, int8_t); }
+  if (bits == 32) { if (rl.cols == 1) DQRM_PACK(1, float); else if (rl.cols == 2) DQRM_PACK(2, float); else DQRM_PACK(4, float); }
+  else if (bits <= 8) { if (rl.cols == 1) DQRM_PACK(1, int8_t); else if (rl.cols == 2) DQRM_PACK(2, int8_t); else DQRM_PACK(4, int8_t); }
   else           { if (rl.cols == 1) DQRM_PACK(1, int16_t); else if (rl.cols == 2) DQRM_PACK(2, int16_t); else DQRM_PACK(4, int16_t); }
 #undef DQRM_PACK
   DQRM_LAUNCH_CHECK("grad_pack_kernel");
@@ -216,7 +229,7 @@ extern "C" int dqrm_grad_merge_apply(int num_tables, float* const* weight, const
                                      int32_t* status, void* stream) {
   DQRM_REQUIRE(weight && rows && gathered && scale_mean && status, -EINVAL, "grad_merge_apply: null argument");
   DQRM_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= 512, -EINVAL, "grad_merge_apply: dim=%d", dim);
-  DQRM_REQUIRE(bits >= 2 && bits <= 16, -EINVAL, "grad_merge_apply: bits=%d outside [2,16]", bits);
+  DQRM_REQUIRE((bits >= 2 && bits <= 16) || bits == 32, -EINVAL, "grad_merge_apply: bits=%d outside [2,16] and != 32", bits);
   DQRM_REQUIRE(world >= 1 && world <= 65535 && capacity >= 1, -EINVAL, "grad_merge_apply: world=%d capacity=%lld", world, (long long)capacity);
   DQRM_REQUIRE((updated_rows == nullptr) == (updated_count == nullptr), -EINVAL, "grad_merge_apply: updated_rows/updated_count must come together");
   DQRM_REQUIRE(!qbar || updated_rows, -EINVAL, "grad_merge_apply: qbar needs updated_rows");
@@ -238,7 +251,8 @@ extern "C" int dqrm_grad_merge_apply(int num_tables, float* const* weight, const
   grad_merge_apply_kernel<COLS, CT><<<grid, 256, 0, st>>>(ts, dim / 4, rl.group, static_cast<const unsigned char*>(gathered), \
                                                           lay, world, capacity, scale_mean, neg_lr, inv_world,        \
                                                           updated_rows, updated_count, qbar, status)
-  if (bits <= 8) { if (rl.cols == 1) DQRM_MERGE(1, int8_t); else if (rl.cols == 2) DQRM_MERGE(2, int8_t); else DQRM_MERGE(4, int8_t); }
+  if (bits == 32) { if (rl.cols == 1) DQRM_MERGE(1, float); else if (rl.cols == 2) DQRM_MERGE(2, float); else DQRM_MERGE(4, float); }
+  else if (bits <= 8) { if (rl.cols == 1) DQRM_MERGE(1, int8_t); else if (rl.cols == 2) DQRM_MERGE(2, int8_t); else DQRM_MERGE(4, int8_t); }
   else           { if (rl.cols == 1) DQRM_MERGE(1, int16_t); else if (rl.cols == 2) DQRM_MERGE(2, int16_t); else DQRM_MERGE(4, int16_t); }
 #undef DQRM_MERGE
   DQRM_LAUNCH_CHECK("grad_merge_apply_kernel");

@@ -130,7 +130,7 @@ extern "C" int dqrm_blockmax_update(int num_tables, const float* const* weight, 
   size_t slot_bytes = 0, rows_off = 0, codes_off = 0;
   int ranks = 1;
   if (gathered) {
-    DQRM_REQUIRE(world >= 1 && world <= 65535 && bits >= 2 && bits <= 16, -EINVAL, "blockmax_update: world/bits");
+    DQRM_REQUIRE(world >= 1 && world <= 65535 && ((bits >= 2 && bits <= 16) || bits == 32), -EINVAL, "blockmax_update: world/bits");
     slot_bytes = dqrm_slot_bytes(num_tables, capacity, dim, bits);
     dqrm_slot_layout(num_tables, capacity, dim, bits, &rows_off, &codes_off);
     ranks = world;

@@ -221,6 +221,9 @@ class DLRM_Net(nn.Module):
         return g
 
     fuse_mlp = True               # fused QuantLinear+activation kernels over the dense arena (a15)
+    fuse_mlp_max_batch = 2048     # above this the weight-gradient GEMM's K (= batch) outgrows the 8-CTA cluster
+                                  # split and plain cuBLAS SGEMM (library) is faster: measured at batch 8192,
+                                  # Terabyte shape, 6.0 ms fused vs 2.1 ms cuBLAS for the non-scan part of the step
 
     def _fused_mlp_arena(self):
         """The dense arena if the fused MLP path applies (all layers quantised per channel on CUDA)."""
@@ -260,8 +263,14 @@ class DLRM_Net(nn.Module):
         fp = full_precision_flag or any(e.full_precision_flag for e in self.emb_l)
         idx, off, idx_begin, bags = EmbeddingTableGroup.pack_inputs(lS_i, lS_o, g.device)
         if ((not fp and not test_mode) or not g.scale_valid) and not self.external_scan:
-            g.scan_scales(shard_rank=g.dp_rank if self.shard_scan else 0,
-                          shard_world=g.dp_world if self.shard_scan else 1)
+            # periodic update (qm:303-315,354-363; the paper's period-200 numbers): after the first scan, rescan
+            # only when `scale_update_period` forwards have passed; 0 = every forward (the shipped behaviour)
+            if not g.scale_valid or self._since_scan >= self.scale_update_period:
+                g.scan_scales(shard_rank=g.dp_rank if self.shard_scan else 0,
+                              shard_world=g.dp_world if self.shard_scan else 1)
+                self._since_scan = 0
+            else:
+                self._since_scan += 1
         if not self._scale_views_bound:
             for t, e in enumerate(self.emb_l):
                 e.eb_scaling_factor = g.scale[t]
@@ -271,6 +280,8 @@ class DLRM_Net(nn.Module):
         ly.stacked, ly.group = out, g
         return ly
 
+    scale_update_period = 0       # 0: rescan every forward (shipped reference); P: rescan every P+1 forwards
+    _since_scan = 0
     shard_scan = False            # multi-GPU: scan 1/world of every table per rank + MAX all-reduce
     external_scan = False         # the caller launches group.scan_scales() itself before every forward
     _scale_views_bound = False
@@ -293,7 +304,7 @@ class DLRM_Net(nn.Module):
         if not self.quantization_flag or self.quantize_activation:
             raise NotImplementedError("only the --quantization_flag --linear_channel flow is built "
                                       "(dlrm_s_pytorch_comm_grad.py:855-859)")
-        self._mlp_arena = self._fused_mlp_arena()
+        self._mlp_arena = self._fused_mlp_arena() if dense_x.shape[0] <= self.fuse_mlp_max_batch else None
         if self._mlp_arena is not None:
             self._mlp_arena.fakequant_all()          # all 7 layers' weights + biases, one launch
         x = self.apply_mlp(dense_x, self.bot_l, prev_act_scaling_factor=None)
@@ -388,6 +399,10 @@ def make_parser():
     p.add_argument("--quantize_act_and_lin", action="store_true", default=False)
     p.add_argument("--quantize_embedding_bag_gradient", action="store_true", default=False)
     p.add_argument("--embedding_bag_gradient_bit_num", type=int, default=16)
+    p.add_argument("--scale-update-period", type=int, default=0,
+                   help="extension: rescan the tables for their scale every P+1 iterations (0 = every iteration)")
+    p.add_argument("--scale-policy", type=str, default="full", choices=["full", "incremental"],
+                   help="extension: full rescan (reference) or the exact incremental block-max tracker")
     p.add_argument("-n", "--nodes", default=1, type=int, metavar="N")
     p.add_argument("-g", "--gpus", default=1, type=int)
     p.add_argument("-nr", "--nr", default=0, type=int)

@@ -101,8 +101,10 @@ def grad_update_parallel_comm(model, number_of_gpus, emb_grad_quantized=True, nu
                     for t, e in enumerate(g.modules):
                         e.emb_scaling_factor = g.grad_scale_mean[t:t + 1]
             elif world > 1:
-                raise NotImplementedError("un-quantised embedding-gradient exchange across ranks is not built yet "
-                                          "(every DQRM script passes --quantize_embedding_bag_gradient)")
+                # emb_grad_quantized=False (sgd:319-329): same slots, fp32 payload, summed in rank order
+                if g.grad_bit != 32:
+                    g.set_grad_bit(32)
+                g.exchange(world=world, rank=rank)
         arena = _dense_arena(model)
         arena.quantize_exchange(world=world, bits=8, quantized=mlp_layer_quantized)
 
@@ -115,10 +117,10 @@ def weight_update_parallel_comm(model, lr, emb_grad_quantized=True, update_embed
     with torch.no_grad():
         if update_embedding:
             for g in _emb_groups(model):
-                if emb_grad_quantized:
+                if emb_grad_quantized or num_gpus > 1:
                     g.merge_apply(lr)
                 else:
-                    g.sgd_apply(lr, inv_world=1.0 / num_gpus)
+                    g.sgd_apply(lr, inv_world=1.0)
         _dense_arena(model).apply(lr, world=num_gpus, quantized=mlp_layer_quantized)
 
 

@@ -247,7 +247,7 @@ class EmbeddingTableGroup:
                                  dout.data_ptr(), dout.stride(0), dout.stride(1),
                                  None if (full_precision or ste_done) else self.scale.data_ptr(),
                                  self.capacity, self.uniq_rows.data_ptr(), self.uniq_count.data_ptr(),
-                                 self.grad_sums.data_ptr(), self.grad_bit, self.grad_scale_local.data_ptr(),
+                                 self.grad_sums.data_ptr(), min(self.grad_bit, 16), self.grad_scale_local.data_ptr(),
                                  self.status.data_ptr(), self._bwd_ws.data_ptr(), self._bwd_ws_bytes, st)
         _lib.check(rc, "dqrm_embbag_bwd")
 
@@ -259,10 +259,11 @@ class EmbeddingTableGroup:
         sb = int(self.lib.dqrm_slot_bytes(self.T, self.capacity, self.dim, self.grad_bit))
         self.slot_bytes = sb
         self.gathered = torch.zeros(self.world * sb, dtype=torch.uint8, device=self.device)
-        _lib.check(self.lib.dqrm_grad_absmax_scale(self.T, self.dim, self.grad_sums.data_ptr(),
-                                                   self.uniq_count.data_ptr(), self.capacity, self.grad_bit,
-                                                   self.grad_scale_local.data_ptr(), _lib.stream_ptr()),
-                   "dqrm_grad_absmax_scale")
+        if self.grad_bit != 32:
+            _lib.check(self.lib.dqrm_grad_absmax_scale(self.T, self.dim, self.grad_sums.data_ptr(),
+                                                       self.uniq_count.data_ptr(), self.capacity, self.grad_bit,
+                                                       self.grad_scale_local.data_ptr(), _lib.stream_ptr()),
+                       "dqrm_grad_absmax_scale")
 
     def topk(self, k):
         """(a8) keep the k highest-energy rows per table, then refresh the local scale."""
@@ -338,9 +339,9 @@ class EmbeddingTableGroup:
         s = self.gathered[rank * sb:(rank + 1) * sb]
         cnt = s[:self.T * 4].view(torch.int32)
         rows = s[ro.value:ro.value + self.T * self.capacity * 4].view(torch.int32).view(self.T, self.capacity)
-        cb = 1 if self.grad_bit <= 8 else 2
+        cb, dt = (4, torch.float32) if self.grad_bit == 32 else ((1, torch.int8) if self.grad_bit <= 8 else (2, torch.int16))
         codes = s[co.value:co.value + self.T * self.capacity * self.dim * cb]
-        codes = codes.view(torch.int8 if cb == 1 else torch.int16).view(self.T, self.capacity, self.dim)
+        codes = codes.view(dt).view(self.T, self.capacity, self.dim)
         return cnt, rows, codes
 
     def sparse_grad(self, t):

@@ -174,11 +174,14 @@ DQRM_API int dqrm_sgd_rows(int num_tables, float* const* weight, const int64_t* 
  *   s_bar[k] = (sum_r gathered_scales[r][k]) * (1/world), summed in rank order
  *              (all_reduce(SUM) then mul_(1./N), sgd...parallel_comm.py:865-866)
  *   q        = clamp(rint((1/s_bar) * sums), -2^(bits-1), 2^(bits-1)-1)   (:869)
+ * bits == 32 selects the UN-quantised exchange (emb_grad_quantized=False: coalesce, all-reduce, 1/N, W += -lr*g,
+ * sgd...parallel_comm.py:319-329, 626): the slot carries the fp32 sums, gathered_scales is ignored, and
+ * dqrm_grad_merge_apply sums them in rank order.
  * Slot layout (dqrm_slot_bytes; offsets from dqrm_slot_layout), fixed capacity
  * so one all-gather of `slot_bytes` per rank replaces the reference's Gloo
  * sparse all-reduce (:878):
  *   int32 count[num_tables] | int32 rows[num_tables][capacity] |
- *   int8 (bits<=8) or int16 codes[num_tables][capacity][dim]
+ *   int8 (bits<=8), int16 (bits<=16) or fp32 (bits==32) codes[num_tables][capacity][dim]
  *   gathered_scales dev [world, num_tables];  scale_mean dev [num_tables] out
  */
 DQRM_API size_t dqrm_slot_bytes(int num_tables, int64_t capacity, int dim, int bits);

@@ -280,6 +280,23 @@ def exchange_emb_grad_spec(per_rank, bits: int, num_rows: int):
     return dict(s_local=s_local, s_bar=s_bar, codes=codes, union_rows=union, qbar=qbar)
 
 
+def exchange_emb_grad_unquantized_spec(per_rank):
+    """emb_grad_quantized=False across N ranks (sgd:319-329): coalesce, sparse all-reduce(SUM) -- coinciding
+    rows summed in rank order --, ``mul_(1./N)``.  Returns (union_rows, gmean)."""
+    world = len(per_rank)
+    union = np.unique(np.concatenate([r for r, _ in per_rank]))
+    D = per_rank[0][1].shape[1]
+    acc = np.zeros((union.shape[0], D), dtype=F32)
+    seen = np.zeros(union.shape[0], dtype=bool)
+    for rows, sums in per_rank:
+        pos = np.searchsorted(union, rows)
+        first = ~seen[pos]
+        acc[pos[first]] = sums[first]
+        acc[pos[~first]] = (acc[pos[~first]] + sums[~first]).astype(F32)
+        seen[pos] = True
+    return union, (acc * F32(1.0 / world)).astype(F32)
+
+
 def weight_update_emb_spec(W: np.ndarray, union_rows, qbar, s_bar, lr: float) -> None:
     """W[row] += (-lr) * (qbar * s_bar), each product rounded to fp32, in that
     association (sgd:618,622).  In place."""

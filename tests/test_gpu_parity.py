@@ -367,3 +367,51 @@ def test_symmetric_quant_function_api():
     assert np.array_equal(cpu(q), O.quantize_spec(x, 8, srow))
     with pytest.raises(ValueError):
         qu.SymmetricQuantFunction.apply(xd, 4, None)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_unquantized_exchange_emulated_ranks(world):
+    """emb_grad_quantized=False across ranks: fp32 payload in the same slots, rank-ordered sums."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    rows, dim, B = [40, 3000], 16, 48
+    rng = np.random.RandomState(100 + world)
+    Ws = [synthetic.table_weights_numpy(n, dim, rng) for n in rows]
+    groups, per_rank = [], []
+    for r in range(world):
+        g = tables.EmbeddingTableGroup([torch.tensor(w, device="cuda") for w in Ws], embedding_bit=4)
+        X, lS_o, lS_i, T = synthetic.criteo_batch(rows, B, seed=150 + r, zipf=1.2)
+        idx, off, ib, bags = tables.EmbeddingTableGroup.pack_inputs(lS_i, lS_o, "cuda")
+        g.scan_scales()
+        g.forward(idx, off, ib, bags)
+        dout = (rng.randn(g.T, bags, dim) * 0.01).astype(np.float32)
+        g.backward(torch.tensor(dout, device="cuda"), world=world)
+        g.set_grad_bit(32)
+        g.keep_debug = True
+        groups.append(g)
+        per_rank.append((lS_i.numpy(), lS_o.numpy(), dout))
+    for r, g in enumerate(groups):
+        g.stage_scale(r)
+        g.pack(r)
+    sb = groups[0].slot_bytes
+    for g in groups:
+        for r2, g2 in enumerate(groups):
+            if g2 is not g:
+                g.gathered[r2 * sb:(r2 + 1) * sb].copy_(g2.gathered[r2 * sb:(r2 + 1) * sb])
+    for g in groups:
+        g.merge_apply(0.1)
+        g.check_status()
+    for t in range(len(rows)):
+        s = O.table_scale_spec(Ws[t], 4)
+        pr = []
+        for (li, lo, dout) in per_rank:
+            r0, v0 = O.embbag_backward_spec(dout[t], li[t], lo[t], s)
+            pr.append(O.coalesce_spec(r0, v0))
+        union, gmean = O.exchange_emb_grad_unquantized_spec(pr)
+        Wn = Ws[t].copy()
+        O.weight_update_emb_unquantized_spec(Wn, union, gmean, 0.1)
+        for g in groups:
+            nu = int(g.updated_count[t])
+            order = np.argsort(cpu(g.updated_rows[t, :nu]))
+            assert np.array_equal(cpu(g.updated_rows[t, :nu])[order], union)
+            assert bits_equal(cpu(g.qbar[t, :nu])[order], gmean)
+            assert bits_equal(cpu(g.weights[t]), Wn)

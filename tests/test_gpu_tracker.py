@@ -49,3 +49,49 @@ def test_tracker_bit_identical_to_full_scan(dim, quantized):
     inc.invalidate_tracker()
     full.scan_scales(); inc.scan_scales()
     assert torch.equal(full.scale, inc.scale)
+
+
+def test_periodic_scale_update_policy():
+    """--scale-update-period P: the scale is refreshed on the first forward and then every P+1 forwards
+    (the reference's commented-out bookkeeping, qm:303-315, 354-363)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import C_SMALL, build_cuda_model, emulated_dp_step, shard
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    m = build_cuda_model(C_SMALL)
+    m.scale_update_period = 2
+    scans = []
+    for step in range(7):
+        n0 = _lib.launch_counts["dqrm_table_absmax_scale"]
+        emulated_dp_step([m], [shard(1, 0, False, step, C_SMALL["rows"])], lr=0.1, keep_debug=False)
+        scans.append(_lib.launch_counts["dqrm_table_absmax_scale"] - n0)
+    assert scans == [1, 0, 0, 1, 0, 0, 1]
+
+
+def test_rwsadagrad_optimizer_class():
+    from deep_quantized_recommendation_model_dqrm_b200 import synthetic, tables
+    from deep_quantized_recommendation_model_dqrm_b200.optim.rwsadagrad import RWSAdagrad
+    rows, dim, B = [500, 7], 16, 64
+    rng = np.random.RandomState(8)
+    Ws = [synthetic.table_weights_numpy(n, dim, rng) for n in rows]
+    g = tables.EmbeddingTableGroup([torch.nn.Parameter(torch.tensor(w, device="cuda")) for w in Ws], embedding_bit=4)
+    opt = RWSAdagrad(g.weights, lr=0.05, eps=1e-10)
+    mom = opt.attach_table_group(g)
+    ref_m = [np.zeros(n, dtype=np.float32) for n in rows]
+    ref_W = [w.copy() for w in Ws]
+    for step in range(3):
+        X, lS_o, lS_i, T = synthetic.criteo_batch(rows, B, seed=30 + step)
+        idx, off, ib, bags = tables.EmbeddingTableGroup.pack_inputs(lS_i, lS_o, "cuda")
+        g.scan_scales(); g.forward(idx, off, ib, bags)
+        dout = torch.tensor(rng.randn(2, B, dim).astype(np.float32), device="cuda")
+        g.backward(dout, world=1)
+        for t in range(2):
+            U = int(g.uniq_count[t])
+            r = g.uniq_rows[t, :U].cpu().numpy().astype(np.int64)
+            v = g.grad_sums[t, :U].cpu().numpy()
+            ref_m[t][r] += (v ** 2).mean(axis=1)
+            ref_W[t][r] += -0.05 * (v / (np.sqrt(ref_m[t][r]) + 1e-10)[:, None])
+        opt.step()
+    for t in range(2):
+        np.testing.assert_allclose(mom[t].cpu().numpy(), ref_m[t], rtol=1e-5, atol=1e-12)
+        np.testing.assert_allclose(g.weights[t].detach().cpu().numpy(), ref_W[t], rtol=1e-5, atol=1e-7)
