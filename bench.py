@@ -288,7 +288,7 @@ def run_ours(args):
     dlrm.emb_group.check_status()
     final_loss = float(step.loss.item())
     extra = None
-    if args.scale_policy == "full" and not args.no_incremental_extra:
+    if args.scale_policy == "full" and not args.no_incremental_extra and world == 1:
         # the same step with the exact incremental scale tracker (bit-identical scales,
         # tests/test_gpu_tracker.py): reported beside the headline, never instead of it
         dlrm.emb_group.scale_policy = "incremental"
