@@ -7,6 +7,7 @@ against the CPU oracle (the reference's path restated, all host threads).
 Per grid point (rows N, dim D, pooling P, batch B) it times, with CUDA events after warm-up:
   scan      dqrm_table_absmax_scale                          bytes N*D*4
   fwd       dqrm_embbag_fwd (scale given)                    bytes L(4D+8) + B(8+4D) + B*D (int8 codes)
+  fwd_int4  dqrm_embbag_fwd_int4 on bit-packed tables        bytes L(D/2+8) + B(8+4D)
   bwd       dqrm_embbag_bwd + grad_pack + grad_merge_apply   bytes B*4D + L*8 + U*8D   
 and reports achieved GB/s on those ALGORITHMIC bytes (U = unique rows, counted on the device).
 Tables are larger than the 126 MB L2 for N >= 4M (D=16) so no flush is needed there; for smaller tables a
@@ -42,25 +43,56 @@ def gpu_point(N, D, P, B, iters=5, flush=None):
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
-    t = {"scan": [], "fwd": [], "bwd": []}
-    for it in range(iters + 2):
-        if flush is not None:
-            flush.add_(1.0)
-        e = [ev() for _ in range(4)]
-        e[0].record(); g.scan_scales()
-        e[1].record(); g.forward(idx, off, ib, B, out=out)
-        e[2].record(); g.backward(dout, world=1); g.exchange(world=1, rank=0); g.merge_apply(0.1)
-        e[3].record()
+
+    # every phase is captured in its own CUDA graph so that the timings are GPU time, not Python launch
+    # overhead (the forward kernels run for ~5 us)
+    def run_scan():
+        g.scan_scales()
+
+    def run_fwd():
+        g.forward(idx, off, ib, B, out=out)
+
+    def run_bwd():
+        g.backward(dout, world=1); g.exchange(world=1, rank=0); g.merge_apply(0.1)
+
+    def run_int4():
+        g.forward_int4(idx, off, ib, B, out=out)
+
+    g.scan_scales()
+    g.pack_int4()
+    phases = {"scan": run_scan, "fwd": run_fwd, "bwd": run_bwd, "fwd_int4": run_int4}
+    graphs = {}
+    side = torch.cuda.Stream()
+    for name, fn in phases.items():
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn()
         torch.cuda.synchronize()
-        if it >= 2:
-            t["scan"].append(e[0].elapsed_time(e[1])); t["fwd"].append(e[1].elapsed_time(e[2])); t["bwd"].append(e[2].elapsed_time(e[3]))
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        graphs[name] = gr
+    torch.cuda.synchronize()
+    t = {k: [] for k in phases}
+    for it in range(iters + 2):
+        for name in ("scan", "fwd", "bwd", "fwd_int4"):
+            if flush is not None:
+                flush.add_(1.0)
+            a, b = ev(), ev()
+            a.record(); graphs[name].replay(); b.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                t[name].append(a.elapsed_time(b))
     g.check_status()
     U = int(g.uniq_count[0].item())
     ms = {k: float(np.median(v)) for k, v in t.items()}
     by = {"scan": N * D * 4, "fwd": L * (4 * D + 8) + B * (8 + 4 * D) + B * D, "bwd": B * 4 * D + L * 8 + U * 8 * D}
+    t4 = t["fwd_int4"]
+    ms["fwd_int4"] = float(np.median(t4))
+    by["fwd_int4"] = L * (D // 2 + 8) + B * (8 + 4 * D)
     res = {"rows": N, "dim": D, "pooling": P, "batch": B, "lookups": L, "unique_rows": U, "ms": ms, "bytes": by,
            "GBps": {k: by[k] / (ms[k] * 1e-3) / 1e9 for k in ms},
-           "fwd_bwd_GBps_with_scan": sum(by.values()) / (sum(ms.values()) * 1e-3) / 1e9,
+           "fwd_bwd_GBps_with_scan": sum(by[k] for k in ("scan", "fwd", "bwd")) / (sum(ms[k] for k in ("scan", "fwd", "bwd")) * 1e-3) / 1e9,
            "fwd_bwd_GBps_gather_only": (by["fwd"] + by["bwd"]) / ((ms["fwd"] + ms["bwd"]) * 1e-3) / 1e9}
     del g, W
     torch.cuda.empty_cache()
@@ -111,7 +143,7 @@ def main():
             r = gpu_point(N, D, P, B, flush=flush if N * D * 4 < 512 * 1024 * 1024 else None)
             if a.cpu and N <= 4_000_000:
                 r["cpu"] = cpu_point(N, D, P, B)
-                r["speedup_vs_cpu"] = r["cpu"]["ms_total"] / sum(r["ms"].values())
+                r["speedup_vs_cpu"] = r["cpu"]["ms_total"] / sum(r["ms"][k] for k in ("scan", "fwd", "bwd"))
             f.write(json.dumps(r) + "\n")
             f.flush()
             print(json.dumps(r), flush=True)

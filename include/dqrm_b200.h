@@ -125,6 +125,23 @@ DQRM_API int dqrm_embbag_fwd(int num_tables, const float* const* weight, const i
                     float* out, int64_t out_table_stride, int64_t out_bag_stride,
                     void* codes, int32_t* status, void* stream);
 
+/* Bit-packed INT4 tables and the forward that reads them (north_star kernel 2; SURVEY.md section 8 f-4:
+ * the packed checkpoint / serving format next to this path; the reference's own inference path uses ATen
+ * quantized.embedding_bag_4bit_*, dlrm_s_pytorch.py:428-469).
+ *   dqrm_table_pack_int4 : code = clamp(rint(inv_scale_k * w), -8, 7) (quant_utils.py:101,343); element d of a
+ *                          row is stored in byte d/2, low nibble for even d.  packed[k] is dev [rows_k, dim/2].
+ *   dqrm_embbag_fwd_int4 : out[b] = scale_k * sum_{l in bag b} code(row_l): exact integer pooling, one multiply.
+ *                          Bit-identical to dqrm_embbag_fwd when every bag has one index (Criteo); for longer
+ *                          bags it is quantise-then-pool (serving), not the training pool-then-quantise.
+ * dim must be a multiple of 16 with dim/16 a power of two.
+ */
+DQRM_API int dqrm_table_pack_int4(int num_tables, const float* const* weight, const int64_t* rows, int dim,
+                                  const float* inv_scale, uint8_t* const* packed, void* stream);
+DQRM_API int dqrm_embbag_fwd_int4(int num_tables, const uint8_t* const* packed, const int64_t* rows, int dim,
+                                  const int64_t* indices, const int64_t* offsets, const int64_t* idx_begin,
+                                  int64_t bags, const float* scale, float* out, int64_t out_table_stride,
+                                  int64_t out_bag_stride, int32_t* status, void* stream);
+
 /* ------------------------------------------------- (a4 bwd, a5, a7 step 1-2) --
  * Sparse row gradient of (a3), de-duplicated: dy = (g*s)/s (autograd of
  * qm:393 then SymmetricQuantFunction.backward, quant_utils.py:348-363; no clip

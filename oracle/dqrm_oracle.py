@@ -211,6 +211,40 @@ def embbag_backward_spec(dout: np.ndarray, idx: np.ndarray, offsets: np.ndarray,
 
 
 # --------------------------------------------------------------------------
+# packed INT4 export / serving forward (SURVEY.md section 8 f-4)
+# --------------------------------------------------------------------------
+
+def pack_int4_spec(W: np.ndarray, scale) -> np.ndarray:
+    """[N, D] fp32 -> [N, D/2] bytes: code = clamp(rint((1/s) w), -8, 7) (qu:101,343); element d in byte d/2,
+    low nibble for even d."""
+    q = quantize_spec(W, 4, scale).astype(np.int8)
+    n = (q & 0x0F).astype(np.uint8)
+    return (n[:, 0::2] | (n[:, 1::2] << 4)).astype(np.uint8)
+
+
+def unpack_int4_spec(packed: np.ndarray) -> np.ndarray:
+    lo = (packed & 0x0F).astype(np.int8)
+    hi = (packed >> 4).astype(np.int8)
+    lo = np.where(lo > 7, lo - 16, lo)
+    hi = np.where(hi > 7, hi - 16, hi)
+    out = np.empty((packed.shape[0], packed.shape[1] * 2), dtype=np.int32)
+    out[:, 0::2], out[:, 1::2] = lo, hi
+    return out
+
+
+def embbag_forward_int4_spec(packed: np.ndarray, idx, offsets, scale) -> np.ndarray:
+    """out[b] = s * sum_l code(row_l): exact integer pooling of the stored codes, one fp32 multiply."""
+    codes = unpack_int4_spec(packed)
+    idx = np.asarray(idx, dtype=np.int64)
+    starts, ends = bag_bounds(offsets, idx.shape[0])
+    out = np.zeros((starts.shape[0], codes.shape[1]), dtype=np.int64)
+    for b, (a, e) in enumerate(zip(starts, ends)):
+        if e > a:
+            out[b] = codes[idx[a:e]].sum(axis=0)
+    return (out.astype(F32) * F32(scale)).astype(F32)
+
+
+# --------------------------------------------------------------------------
 # (a7 step 1) coalesce                                              sgd:859
 # --------------------------------------------------------------------------
 

@@ -197,3 +197,16 @@ def test_get_my_slice():
         for r in range(w):
             got += list(range(n))[O.get_my_slice(n, w, r)]
         assert got == list(range(n))
+
+
+def test_int4_pack_roundtrip_and_onehot_equivalence():
+    rng = np.random.RandomState(3)
+    W = synthetic.table_weights_numpy(257, 32, rng)
+    s = O.table_scale_spec(W, 4)
+    packed = O.pack_int4_spec(W, s)
+    assert packed.shape == (257, 16) and packed.dtype == np.uint8
+    assert np.array_equal(O.unpack_int4_spec(packed), O.quantize_spec(W, 4, s).astype(np.int32))
+    idx = rng.randint(0, 257, size=40)
+    off = np.arange(40)
+    _, _, out = O.embbag_forward_spec(W, idx, off, 4)
+    assert np.array_equal(O.embbag_forward_int4_spec(packed, idx, off, s), out)            # one-index bags
