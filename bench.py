@@ -54,10 +54,12 @@ def parse():
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-steps", type=int, default=5)
-    p.add_argument("--scale-policy", type=str, default="full", choices=["full", "incremental"],
-                   help="full = rescan all tables every step (reference semantics); incremental = exact block-max tracker")
-    p.add_argument("--no-incremental-extra", action="store_true",
-                   help="skip the additional measurement of the incremental tracker reported beside the headline")
+    p.add_argument("--scale-policy", type=str, default="pipelined", choices=["pipelined", "full", "incremental"],
+                   help="pipelined = full rescan of every table every step, overlapped with the step on a side stream "
+                        "(headline); full = the same rescan serialised in front of the forward; incremental = exact "
+                        "block-max tracker (reads only the touched blocks)")
+    p.add_argument("--no-extras", "--no-incremental-extra", dest="no_extras", action="store_true",
+                   help="skip the additional measurements (serial rescan, incremental tracker) reported beside the headline")
     return p.parse_args()
 
 
@@ -240,7 +242,9 @@ def run_ours(args):
     step = GraphedTrainStep(dlrm, *devb[0], lr=LR, world_size=world, rank=rank, grad_bits=8, warmup=3,
                             use_graph=not args.no_graph)
     n0 = _lib.total_launches()                                # count OUR kernel launches of one step: one more
-    step.scan(); step._body()                                 # eager iteration (the graph replays the same list)
+    with torch.cuda.stream(step.stream):
+        step.scan(); step._body()                             # eager iteration (the graphs replay the same list)
+    torch.cuda.synchronize()
     launches_per_step = _lib.total_launches() - n0
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
@@ -250,6 +254,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(step, K, W, from_host):
+        with torch.cuda.stream(step.stream):                 # high-priority stream of the step (graph_step.py)
+            return timed_on_stream(step, K, W, from_host)
+
+    def timed_on_stream(step, K, W, from_host):
         ev_scan = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         src = host if from_host else devb
@@ -261,11 +269,7 @@ def run_ours(args):
         e0.record()
         for i in range(K):
             step.load(*src[(W + i) % pool])
-            step.scan(events=ev_scan[i])
-            if step.graph is not None:
-                step.graph.replay()
-            else:
-                step._body()
+            step.run(events=ev_scan[i])                      # scan launch (event-bracketed on ITS stream) + replay
             if from_host:                                    # the reference reads the loss every step (:1928)
                 loss_host.copy_(step.loss, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
@@ -287,24 +291,30 @@ def run_ours(args):
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     dlrm.emb_group.check_status()
     final_loss = float(step.loss.item())
-    extra = None
-    if args.scale_policy == "full" and not args.no_incremental_extra and world == 1:
-        # the same step with the exact incremental scale tracker (bit-identical scales,
-        # tests/test_gpu_tracker.py): reported beside the headline, never instead of it
-        dlrm.emb_group.scale_policy = "incremental"
-        step2 = GraphedTrainStep(dlrm, *devb[0], lr=LR, world_size=world, rank=rank, grad_bits=8, warmup=3,
-                                 use_graph=not args.no_graph)
-        ms_inc, red_ms = timed(step2, args.steps, args.warmup, from_host=False)
-        ms_inc_e2e, _ = timed(step2, args.steps, args.warmup, from_host=True)
-        dlrm.emb_group.check_status()
-        extra = {"value": B * world * args.steps / (ms_inc / 1000.0), "unit": "samples/s",
-                 "ms_per_step": ms_inc / args.steps,
-                 "e2e_value": B * world * args.steps / (ms_inc_e2e / 1000.0),
-                 "blockmax_reduce_ms": red_ms,
-                 "note": "exact block-max tracker instead of the full rescan: scales bit-identical to the rescan "
-                         "(SURVEY.md 8 f-1); not the headline because the reference rescans every step"}
-        dlrm.emb_group.scale_policy = "full"
-        del step2
+    extras = {}
+    if args.scale_policy == "pipelined" and not args.no_extras:
+        # the same step with (a) the rescan serialised in front of the forward, as the reference orders it, and
+        # (b, N=1) the exact incremental tracker; reported beside the headline, never instead of it
+        variants = [("serial_rescan", "full", "same full rescan, serialised before the forward (reference order)")]
+        if world == 1:
+            variants.append(("incremental_scale_tracker", "incremental",
+                             "exact block-max tracker: reads only the touched blocks; scales bit-identical to the "
+                             "rescan (SURVEY.md 8 f-1); not the headline because the reference rescans every step"))
+        for key, policy, note in variants:
+            dlrm.emb_group.scale_policy = policy
+            dlrm.emb_group.scale_valid = False
+            step2 = GraphedTrainStep(dlrm, *devb[0], lr=LR, world_size=world, rank=rank, grad_bits=8, warmup=3,
+                                     use_graph=not args.no_graph)
+            ms2, scan2 = timed(step2, args.steps, args.warmup, from_host=False)
+            ms2_e2e, _ = timed(step2, args.steps, args.warmup, from_host=True)
+            dlrm.emb_group.check_status()
+            extras[key] = {"value": B * world * args.steps / (ms2 / 1000.0), "unit": "samples/s",
+                           "ms_per_step": ms2 / args.steps,
+                           "e2e_value": B * world * args.steps / (ms2_e2e / 1000.0),
+                           "scan_kernel_ms": scan2, "note": note}
+            del step2
+        dlrm.emb_group.scale_policy = args.scale_policy
+        dlrm.emb_group.scale_valid = False
 
     gbatch = B * world
     value = gbatch * args.steps / (ms_dev / 1000.0)
@@ -327,8 +337,11 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}-shape DQRM: {len(cfg['rows'])} tables ({sum(cfg['rows'])} rows, "
                                f"{table_bytes / 1e9:.3f} GB fp32), dim {cfg['dim']}, INT4 emb+MLP QAT, INT8 grad exchange, "
                                f"batch {B}/GPU", "global_batch": gbatch, "parallelism": f"dp{world}",
-                   "scale_scan": ("exact incremental block-max tracker" if args.scale_policy == "incremental" else
-                                  "full rescan every step (reference period-1 semantics)" +
+                   "scale_scan": ({"incremental": "exact incremental block-max tracker",
+                                   "full": "full rescan every step (reference period-1 semantics), serialised before the forward",
+                                   "pipelined": "full rescan every step (every table byte read once per step, reference "
+                                                "period-1 semantics), overlapped with the step on a low-priority stream; "
+                                                "blocks holding updated rows are re-read after the update"}[args.scale_policy] +
                                   (", row-sharded 1/N + MAX all-reduce" if dlrm.shard_scan else "")),
                    "l2": "table arena (2.16 GB) is 17x the 126 MB L2: inputs larger than L2, no flush needed",
                    "cuda_graph": step.graph is not None, "final_loss": final_loss},
@@ -336,16 +349,16 @@ def run_ours(args):
                 "h2d_bytes_per_step": step.input_bytes(), "d2h_bytes_per_step": 4},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
-        "roofline": {"kernel": "table_absmax_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": {"pipelined": "blockmax_scan_kernel", "full": "table_absmax_kernel",
+                                "incremental": "table_absmax_kernel (block maxima)"}[args.scale_policy], "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_SCAN_TRAFFIC.get((args.workload, world)),
+                     "traffic": NCU_SCAN_TRAFFIC.get((args.workload, world, args.scale_policy)),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": scan_ms,
                      "share_of_step": scan_ms / (ms_dev / args.steps)},
         "clocks": clocks,
     }
-    if extra is not None:
-        line["incremental_scale_tracker"] = extra
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         del step, dlrm
         torch.cuda.empty_cache()
@@ -360,7 +373,7 @@ def run_ours(args):
 
 # DRAM traffic of one table_absmax_kernel launch from `ncu --set full` (dram__bytes_read.sum +
 # dram__bytes_write.sum, profiles/r01_scan_kernel_ncu_full.txt); valid for the full (unsharded) Kaggle scan.
-NCU_SCAN_TRAFFIC = {("kaggle", 1): 2.1647e9 + 3.9e6}
+NCU_SCAN_TRAFFIC = {("kaggle", 1, "full"): 2.1647e9 + 3.9e6}
 
 
 def main():

@@ -30,6 +30,9 @@ SIGNATURES = {
     "dqrm_blockmax_entries": (_i64, [_i64, _i32]),
     "dqrm_blockmax_build": (_i32, [_i32, _p, _p, _i32, _i32, _p, _p]),
     "dqrm_blockmax_update": (_i32, [_i32, _p, _p, _i32, _i32, _p, _p, _i32, _i64, _i32, _p, _p, _p]),
+    "dqrm_blockmax_scan": (_i32, [_i32, _p, _p, _i32, _i32, _p, _i32, _i32, _p]),
+    "dqrm_blockmax_update_shard": (_i32, [_i32, _p, _p, _i32, _i32, _p, _p, _i32, _i64, _i32, _p, _p, _i32, _i32, _p]),
+    "dqrm_blockmax_reduce": (_i32, [_i32, _p, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "dqrm_embbag_fwd": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _p, _p, _i32, _p, _i64, _i64, _p, _p, _p]),
     "dqrm_table_pack_int4": (_i32, [_i32, _p, _p, _i32, _p, _p, _p]),
     "dqrm_embbag_fwd_int4": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _p, _p, _i64, _i64, _p, _p]),
@@ -62,7 +65,8 @@ LAUNCHING = ("dqrm_table_absmax_scale", "dqrm_scale_from_absmax", "dqrm_embbag_f
              "dqrm_grad_absmax_scale", "dqrm_sgd_rows", "dqrm_grad_pack", "dqrm_grad_topk", "dqrm_grad_merge_apply",
              "dqrm_interact_fwd", "dqrm_interact_bwd", "dqrm_linear_fakequant", "dqrm_fake_quant",
              "dqrm_mlp_fakequant_all", "dqrm_linear_fwd", "dqrm_linear_bwd",
-             "dqrm_blockmax_build", "dqrm_blockmax_update", "dqrm_table_pack_int4", "dqrm_embbag_fwd_int4",
+             "dqrm_blockmax_build", "dqrm_blockmax_update", "dqrm_blockmax_scan", "dqrm_blockmax_update_shard",
+             "dqrm_blockmax_reduce", "dqrm_table_pack_int4", "dqrm_embbag_fwd_int4",
              "dqrm_dense_grad_scale", "dqrm_dense_grad_quant", "dqrm_dense_apply")
 launch_counts = {}
 

@@ -13,6 +13,8 @@
 // no split-K: the summation order is fixed, so data-parallel replicas stay bit-identical.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dqrm {
@@ -248,8 +250,9 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
 
 // cluster size: enough K-slices to put >= ~128 CTAs on the chip, each slice >= 2 K-tiles
 static int pick_split(int tiles, int K) {
+  static const int max_s = [] { const char* e = getenv("DQRM_MLP_MAX_CLUSTER"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   int S = 1;
-  while (S < 8 && tiles * S < 128 && K / (S * 2) >= 2 * BK) S *= 2;
+  while (S < max_s && tiles * S < 128 && K / (S * 2) >= 2 * BK) S *= 2;
   return S;
 }
 
@@ -273,7 +276,7 @@ static int launch_gemm(const float* x, const float* W_int, const float* b_int, c
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = S > 1 ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, linear_gemm_kernel<MODE>, x, W_int, b_int, s_row, dout, out, C, db, batch,
                                      out_f, in_f, act, kc, accumulate);
   if (e != cudaSuccess) { set_error("linear_gemm_kernel<%d>: %s", MODE, cudaGetErrorString(e)); return -EIO; }

@@ -72,7 +72,7 @@ class DenseArena:
         self.fused_ok = n <= 16 and len({l.weight_bit for l in self.layers}) == 1 and \
             all((l.bias is None) or (l.quantize_bias and l.bias_bit == l.weight_bit) for l in self.layers)
         # weight-gradient GEMMs run on a side stream, off the critical dx chain (None = same stream)
-        self.side_stream = torch.cuda.Stream(device=device) if self.flat.is_cuda else None
+        self.side_stream = torch.cuda.Stream(device=device, priority=-1) if self.flat.is_cuda else None
         self.keepalive = []
         for l in self.layers:
             l._arena = self

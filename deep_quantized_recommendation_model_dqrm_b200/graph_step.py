@@ -1,4 +1,4 @@
-"""The custom-DP training iteration (dlrm_s_pytorch_comm_grad.py:1909-1957) captured as a CUDA graph.
+"""The custom-DP training iteration (dlrm_s_pytorch_comm_grad.py:1909-1957) captured as CUDA graphs.
 
 The reference step is launch- and sync-bound (~1.6k ATen launches, >= 53 host syncs, 80 Gloo
 collectives at Kaggle shape).  Every kernel of this implementation is sync-free and its shapes are
@@ -18,7 +18,12 @@ class GraphedTrainStep:
     def __init__(self, dlrm, X, lS_o, lS_i, T, lr, world_size=1, rank=0, grad_bits=8, warmup=3, use_graph=True,
                  mlp_layer_quantized=True):
         """X, lS_o, lS_i, T: an example LOCAL batch (this rank's shard) fixing the static shapes;
-        lS_i / lS_o must be stacked [T, B] tensors (Criteo shape)."""
+        lS_i / lS_o must be stacked [T, B] tensors (Criteo shape).
+
+        With ``group.scale_policy == "pipelined"`` the table rescan runs on the group's low-priority side stream
+        concurrently with the step (tables.py); the step itself must then run on ``self.stream`` (high priority)
+        so that its short kernels are scheduled ahead of the scan's CTAs:
+        ``with torch.cuda.stream(step.stream): step.load(...); step.run()``."""
         self.dlrm, self.lr, self.world, self.rank = dlrm, float(lr), world_size, rank
         self.grad_bits = grad_bits
         self.mlp_layer_quantized = mlp_layer_quantized
@@ -31,19 +36,37 @@ class GraphedTrainStep:
         self.loss = torch.zeros((), device=dev)
         self.group = dlrm._ensure_group()
         self.group.dp_world, self.group.dp_rank = world_size, rank
+        self.pipelined = self.group.scale_policy == "pipelined"
+        self.stream = torch.cuda.Stream(device=dev, priority=-1)
         dlrm.external_scan = True
-        self.graph = None
-        self.scan()
-        for _ in range(max(warmup, 1)):               # eager warm-up: creates arenas / step buffers / cuBLAS handles
+        self.graph = self.graph_b = None
+        torch.cuda.synchronize()
+        with torch.cuda.stream(self.stream):
+            self.group.pipe_external_join = False
             self.scan()
-            self._body()
-        if use_graph:
+            for _ in range(max(warmup, 1)):           # eager warm-up: creates arenas / step buffers / cuBLAS handles
+                self.scan()
+                self._body_a()
+                self._body_b()
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            self.scan()
-            with torch.cuda.graph(self.graph):
-                self._body()
-            torch.cuda.synchronize()
+            if use_graph:
+                self.scan()
+                self.graph = torch.cuda.CUDAGraph()
+                if self.pipelined:
+                    # two graphs: everything that does not need the scan (A), then update + fix-up + reduce (B);
+                    # run() orders B after the side-stream pass with an event wait between the two replays
+                    self.group.pipe_external_join = True
+                    with torch.cuda.graph(self.graph, stream=self.stream):
+                        self._body_a()
+                    torch.cuda.current_stream().wait_event(self.group.pipe_event)
+                    self.graph_b = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph_b, pool=self.graph.pool(), stream=self.stream):
+                        self._body_b()
+                else:
+                    with torch.cuda.graph(self.graph, stream=self.stream):
+                        self._body_a()
+                        self._body_b()
+                torch.cuda.synchronize()
 
     def scan(self, events=None):
         """(a1) one launch for all tables; with world > 1 each rank scans 1/world of the rows."""
@@ -52,7 +75,7 @@ class GraphedTrainStep:
         g.scan_scales(shard_rank=self.rank if sharded else 0, shard_world=self.world if sharded else 1,
                       events=events)
 
-    def _body(self):
+    def _body_a(self):
         d = self.dlrm
         Z = d(self.X, self.lS_o, self.lS_i)
         E = torch.nn.functional.binary_cross_entropy(Z, self.T)
@@ -61,10 +84,18 @@ class GraphedTrainStep:
         drv.grad_update_parallel_comm(d, self.world, emb_grad_quantized=True, num_bits=self.grad_bits,
                                       ranking_range=False, rank_for_debug=self.rank,
                                       mlp_layer_quantized=self.mlp_layer_quantized)
-        drv.weight_update_parallel_comm(d, self.lr, emb_grad_quantized=True, update_embedding=True,
+        self.loss.copy_(E.detach())
+
+    def _body_b(self):
+        drv.weight_update_parallel_comm(self.dlrm, self.lr, emb_grad_quantized=True, update_embedding=True,
                                         num_gpus=self.world, rank_for_debug=self.rank,
                                         mlp_layer_quantized=self.mlp_layer_quantized)
-        self.loss.copy_(E.detach())
+
+    def _body(self):
+        self._body_a()
+        if self.pipelined and self.group.pipe_external_join:
+            torch.cuda.current_stream().wait_event(self.group.pipe_event)
+        self._body_b()
 
     def load(self, X, lS_o, lS_i, T):
         """Refill the static inputs (host pinned or device tensors); asynchronous."""
@@ -73,13 +104,20 @@ class GraphedTrainStep:
         self.lS_i.copy_(lS_i, non_blocking=True)
         self.T.copy_(T, non_blocking=True)
 
-    def run(self):
-        """scan + (graph replay | eager body); returns the device loss tensor (no sync)."""
-        self.scan()
-        if self.graph is not None:
-            self.graph.replay()
-        else:
+    def replay(self):
+        """Everything after the scan launch, on the current stream."""
+        if self.graph is None:
             self._body()
+            return
+        self.graph.replay()
+        if self.graph_b is not None:
+            torch.cuda.current_stream().wait_event(self.group.pipe_event)
+            self.graph_b.replay()
+
+    def run(self, events=None):
+        """scan + (graph replay | eager body); returns the device loss tensor (no sync)."""
+        self.scan(events)
+        self.replay()
         return self.loss
 
     def input_bytes(self):

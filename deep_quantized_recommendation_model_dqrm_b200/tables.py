@@ -60,8 +60,16 @@ class EmbeddingTableGroup:
         self._bwd_ws = None
         self.last = None          # (indices, offsets, idx_begin, idx_begin_arr, bags, full_precision)
         # (a1) scale policy: "full" = rescan every table on every call (reference semantics, HBM-bound);
-        # "incremental" = exact block-max tracker (bit-identical scales, O(touched rows) per step)
+        # "incremental" = exact block-max tracker (bit-identical scales, O(touched rows) per step);
+        # "pipelined" = full rescan of every table on every step, but overlapped with the step on a side stream
+        #               (block maxima + fix-up of the updated blocks after the row update; bit-identical scales)
         self.scale_policy = "full"
+        self.pipe_stream = None            # side stream of the pipelined rescan (created on first use)
+        self.pipe_event = None             # recorded after the block-max pass
+        self.pipe_pending = False          # a block-max pass was issued since the last table update
+        self.pipe_shard = (0, 1)
+        self.pipe_group = None             # process group of the MAX all-reduce when the pass is row-sharded
+        self.pipe_external_join = False    # the caller orders update-after-scan itself (graph replay)
         self.block_rows = 64
         self._bm_buf = None
         self._bm_valid = False
@@ -149,6 +157,8 @@ class EmbeddingTableGroup:
         self.scale_valid = True
 
     def _tracker_update(self, from_slots):
+        if self.scale_policy == "pipelined":
+            return self._pipe_finish(from_slots)
         if self.scale_policy != "incremental" or not self._bm_valid:
             return
         st = _lib.stream_ptr()
@@ -162,6 +172,78 @@ class EmbeddingTableGroup:
                                                self.uniq_rows.data_ptr(), self.uniq_count.data_ptr(), st)
         _lib.check(rc, "dqrm_blockmax_update")
 
+    # ---- (a1) pipelined full rescan ----------------------------------------
+    def _pipe_reduce(self):
+        """Block maxima of this rank's shard -> absmax -> (MAX all-reduce) -> scale, on the current stream."""
+        lib, st = self.lib, _lib.stream_ptr()
+        r, w = self.pipe_shard
+        sharded = w > 1
+        rc = lib.dqrm_blockmax_reduce(self.T, self._rows_arr, self.block_rows, self._bm_ptrs, r, w, self.embedding_bit,
+                                      self.absmax.data_ptr(), None if sharded else self.scale.data_ptr(),
+                                      None if sharded else self.inv_scale.data_ptr(), self._scan_ws.data_ptr(), st)
+        _lib.check(rc, "dqrm_blockmax_reduce")
+        if sharded:
+            import torch.distributed as dist
+            dist.all_reduce(self.absmax, op=dist.ReduceOp.MAX, group=self.pipe_group)
+            _lib.check(lib.dqrm_scale_from_absmax(self.T, self.absmax.data_ptr(), self.embedding_bit,
+                                                  self.scale.data_ptr(), self.inv_scale.data_ptr(), st),
+                       "dqrm_scale_from_absmax")
+        self.scale_valid = True
+
+    def _pipe_pass(self, events=None):
+        """The HBM-bound part: every byte of this rank's shard once -> block maxima (current stream)."""
+        r, w = self.pipe_shard
+        if events is not None:
+            events[0].record()
+        rc = self.lib.dqrm_blockmax_scan(self.T, self._wptrs(), self._rows_arr, self.dim, self.block_rows,
+                                         self._bm_ptrs, r, w, _lib.stream_ptr())
+        if events is not None:
+            events[1].record()
+        _lib.check(rc, "dqrm_blockmax_scan")
+
+    def _pipelined_scan(self, shard_rank, shard_world, process_group, events):
+        """Called where the reference rescans (before a forward).  The scale of THIS forward was produced by the
+        previous update's fix-up (or is bootstrapped here); the pass issued now, on the side stream, feeds the
+        scale of the NEXT forward and overlaps with this step."""
+        self._ensure_blockmax()
+        if (shard_rank, shard_world) != self.pipe_shard:
+            self.pipe_shard, self.scale_valid = (shard_rank, shard_world), False
+        self.pipe_group = process_group
+        cur = torch.cuda.current_stream()
+        if not self.scale_valid:                       # bootstrap: serial pass + reduce
+            self._pipe_pass()
+            self._pipe_reduce()
+        if self.pipe_stream is None:
+            self.pipe_stream = torch.cuda.Stream(device=self.device)      # default (lowest) priority
+            self.pipe_event = torch.cuda.Event()
+        side = self.pipe_stream
+        side.wait_stream(cur)                          # the tables are final as of the current stream
+        with torch.cuda.stream(side):
+            self._pipe_pass(events)
+            self.pipe_event.record(side)
+        self.pipe_pending = True
+
+    def _pipe_finish(self, from_slots):
+        """After a row update: recompute the touched blocks, reduce -> scale of the next forward."""
+        if not self.pipe_pending:
+            self.scale_valid = False                   # tables changed with no pass in flight: next scan bootstraps
+            return
+        if not self.pipe_external_join:
+            torch.cuda.current_stream().wait_event(self.pipe_event)
+        st = _lib.stream_ptr()
+        r, w = self.pipe_shard
+        if from_slots:
+            rc = self.lib.dqrm_blockmax_update_shard(self.T, self._wptrs(), self._rows_arr, self.dim, self.block_rows,
+                                                     self._bm_ptrs, self.gathered.data_ptr(), self.world,
+                                                     self.capacity, self.grad_bit, None, None, r, w, st)
+        else:
+            rc = self.lib.dqrm_blockmax_update_shard(self.T, self._wptrs(), self._rows_arr, self.dim, self.block_rows,
+                                                     self._bm_ptrs, None, 0, self.capacity, self.grad_bit,
+                                                     self.uniq_rows.data_ptr(), self.uniq_count.data_ptr(), r, w, st)
+        _lib.check(rc, "dqrm_blockmax_update_shard")
+        self._pipe_reduce()
+        self.pipe_pending = False
+
     # ---- (a1) -----------------------------------------------------------
     def scan_scales(self, shard_rank=0, shard_world=1, process_group=None, events=None):
         """Recompute every table's scale from a full max-abs pass (one launch).
@@ -169,6 +251,8 @@ class EmbeddingTableGroup:
         are combined with a MAX all-reduce (replicas are bit-identical)."""
         if self.scale_policy == "incremental":
             return self._tracker_scan(events)
+        if self.scale_policy == "pipelined":
+            return self._pipelined_scan(shard_rank, shard_world, process_group, events)
         lib, st = self.lib, _lib.stream_ptr()
         sharded = shard_world > 1
         if events is not None:            # (start, end) CUDA events bracketing exactly the scan kernel

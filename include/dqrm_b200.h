@@ -103,6 +103,31 @@ DQRM_API int dqrm_blockmax_update(int num_tables, const float* const* weight, co
                                   const void* gathered, int world, int64_t capacity, int bits,
                                   const int32_t* uniq_rows, const int32_t* uniq_count, void* stream);
 
+/* Pipelined form of the period-1 rescan (a1).  The reference serialises a full min/max pass over every table in
+ * front of every forward (quant_modules_not_quantize_grad.py:337 -> quant_utils.py:177-178).  The tables are
+ * read-only between two updates, so the pass that yields the scale of step i+1 can run concurrently with step i:
+ *   dqrm_blockmax_scan          (any stream, typically a low-priority one) reads this rank's shard of every table
+ *                               once and writes one max|w| per block of `block_rows` rows;
+ *   dqrm_blockmax_update_shard  (after the row update) recomputes the blocks that hold an updated row;
+ *   dqrm_blockmax_reduce        block maxima -> absmax[T] (and scale / 1/scale when scale != NULL; with
+ *                               shard_world > 1 pass scale == NULL, MAX-all-reduce absmax, then
+ *                               dqrm_scale_from_absmax).
+ * Every table byte is still read once per step, nothing is carried from one step to the next, and the scale is
+ * bit-identical to dqrm_table_absmax_scale (max is exact and order-free).  Shards are balanced contiguous block
+ * ranges (the get_my_slice rule, dlrm_s_pytorch_comm_grad.py:993-997, applied to blocks); the three calls must
+ * use the same (shard_rank, shard_world).  dim must be a multiple of 4; workspace as dqrm_scan_workspace_bytes. */
+DQRM_API int dqrm_blockmax_scan(int num_tables, const float* const* weight, const int64_t* rows, int dim,
+                                int block_rows, float* const* blockmax, int shard_rank, int shard_world,
+                                void* stream);
+DQRM_API int dqrm_blockmax_update_shard(int num_tables, const float* const* weight, const int64_t* rows, int dim,
+                                        int block_rows, float* const* blockmax,
+                                        const void* gathered, int world, int64_t capacity, int bits,
+                                        const int32_t* uniq_rows, const int32_t* uniq_count,
+                                        int shard_rank, int shard_world, void* stream);
+DQRM_API int dqrm_blockmax_reduce(int num_tables, const int64_t* rows, int block_rows, const float* const* blockmax,
+                                  int shard_rank, int shard_world, int bits, float* absmax, float* scale,
+                                  float* inv_scale, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------ (a3) --
  * Fused gather + sum-pool + fake-quantise + dequantise for all tables in one
  * launch.  Replaces QuantEmbeddingBagTwo.forward steps (ii)-(iv)

@@ -7,21 +7,22 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _two_groups(rows, dim, seed):
+def _two_groups(rows, dim, seed, policy="incremental"):
     from deep_quantized_recommendation_model_dqrm_b200 import synthetic, tables
     rng = np.random.RandomState(seed)
     Ws = [synthetic.table_weights_numpy(n, dim, rng) for n in rows]
     a = tables.EmbeddingTableGroup([torch.tensor(w, device="cuda") for w in Ws], embedding_bit=4)
     b = tables.EmbeddingTableGroup([torch.tensor(w, device="cuda") for w in Ws], embedding_bit=4)
-    b.scale_policy = "incremental"
+    b.scale_policy = policy
     return a, b, rng
 
 
-@pytest.mark.parametrize("dim,quantized", [(16, True), (64, True), (16, False)])
-def test_tracker_bit_identical_to_full_scan(dim, quantized):
+@pytest.mark.parametrize("policy", ["incremental", "pipelined"])
+@pytest.mark.parametrize("dim,quantized", [(16, True), (64, True), (16, False), (8, True)])
+def test_tracker_bit_identical_to_full_scan(dim, quantized, policy):
     from deep_quantized_recommendation_model_dqrm_b200 import synthetic, tables
     rows = [3, 70, 1000, 4097, 50000]
-    full, inc, rng = _two_groups(rows, dim, 21)
+    full, inc, rng = _two_groups(rows, dim, 21, policy)
     B = 256
     for step in range(6):
         X, lS_o, lS_i, T = synthetic.criteo_batch(rows, B, seed=70 + step, zipf=1.3 if step % 2 else None)
@@ -30,8 +31,10 @@ def test_tracker_bit_identical_to_full_scan(dim, quantized):
                 lS_i[k, 0] = int(w.abs().max(dim=1)[0].argmax())
         idx, off, ib, bags = tables.EmbeddingTableGroup.pack_inputs(lS_i, lS_o, "cuda")
         dout = torch.tensor(rng.randn(len(rows), B, dim).astype(np.float32) * (5.0 if step >= 3 else 0.05), device="cuda")
+        used = []
         for g in (full, inc):
             g.scan_scales()
+            used.append(g.scale.clone())             # the scale this step's forward quantises with
             g.forward(idx, off, ib, bags)
             g.backward(dout, world=1)
             if quantized:
@@ -39,16 +42,89 @@ def test_tracker_bit_identical_to_full_scan(dim, quantized):
                 g.merge_apply(0.5)
             else:
                 g.sgd_apply(0.5)
-        assert torch.equal(full.scale, inc.scale), step
+        assert torch.equal(used[0], used[1]), step
         for wa, wb in zip(full.weights, inc.weights):
             assert torch.equal(wa, wb)
     full.scan_scales(); inc.scan_scales()
     assert torch.equal(full.absmax, inc.absmax) and torch.equal(full.scale, inc.scale) and torch.equal(full.inv_scale, inc.inv_scale)
     # external mutation: a replaced table is detected, an in-place one needs invalidate_tracker()
+    torch.cuda.synchronize()
     inc.weights[2].mul_(3.0); full.weights[2].mul_(3.0)
     inc.invalidate_tracker()
+    inc.scale_valid = False          # pipelined: forces the bootstrap pass
     full.scan_scales(); inc.scan_scales()
     assert torch.equal(full.scale, inc.scale)
+
+
+@pytest.mark.parametrize("dim,world", [(16, 1), (16, 3), (64, 8), (128, 2)])
+def test_pipelined_scan_shards_cover_every_block(dim, world):
+    """dqrm_blockmax_scan / _reduce on every shard of a W-way split: the MAX over the shards' absmax equals the
+    full scan bit-for-bit, block maxima equal ATen's per-block abs().max(), and the fix-up honours the shard."""
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib, synthetic, tables
+    rows = [1, 63, 64, 65, 1000, 4097, 200000]
+    rng = np.random.RandomState(3)
+    Ws = [torch.tensor(synthetic.table_weights_numpy(n, dim, rng), device="cuda") for n in rows]
+    g = tables.EmbeddingTableGroup(Ws, embedding_bit=4)
+    g.scan_scales()
+    want_absmax = g.absmax.clone()
+    lib, st = g.lib, _lib.stream_ptr()
+    g._ensure_blockmax()
+    g._bm_buf.fill_(-1.0)
+    parts = []
+    for r in range(world):
+        _lib.check(lib.dqrm_blockmax_scan(g.T, g._wptrs(), g._rows_arr, dim, g.block_rows, g._bm_ptrs, r, world, st), "scan")
+        am = torch.zeros(g.T, device="cuda")
+        _lib.check(lib.dqrm_blockmax_reduce(g.T, g._rows_arr, g.block_rows, g._bm_ptrs, r, world, 4, am.data_ptr(), None,
+                                            None, g._scan_ws.data_ptr(), st), "reduce")
+        parts.append(am)
+    assert torch.equal(torch.stack(parts).max(dim=0)[0], want_absmax)
+    for k, (n, W) in enumerate(zip(rows, Ws)):
+        nb = (n + 63) // 64
+        pad = torch.zeros((nb * 64, dim), device="cuda")
+        pad[:n] = W.abs()
+        assert torch.equal(g._bm_views[k][:nb], pad.view(nb, -1).max(dim=1)[0]), k
+    # unsharded reduce with scale output == the full scan's scale
+    sc, inv, am = torch.zeros(g.T, device="cuda"), torch.zeros(g.T, device="cuda"), torch.zeros(g.T, device="cuda")
+    _lib.check(lib.dqrm_blockmax_reduce(g.T, g._rows_arr, g.block_rows, g._bm_ptrs, 0, 1, 4, am.data_ptr(), sc.data_ptr(),
+                                        inv.data_ptr(), g._scan_ws.data_ptr(), st), "reduce")
+    assert torch.equal(sc, g.scale) and torch.equal(inv, g.inv_scale) and torch.equal(am, want_absmax)
+
+
+def test_pipelined_graph_step_matches_serial_rescan():
+    """GraphedTrainStep with the overlapped rescan (two graphs + side stream) against the serial rescan:
+    losses, scales and every table bit-identical over several iterations."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import build_cuda_model
+    from deep_quantized_recommendation_model_dqrm_b200 import synthetic
+    from deep_quantized_recommendation_model_dqrm_b200.graph_step import GraphedTrainStep
+    cfg = dict(rows=[50, 3, 100000, 2000, 70000], dim=16, ln_bot=[13, 32, 16], ln_top_hidden=[32, 1])
+    B = 64
+    batches = [synthetic.criteo_batch(cfg["rows"], B, seed=900 + i, zipf=1.2 if i % 2 else None) for i in range(6)]
+    results = {}
+    for policy, graph in (("full", True), ("pipelined", True), ("pipelined", False)):
+        m = build_cuda_model(cfg, seed=11)
+        m._ensure_group().scale_policy = policy
+        step = GraphedTrainStep(m, *batches[0], lr=0.5, world_size=1, rank=0, grad_bits=8, warmup=1, use_graph=graph)
+        losses = []
+        with torch.cuda.stream(step.stream):
+            for b in batches:
+                step.load(*b)
+                step.run()
+                losses.append(step.loss.clone())
+        torch.cuda.synchronize()
+        m.emb_group.check_status()
+        if policy == "full":                 # pipelined already holds the post-update scale of the next forward
+            m.emb_group.scan_scales()
+        results[(policy, graph)] = (torch.stack(losses).cpu(), m.emb_group.scale.clone().cpu(),
+                                    [w.detach().clone().cpu() for w in m.emb_group.weights])
+    ref = results[("full", True)]
+    for key in (("pipelined", True), ("pipelined", False)):
+        got = results[key]
+        assert torch.equal(ref[0], got[0]), key
+        assert torch.equal(ref[1], got[1]), key
+        for a, b in zip(ref[2], got[2]):
+            assert torch.equal(a, b), key
 
 
 def test_periodic_scale_update_policy():
