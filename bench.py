@@ -54,10 +54,10 @@ def parse():
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-steps", type=int, default=5)
-    p.add_argument("--scale-policy", type=str, default="pipelined", choices=["pipelined", "full", "incremental"],
-                   help="pipelined = full rescan of every table every step, overlapped with the step on a side stream "
-                        "(headline); full = the same rescan serialised in front of the forward; incremental = exact "
-                        "block-max tracker (reads only the touched blocks)")
+    p.add_argument("--scale-policy", type=str, default="full", choices=["full", "pipelined", "incremental"],
+                   help="full = rescan every table in front of every forward (reference order; headline); pipelined = "
+                        "the same rescan overlapped with the step on a side stream; incremental = exact block-max "
+                        "tracker (reads only the touched blocks)")
     p.add_argument("--no-extras", "--no-incremental-extra", dest="no_extras", action="store_true",
                    help="skip the additional measurements (serial rescan, incremental tracker) reported beside the headline")
     return p.parse_args()
@@ -290,16 +290,21 @@ def run_ours(args):
     ms_e2e, _ = timed(step, args.steps, args.warmup, from_host=True)
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     dlrm.emb_group.check_status()
+    dlrm._dense_arena.check_status()
     final_loss = float(step.loss.item())
+    exchange = "single GPU: no exchange" if world == 1 else (
+        "one-kernel all-gathers over NVLink peer memory (csrc/p2p.cu), 5 per step, no NCCL call in the step"
+        if dlrm.emb_group.p2p is not None else "NCCL: 2 all-gathers + 3 all-reduces per step")
     extras = {}
-    if args.scale_policy == "pipelined" and not args.no_extras:
-        # the same step with (a) the rescan serialised in front of the forward, as the reference orders it, and
-        # (b, N=1) the exact incremental tracker; reported beside the headline, never instead of it
-        variants = [("serial_rescan", "full", "same full rescan, serialised before the forward (reference order)")]
-        if world == 1:
-            variants.append(("incremental_scale_tracker", "incremental",
-                             "exact block-max tracker: reads only the touched blocks; scales bit-identical to the "
-                             "rescan (SURVEY.md 8 f-1); not the headline because the reference rescans every step"))
+    if args.scale_policy == "full" and not args.no_extras and world == 1:
+        # the same step with (a) the rescan overlapped with the step (block maxima on a side stream + fix-up of the
+        # updated blocks) and (b) the exact incremental tracker; reported beside the headline, never instead of it
+        variants = [("pipelined_rescan", "pipelined",
+                     "same full rescan (every table byte read once per step), overlapped with the step on a low-priority "
+                     "stream; scales bit-identical (tests/test_gpu_tracker.py)"),
+                    ("incremental_scale_tracker", "incremental",
+                     "exact block-max tracker: reads only the touched blocks; scales bit-identical to the "
+                     "rescan (SURVEY.md 8 f-1); not the headline because the reference rescans every step")]
         for key, policy, note in variants:
             dlrm.emb_group.scale_policy = policy
             dlrm.emb_group.scale_valid = False
@@ -343,7 +348,8 @@ def run_ours(args):
                                                 "period-1 semantics), overlapped with the step on a low-priority stream; "
                                                 "blocks holding updated rows are re-read after the update"}[args.scale_policy] +
                                   (", row-sharded 1/N + MAX all-reduce" if dlrm.shard_scan else "")),
-                   "l2": "table arena (2.16 GB) is 17x the 126 MB L2: inputs larger than L2, no flush needed",
+                   "exchange": exchange,
+                   "l2": f"table arena ({table_bytes / 1e9:.2f} GB) is {table_bytes / 126e6:.0f}x the 126 MB L2: inputs larger than L2, no flush needed",
                    "cuda_graph": step.graph is not None, "final_loss": final_loss},
         "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": step.input_bytes(), "d2h_bytes_per_step": 4},

@@ -14,8 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqrm_b200.so")
 
 MAX_TABLES = 64
+ABI_VERSION = 2
 BWD_CTA_MAX_LOOKUPS = 16384
-STATUS_INDEX_RANGE, STATUS_OFFSET_ORDER, STATUS_CAPACITY = 1, 2, 4
+STATUS_INDEX_RANGE, STATUS_OFFSET_ORDER, STATUS_CAPACITY, STATUS_P2P_TIMEOUT = 1, 2, 4, 8
 
 _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 _p = C.c_void_p          # every pointer (host arrays are passed as ctypes arrays, device ptrs as ints)
@@ -43,7 +44,7 @@ SIGNATURES = {
     "dqrm_sgd_rows": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _f32, _f32, _p, _f32, _p]),
     "dqrm_slot_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "dqrm_slot_layout": (_i32, [_i32, _i64, _i32, _i32, C.POINTER(_sz), C.POINTER(_sz)]),
-    "dqrm_grad_pack": (_i32, [_i32, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _p, _p, _p]),
+    "dqrm_grad_pack": (_i32, [_i32, _i32, _p, _p, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p]),
     "dqrm_grad_topk": (_i32, [_i32, _i32, _p, _p, _p, _i64, _i64, _p]),
     "dqrm_grad_merge_apply": (_i32, [_i32, _p, _p, _i32, _p, _i32, _i64, _i32, _p, _f32, _p, _p, _p, _p, _p]),
     "dqrm_interact_fwd": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p]),
@@ -56,6 +57,16 @@ SIGNATURES = {
     "dqrm_dense_grad_scale": (_i32, [_p, _p, _i32, _i32, _p, _p]),
     "dqrm_dense_grad_quant": (_i32, [_p, _p, _i32, _p, _f32, _i32, _p, _p, _p]),
     "dqrm_dense_apply": (_i32, [_p, _p, _p, _i32, _p, _f32, _f32, _p]),
+    "dqrm_p2p_alloc": (_i32, [_sz, C.POINTER(_vp), _p]),
+    "dqrm_p2p_open": (_i32, [_p, C.POINTER(_vp)]),
+    "dqrm_p2p_close": (_i32, [_p]),
+    "dqrm_p2p_free": (_i32, [_p]),
+    "dqrm_p2p_site_bytes": (_sz, [_i32, _sz]),
+    "dqrm_p2p_site_layout": (_i32, [_i32, _sz, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "dqrm_p2p_allgather": (_i32, [_p, _i32, _i32, _sz, _sz, _p, _p]),
+    "dqrm_dense_grad_quant_gathered": (_i32, [_p, _p, _i32, _p, _sz, _i32, _i32, _p, _p, _p]),
+    "dqrm_dense_apply_gathered": (_i32, [_p, _p, _sz, _i32, _p, _i32, _p, _f32, _p]),
+    "dqrm_scale_from_absmax_gathered": (_i32, [_i32, _p, _sz, _i32, _i32, _p, _p, _p, _p]),
 }
 
 _lib = None
@@ -67,7 +78,9 @@ LAUNCHING = ("dqrm_table_absmax_scale", "dqrm_scale_from_absmax", "dqrm_embbag_f
              "dqrm_mlp_fakequant_all", "dqrm_linear_fwd", "dqrm_linear_bwd",
              "dqrm_blockmax_build", "dqrm_blockmax_update", "dqrm_blockmax_scan", "dqrm_blockmax_update_shard",
              "dqrm_blockmax_reduce", "dqrm_table_pack_int4", "dqrm_embbag_fwd_int4",
-             "dqrm_dense_grad_scale", "dqrm_dense_grad_quant", "dqrm_dense_apply")
+             "dqrm_dense_grad_scale", "dqrm_dense_grad_quant", "dqrm_dense_apply",
+             "dqrm_p2p_allgather", "dqrm_dense_grad_quant_gathered", "dqrm_dense_apply_gathered",
+             "dqrm_scale_from_absmax_gathered")
 launch_counts = {}
 
 
@@ -112,8 +125,8 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so is stale
         fn.restype, fn.argtypes = res, args
-    if lib.dqrm_abi_version() != 1:
-        raise DqrmLibraryError(f"{LIB_PATH}: ABI version {lib.dqrm_abi_version()} != 1 (stale build)")
+    if lib.dqrm_abi_version() != ABI_VERSION:
+        raise DqrmLibraryError(f"{LIB_PATH}: ABI version {lib.dqrm_abi_version()} != {ABI_VERSION} (stale build)")
     _lib = _Counted(lib)
     return _lib
 

@@ -35,9 +35,9 @@ template <typename CodeT> struct AccOf { using type = int; };
 template <> struct AccOf<float> { using type = float; };
 
 // s_bar = (sum_r s_r) * (1/N) in rank order
-__device__ __forceinline__ float mean_scale(const float* __restrict__ gathered, int world, int T, int t, float inv_world) {
+__device__ __forceinline__ float mean_scale(const float* __restrict__ gathered, int world, long long stride, int t, float inv_world) {
   float acc = gathered[t];
-  for (int r = 1; r < world; ++r) acc = __fadd_rn(acc, gathered[(long long)r * T + t]);
+  for (int r = 1; r < world; ++r) acc = __fadd_rn(acc, gathered[(long long)r * stride + t]);
   return __fmul_rn(acc, inv_world);
 }
 
@@ -45,12 +45,12 @@ template <int COLS, typename CodeT>
 __global__ void __launch_bounds__(256)
 grad_pack_kernel(int T, int dim4, int group, const float* __restrict__ grad_sums, const int* __restrict__ uniq_rows,
                  const int* __restrict__ uniq_count, long long capacity, const float* __restrict__ gathered_scales,
-                 int world, float inv_world, int bits, unsigned char* __restrict__ slot, SlotLayout lay,
+                 long long scale_stride, int world, float inv_world, int bits, unsigned char* __restrict__ slot, SlotLayout lay,
                  float* __restrict__ scale_mean) {
   using C4 = typename Code4<CodeT>::type;
   const int t = blockIdx.y;
   const int U = uniq_count[t];
-  const float s_bar = mean_scale(gathered_scales, world, T, t, inv_world);
+  const float s_bar = mean_scale(gathered_scales, world, scale_stride, t, inv_world);
   const float inv = __fdiv_rn(1.0f, s_bar);
   const float hi = qmax_of(bits), lo = -hi - 1.0f;
   int* cnt = reinterpret_cast<int*>(slot);
@@ -195,8 +195,9 @@ extern "C" int dqrm_slot_layout(int num_tables, int64_t capacity, int dim, int b
 
 extern "C" int dqrm_grad_pack(int num_tables, int dim, const float* grad_sums, const int32_t* uniq_rows,
                               const int32_t* uniq_count, int64_t capacity,
-                              const float* gathered_scales, int world, int bits,
+                              const float* gathered_scales, int64_t scale_stride_elems, int world, int bits,
                               void* slot, float* scale_mean, void* stream) {
+  DQRM_REQUIRE(scale_stride_elems >= num_tables, -EINVAL, "grad_pack: scale_stride_elems=%lld < num_tables", (long long)scale_stride_elems);
   DQRM_REQUIRE(grad_sums && uniq_rows && uniq_count && gathered_scales && slot && scale_mean, -EINVAL, "grad_pack: null argument");
   DQRM_REQUIRE(num_tables >= 1 && num_tables <= DQRM_MAX_TABLES, -E2BIG, "grad_pack: num_tables=%d", num_tables);
   DQRM_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= 512, -EINVAL, "grad_pack: dim=%d", dim);
@@ -212,7 +213,7 @@ extern "C" int dqrm_grad_pack(int num_tables, int dim, const float* grad_sums, c
   const float inv_world = (float)(1.0 / world);
 #define DQRM_PACK(COLS, CT)                                                                                       \
   grad_pack_kernel<COLS, CT><<<grid, 256, 0, st>>>(num_tables, dim / 4, rl.group, grad_sums, uniq_rows, uniq_count, \
-                                                   capacity, gathered_scales, world, inv_world, bits,              \
+                                                   capacity, gathered_scales, scale_stride_elems, world, inv_world, bits, \
                                                    static_cast<unsigned char*>(slot), lay, scale_mean)
   if (bits == 32) { if (rl.cols == 1) DQRM_PACK(1, float); else if (rl.cols == 2) DQRM_PACK(2, float); else DQRM_PACK(4, float); }
   else if (bits <= 8) { if (rl.cols == 1) DQRM_PACK(1, int8_t); else if (rl.cols == 2) DQRM_PACK(2, int8_t); else DQRM_PACK(4, int8_t); }

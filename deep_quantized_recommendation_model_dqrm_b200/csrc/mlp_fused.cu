@@ -86,15 +86,22 @@ constexpr int BM = 32, BN = 64, BK = 16, TM = 4, TN = 4, kGemmThreads = 128;
 constexpr int A_PER_THR = BM * BK / kGemmThreads, B_PER_THR = BK * BN / kGemmThreads;    // 4, 8
 constexpr int APAD = BM + 4, BPAD = BN + 4;
 
-template <int MODE>
+// CL = false: the same kernel with no cluster instruction at all (S = 1).  A grid that uses clusters was
+// measured not to become co-resident with a long-running non-cluster grid (the pipelined table rescan,
+// tracker.cu): the step's GEMMs waited for the whole pass.  See DESIGN.md "pipelined rescan".
+template <int MODE, bool CL = true>
 __global__ void __launch_bounds__(kGemmThreads)
 linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int, const float* __restrict__ b_int,
                    const float* __restrict__ s_row, const float* __restrict__ dout, const float* __restrict__ out,
                    float* __restrict__ C, float* __restrict__ db, int batch, int out_f, int in_f, int act, int kc,
                    int accumulate) {
   namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  int S = 1, rank = 0;
+  if constexpr (CL) {
+    cg::cluster_group cluster = cg::this_cluster();
+    S = (int)cluster.num_blocks();
+    rank = (int)cluster.block_rank();
+  }
   __shared__ __align__(16) float As[2][BK][APAD];
   __shared__ __align__(16) float Bs[2][BK][BPAD];                       // also the partial tile red[BM][BN]
   static_assert(2 * BK * BPAD >= BM * BN, "partial tile must fit in Bs");
@@ -221,7 +228,8 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
         db[m0 + tid] = accumulate ? __fadd_rn(db[m0 + tid], gq) : gq;
       }
     }
-  } else {
+  } else if constexpr (CL) {
+    cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
     for (int i = 0; i < TM; ++i)
       *reinterpret_cast<float4*>(&red[(ty * TM + i) * BN + tx * TN]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -277,8 +285,15 @@ static int launch_gemm(const float* x, const float* W_int, const float* b_int, c
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
   cfg.attrs = attr;
   cfg.numAttrs = S > 1 ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, linear_gemm_kernel<MODE>, x, W_int, b_int, s_row, dout, out, C, db, batch,
-                                     out_f, in_f, act, kc, accumulate);
+  cudaError_t e;
+  if (S > 1) {
+    e = cudaLaunchKernelEx(&cfg, linear_gemm_kernel<MODE, true>, x, W_int, b_int, s_row, dout, out, C, db, batch, out_f,
+                           in_f, act, kc, accumulate);
+  } else {
+    linear_gemm_kernel<MODE, false><<<cfg.gridDim, cfg.blockDim, 0, st>>>(x, W_int, b_int, s_row, dout, out, C, db, batch,
+                                                                          out_f, in_f, act, kc, accumulate);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) { set_error("linear_gemm_kernel<%d>: %s", MODE, cudaGetErrorString(e)); return -EIO; }
   return 0;
 }

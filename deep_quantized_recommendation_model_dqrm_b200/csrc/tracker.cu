@@ -410,10 +410,19 @@ extern "C" int dqrm_blockmax_scan(int num_tables, const float* const* weight, co
     return true;
   }();
   (void)carveout_set;
-  if (wide)
-    blockmax_scan_kernel<true><<<(unsigned)grid, kPipeThreads, 0, st>>>(a, dim / 8, block_rows, (int)bpu, (int)units);
-  else
-    blockmax_scan_kernel<false><<<(unsigned)grid, kPipeThreads, 0, st>>>(a, dim / 4, block_rows, (int)bpu, (int)units);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kPipeThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;           // experiment: dispatch the pass as a 1x1x1-cluster grid
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("DQRM_PIPE_CLUSTER") ? 1 : 0;
+  cudaError_t le;
+  if (wide) le = cudaLaunchKernelEx(&cfg, blockmax_scan_kernel<true>, a, dim / 8, block_rows, (int)bpu, (int)units);
+  else le = cudaLaunchKernelEx(&cfg, blockmax_scan_kernel<false>, a, dim / 4, block_rows, (int)bpu, (int)units);
+  DQRM_REQUIRE(le == cudaSuccess, -EIO, "blockmax_scan_kernel: %s", cudaGetErrorString(le));
   DQRM_LAUNCH_CHECK("blockmax_scan_kernel");
   return 0;
 }

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, p2p as _p2p
 
 
 class DenseArena:
@@ -72,13 +72,18 @@ class DenseArena:
         self.fused_ok = n <= 16 and len({l.weight_bit for l in self.layers}) == 1 and \
             all((l.bias is None) or (l.quantize_bias and l.bias_bit == l.weight_bit) for l in self.layers)
         # weight-gradient GEMMs run on a side stream, off the critical dx chain (None = same stream)
-        self.side_stream = torch.cuda.Stream(device=device, priority=-1) if self.flat.is_cuda else None
+        import os
+        self.side_stream = torch.cuda.Stream(device=device, priority=-1) \
+            if (self.flat.is_cuda and not os.environ.get("DQRM_NO_SIDE_STREAM")) else None
         self.keepalive = []
         for l in self.layers:
             l._arena = self
         self.scale_local = torch.zeros(self.num_chan, dtype=torch.float32, device=device)
         self.scale_mean = torch.zeros(self.num_chan, dtype=torch.float32, device=device)
         self.codes = torch.zeros(total, dtype=torch.float32, device=device)
+        self.p2p = None                    # PeerArena of the NVLink exchange (world > 1, DQRM_EXCHANGE=p2p)
+        self.p2p_world = 1
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self._bind_scale_views()
 
     def _bind_scale_views(self):
@@ -114,6 +119,13 @@ class DenseArena:
                 l.weight_integer, l.bias_integer, l.fc_scaling_factor = l._w_int, l._b_int, l._fc_scale
             self._int_views_bound = True
 
+    def check_status(self):
+        """Device-side errors of the NVLink exchange (D2H sync)."""
+        s = int(self.status.item())
+        if s:
+            self.status.zero_()
+            raise RuntimeError(f"dqrm dense exchange status {s}: a peer never signalled an NVLink exchange site (timeout)")
+
     def join(self):
         """Make the current stream wait for the side-stream weight-gradient kernels of this step."""
         if self.side_stream is not None and self.keepalive:
@@ -126,17 +138,48 @@ class DenseArena:
         for l in self.layers:
             l._grad_dirty = False
 
+    def _ensure_p2p(self, world):
+        """Peer arena for the two MLP exchange sites (collective; first quantised exchange with world > 1)."""
+        if self.p2p is not None and self.p2p_world == world:
+            return self.p2p
+        import torch.distributed as dist
+        self.p2p = None
+        if world > 1 and _p2p.backend() == "p2p" and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size() == world:
+            a = _p2p.PeerArena({"mlp_scale": self.num_chan * 4, "mlp_codes": self.total}, world, dist.get_rank(), self.device)
+            self.p2p, self.p2p_world = a, world
+            self.scale_local = a.my_slot("mlp_scale", torch.float32, self.num_chan)
+            self._scale_slots = a.slots("mlp_scale", torch.float32)
+            self._code_slots = a.slots("mlp_codes", torch.int8)
+            self._codes_mine = a.my_slot("mlp_codes", torch.int8, self.total)
+        return self.p2p
+
     def quantize_exchange(self, world=1, process_group=None, bits=8, quantized=True):
         """quantize_linear_grad / quantize_bias_grad for every tensor at once
-        (sgd_quantized_gradients_parallel_comm.py:892-961): local scales -> SUM all-reduce ->
-        quantise with the mean scale -> SUM all-reduce of the codes."""
+        (sgd_quantized_gradients_parallel_comm.py:892-961): local scales -> SUM over ranks ->
+        quantise with the mean scale -> SUM of the codes over ranks.  NVLink form (default): two one-kernel
+        all-gathers, sums taken in rank order by the consumers, codes travel as int8; NCCL form: two all-reduces."""
         if world > 1:
             import torch.distributed as dist
         self.join()
+        self.exchanged_p2p = False
         if not quantized:
             self.codes.copy_(self.flat_grad)
             if world > 1:
                 dist.all_reduce(self.codes, group=process_group)
+            return
+        if world > 1 and bits <= 8 and self._ensure_p2p(world) is not None:
+            a = self.p2p
+            self.local_scale(bits)                                  # -> this rank's slot of the scale site
+            a.allgather("mlp_scale", self.status)
+            rc = self.lib.dqrm_dense_grad_quant_gathered(self.flat_grad.data_ptr(), self.chan_begin.data_ptr(),
+                                                         self.num_chan, self._scale_slots.data_ptr(),
+                                                         self._scale_slots.stride(0), world, bits,
+                                                         self._codes_mine.data_ptr(), self.scale_mean.data_ptr(),
+                                                         _lib.stream_ptr())
+            _lib.check(rc, "dqrm_dense_grad_quant_gathered")
+            a.allgather("mlp_codes", self.status)
+            self.exchanged_p2p = True
             return
         self.local_scale(bits)
         if world > 1:
@@ -161,6 +204,12 @@ class DenseArena:
     def apply(self, lr, world=1, quantized=True):
         """MLP half of weight_update_parallel_comm (sgd_quantized_gradients_parallel_comm.py:630-663)."""
         st = _lib.stream_ptr()
+        if quantized and getattr(self, "exchanged_p2p", False):
+            rc = self.lib.dqrm_dense_apply_gathered(self.flat.data_ptr(), self._code_slots.data_ptr(),
+                                                    self._code_slots.stride(0), world, self.chan_begin.data_ptr(),
+                                                    self.num_chan, self.scale_mean.data_ptr(), float(lr), st)
+            _lib.check(rc, "dqrm_dense_apply_gathered")
+            return
         _lib.check(self.lib.dqrm_dense_apply(self.flat.data_ptr(), self.codes.data_ptr(), self.chan_begin.data_ptr(),
                                              self.num_chan, self.scale_mean.data_ptr() if quantized else None,
                                              float(1.0 / world), float(lr), st), "dqrm_dense_apply")

@@ -38,6 +38,11 @@ class GraphedTrainStep:
         self.group.dp_world, self.group.dp_rank = world_size, rank
         self.pipelined = self.group.scale_policy == "pipelined"
         self.stream = torch.cuda.Stream(device=dev, priority=-1)
+        if self.pipelined:
+            # measured on B200: a graph with forked branches is not co-scheduled with the side-stream pass (its
+            # kernels wait for the whole scan); a linear graph is.  Keep the weight-gradient GEMMs in line.
+            from .sgd_quantized_gradients_parallel_comm import _dense_arena
+            _dense_arena(dlrm).side_stream = None
         dlrm.external_scan = True
         self.graph = self.graph_b = None
         torch.cuda.synchronize()

@@ -21,7 +21,12 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, p2p as _p2p
+
+
+def _dist_world():
+    import torch.distributed as dist
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
 
 class EmbeddingTableGroup:
@@ -74,6 +79,8 @@ class EmbeddingTableGroup:
         self._bm_buf = None
         self._bm_valid = False
         self._bm_wptrs = None
+        self.p2p = None             # PeerArena of the NVLink exchange (world > 1, DQRM_EXCHANGE=p2p)
+        self.dp_world, self.dp_rank = 1, 0
         self.fixed_capacity = None  # rows per table in the exchange slots (default: this step's largest table)
         self.keep_debug = False   # also emit updated_rows / qbar in merge (parity tests, .grad materialisation)
 
@@ -92,7 +99,8 @@ class EmbeddingTableGroup:
         s = int(self.status.item())
         if s:
             self.status.zero_()
-            names = [n for b, n in ((1, "index out of range"), (2, "offsets not monotone"), (4, "capacity exceeded")) if s & b]
+            names = [n for b, n in ((1, "index out of range"), (2, "offsets not monotone"), (4, "capacity exceeded"),
+                                      (8, "a peer never signalled an NVLink exchange site (timeout)")) if s & b]
             raise IndexError("dqrm kernel status: " + ", ".join(names))
 
     @staticmethod
@@ -179,15 +187,11 @@ class EmbeddingTableGroup:
         r, w = self.pipe_shard
         sharded = w > 1
         rc = lib.dqrm_blockmax_reduce(self.T, self._rows_arr, self.block_rows, self._bm_ptrs, r, w, self.embedding_bit,
-                                      self.absmax.data_ptr(), None if sharded else self.scale.data_ptr(),
+                                      self._absmax_out(sharded).data_ptr(), None if sharded else self.scale.data_ptr(),
                                       None if sharded else self.inv_scale.data_ptr(), self._scan_ws.data_ptr(), st)
         _lib.check(rc, "dqrm_blockmax_reduce")
         if sharded:
-            import torch.distributed as dist
-            dist.all_reduce(self.absmax, op=dist.ReduceOp.MAX, group=self.pipe_group)
-            _lib.check(lib.dqrm_scale_from_absmax(self.T, self.absmax.data_ptr(), self.embedding_bit,
-                                                  self.scale.data_ptr(), self.inv_scale.data_ptr(), st),
-                       "dqrm_scale_from_absmax")
+            self._allreduce_absmax_to_scale(self.pipe_group)
         self.scale_valid = True
 
     def _pipe_pass(self, events=None):
@@ -258,7 +262,7 @@ class EmbeddingTableGroup:
         if events is not None:            # (start, end) CUDA events bracketing exactly the scan kernel
             events[0].record()
         rc = lib.dqrm_table_absmax_scale(self.T, self._wptrs(), self._rows_arr, self.dim, self.embedding_bit,
-                                         shard_rank, shard_world, self.absmax.data_ptr(),
+                                         shard_rank, shard_world, self._absmax_out(sharded).data_ptr(),
                                          None if sharded else self.scale.data_ptr(),
                                          None if sharded else self.inv_scale.data_ptr(),
                                          self._scan_ws.data_ptr(), st)
@@ -266,11 +270,7 @@ class EmbeddingTableGroup:
             events[1].record()
         _lib.check(rc, "dqrm_table_absmax_scale")
         if sharded:
-            import torch.distributed as dist
-            dist.all_reduce(self.absmax, op=dist.ReduceOp.MAX, group=process_group)
-            rc = lib.dqrm_scale_from_absmax(self.T, self.absmax.data_ptr(), self.embedding_bit,
-                                            self.scale.data_ptr(), self.inv_scale.data_ptr(), st)
-            _lib.check(rc, "dqrm_scale_from_absmax")
+            self._allreduce_absmax_to_scale(process_group)
         self.scale_valid = True
 
     # ---- (a3) -----------------------------------------------------------
@@ -339,15 +339,54 @@ class EmbeddingTableGroup:
         self.uniq_rows = torch.zeros((T, capacity), dtype=torch.int32, device=dev)
         self.uniq_count = torch.zeros(T, dtype=torch.int32, device=dev)
         self.grad_sums = torch.zeros((T, capacity, D), dtype=torch.float32, device=dev)
-        self.gathered_scales = torch.zeros((world, T), dtype=torch.float32, device=dev)
-        sb = int(self.lib.dqrm_slot_bytes(T, capacity, D, self.grad_bit))
-        self.slot_bytes = sb
-        self.gathered = torch.zeros(world * sb, dtype=torch.uint8, device=dev)
+        self._alloc_exchange_buffers()
         self.slot = None   # view of this rank's slice of `gathered`, set by exchange()
         self.updated_rows = self.updated_count = self.qbar = None
         wsb = int(self.lib.dqrm_bwd_workspace_bytes(T, capacity, D))
         self._bwd_ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
         self._bwd_ws_bytes = wsb
+
+    def _alloc_exchange_buffers(self):
+        """gathered_scales [world, T(+pad)], gathered [world * slot_bytes] (+ the local scale slot): plain device
+        buffers, or -- with world > 1 real ranks and DQRM_EXCHANGE=p2p -- views of this rank's peer arena, which
+        the other ranks write into directly over NVLink (collective: all ranks get here in the same step)."""
+        dev, T, D, world = self.device, self.T, self.dim, self.world
+        sb = int(self.lib.dqrm_slot_bytes(T, self.capacity, D, self.grad_bit))
+        self.slot_bytes = sb
+        self.p2p = None
+        if world > 1 and _p2p.backend() == "p2p" and _dist_world() == world:
+            a = _p2p.PeerArena({"emb_scale": T * 4, "emb_slot": sb, "absmax": T * 4}, world, self.dp_rank, dev)
+            self.p2p = a
+            self.gathered_scales = a.slots("emb_scale", torch.float32)
+            self.grad_scale_local = a.my_slot("emb_scale", torch.float32, T)
+            self.gathered = a.slots("emb_slot").view(-1)              # slot stride == slot_bytes (16-byte multiple)
+            assert a.stride("emb_slot") == sb
+            self._absmax_slots = a.slots("absmax", torch.float32)
+            self._absmax_mine = a.my_slot("absmax", torch.float32, T)
+        else:
+            if self.grad_scale_local.numel() != T or self.grad_scale_local.data_ptr() % 16:     # was an arena view
+                self.grad_scale_local = torch.zeros(T, dtype=torch.float32, device=dev)
+            self.gathered_scales = torch.zeros((world, T), dtype=torch.float32, device=dev)
+            self.gathered = torch.zeros(world * sb, dtype=torch.uint8, device=dev)
+
+    def _allreduce_absmax_to_scale(self, process_group):
+        """Row-sharded scan: per-shard maxima in the absmax out-buffer -> MAX over ranks -> scale, 1/scale."""
+        lib, st = self.lib, _lib.stream_ptr()
+        if self.p2p is not None:
+            self.p2p.allgather("absmax", self.status)
+            rc = lib.dqrm_scale_from_absmax_gathered(self.T, self._absmax_slots.data_ptr(), self._absmax_slots.stride(0),
+                                                     self.world, self.embedding_bit, self.absmax.data_ptr(),
+                                                     self.scale.data_ptr(), self.inv_scale.data_ptr(), st)
+            _lib.check(rc, "dqrm_scale_from_absmax_gathered")
+            return
+        import torch.distributed as dist
+        dist.all_reduce(self.absmax, op=dist.ReduceOp.MAX, group=process_group)
+        _lib.check(lib.dqrm_scale_from_absmax(self.T, self.absmax.data_ptr(), self.embedding_bit,
+                                              self.scale.data_ptr(), self.inv_scale.data_ptr(), st), "dqrm_scale_from_absmax")
+
+    def _absmax_out(self, sharded):
+        """Where a sharded scan writes its per-shard maxima: this rank's slot of the absmax site, else self.absmax."""
+        return self._absmax_mine if (sharded and self.p2p is not None) else self.absmax
 
     def backward(self, dout, world=1, last=None, ste_done=False):
         """De-duplicated row gradients of a forward (default: the last one) from dOut [T, B, D]-strided."""
@@ -375,9 +414,7 @@ class EmbeddingTableGroup:
         self.grad_bit = int(bits)
         if self.uniq_rows is None:
             return
-        sb = int(self.lib.dqrm_slot_bytes(self.T, self.capacity, self.dim, self.grad_bit))
-        self.slot_bytes = sb
-        self.gathered = torch.zeros(self.world * sb, dtype=torch.uint8, device=self.device)
+        self._alloc_exchange_buffers()
         if self.grad_bit != 32:
             _lib.check(self.lib.dqrm_grad_absmax_scale(self.T, self.dim, self.grad_sums.data_ptr(),
                                                        self.uniq_count.data_ptr(), self.capacity, self.grad_bit,
@@ -399,6 +436,13 @@ class EmbeddingTableGroup:
         embedding exchange, replacing 52 Gloo calls).  Composed of the three phases below so that
         tests can emulate several ranks on one GPU by copying between replicas' buffers."""
         assert world == self.world, "backward() and exchange() must agree on world size"
+        if self.p2p is not None:
+            # one-kernel all-gathers over NVLink peer memory (csrc/p2p.cu): the backward already wrote the local
+            # scales into this rank's slot, pack() writes the codes into its slot of the gathered buffer
+            self.p2p.allgather("emb_scale", self.status)
+            self.pack(rank)
+            self.p2p.allgather("emb_slot", self.status)
+            return
         self.stage_scale(rank)
         if world > 1:
             import torch.distributed as dist
@@ -410,7 +454,8 @@ class EmbeddingTableGroup:
 
     def stage_scale(self, rank=0):
         """Phase 1: this rank's 26 local gradient scales into row `rank` of gathered_scales."""
-        self.gathered_scales[rank].copy_(self.grad_scale_local)
+        if self.p2p is None:
+            self.gathered_scales[rank, :self.T].copy_(self.grad_scale_local)
 
     def pack(self, rank=0):
         """Phase 2 (after the scale all-gather): quantise with the rank-mean scale into slot `rank`."""
@@ -418,7 +463,7 @@ class EmbeddingTableGroup:
         self.slot = self.gathered[rank * sb:(rank + 1) * sb]
         rc = self.lib.dqrm_grad_pack(self.T, self.dim, self.grad_sums.data_ptr(), self.uniq_rows.data_ptr(),
                                      self.uniq_count.data_ptr(), self.capacity, self.gathered_scales.data_ptr(),
-                                     self.world, self.grad_bit, self.slot.data_ptr(), self.grad_scale_mean.data_ptr(),
+                                     self.gathered_scales.stride(0), self.world, self.grad_bit, self.slot.data_ptr(), self.grad_scale_mean.data_ptr(),
                                      _lib.stream_ptr())
         _lib.check(rc, "dqrm_grad_pack")
 

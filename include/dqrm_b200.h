@@ -46,13 +46,14 @@ extern "C" {
 #define DQRM_API
 #endif
 
-#define DQRM_ABI_VERSION 1
+#define DQRM_ABI_VERSION 2
 #define DQRM_MAX_TABLES 64           /* tables per call (kernel-parameter descriptor size) */
 #define DQRM_BWD_CTA_MAX_LOOKUPS 16384 /* per-table lookups handled by the single-CTA sort path */
 
 #define DQRM_STATUS_INDEX_RANGE 1    /* an index was <0 or >= rows (clamped) */
 #define DQRM_STATUS_OFFSET_ORDER 2   /* offsets not monotone / outside the index segment */
 #define DQRM_STATUS_CAPACITY 4       /* more unique rows than `capacity` */
+#define DQRM_STATUS_P2P_TIMEOUT 8    /* a peer never signalled an exchange site (dqrm_p2p_allgather gave up after ~2 s) */
 
 DQRM_API int dqrm_abi_version(void);
 DQRM_API const char* dqrm_last_error(void);
@@ -224,14 +225,15 @@ DQRM_API int dqrm_sgd_rows(int num_tables, float* const* weight, const int64_t* 
  * sparse all-reduce (:878):
  *   int32 count[num_tables] | int32 rows[num_tables][capacity] |
  *   int8 (bits<=8), int16 (bits<=16) or fp32 (bits==32) codes[num_tables][capacity][dim]
- *   gathered_scales dev [world, num_tables];  scale_mean dev [num_tables] out
+ *   gathered_scales dev [world] rows of num_tables floats, row r at r * scale_stride_elems (= num_tables for a
+ *   dense [world, num_tables] array; the padded slot stride of a peer-arena site);  scale_mean dev [num_tables] out
  */
 DQRM_API size_t dqrm_slot_bytes(int num_tables, int64_t capacity, int dim, int bits);
 DQRM_API int dqrm_slot_layout(int num_tables, int64_t capacity, int dim, int bits,
                      size_t* rows_offset, size_t* codes_offset);
 DQRM_API int dqrm_grad_pack(int num_tables, int dim, const float* grad_sums, const int32_t* uniq_rows,
                    const int32_t* uniq_count, int64_t capacity,
-                   const float* gathered_scales, int world, int bits,
+                   const float* gathered_scales, int64_t scale_stride_elems, int world, int bits,
                    void* slot, float* scale_mean, void* stream);
 
 /* ------------------------------------------------------------------ (a8) --
@@ -345,6 +347,45 @@ DQRM_API int dqrm_dense_grad_quant(const float* grad, const int64_t* chan_begin,
                           float* codes, float* scale_mean, void* stream);
 DQRM_API int dqrm_dense_apply(float* param, const float* code_sum, const int64_t* chan_begin, int num_chan,
                      const float* scale_mean, float inv_world, float lr, void* stream);
+
+/* ------------------------------------------- exchange over NVLink peer memory --
+ * One-kernel all-gathers that replace the step's collectives when world > 1 (the reference: Gloo all-reduces
+ * per table / per tensor, sgd_quantized_gradients_parallel_comm.py:865,878,913,925,949,957; this library's
+ * portable form: 2 NCCL all-gathers + 3 all-reduces).  Every rank allocates one PEER ARENA and maps the arenas
+ * of the other ranks of the box (CUDA IPC; the 64-byte handles travel through the caller's own channel, e.g.
+ * torch.distributed.all_gather).  A SITE is a region at the same offset in every arena:
+ *     ctl[16 B] | flag[world] u32 (padded to 16 B) | slot[world][slot_stride]      (dqrm_p2p_site_layout)
+ * The producer kernel writes this rank's contribution into slot[rank] of its own arena; dqrm_p2p_allgather
+ * copies it into slot[rank] of every peer with remote stores, signals, and waits for every peer's signal, so
+ * that when it retires slot[0..world) of the LOCAL arena is complete.  The consumers below reduce the slots in
+ * rank order (deterministic, identical on every rank).  Sequence numbers live on the device: the call is
+ * CUDA-graph replayable.  Requirements: every rank calls the same sites in the same order on one stream, at
+ * least two distinct sites per step (single buffering, see csrc/p2p.cu), arenas zero-initialised (p2p_alloc
+ * does) and all ranks past a barrier after opening the handles.  A peer that never arrives makes the wait give
+ * up after ~2 s with DQRM_STATUS_P2P_TIMEOUT in *status. */
+DQRM_API int dqrm_p2p_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_64);
+DQRM_API int dqrm_p2p_open(const void* ipc_handle_64, void** dev_ptr);
+DQRM_API int dqrm_p2p_close(void* dev_ptr);
+DQRM_API int dqrm_p2p_free(void* dev_ptr);
+DQRM_API size_t dqrm_p2p_site_bytes(int world, size_t slot_bytes);
+DQRM_API int dqrm_p2p_site_layout(int world, size_t slot_bytes, size_t* flag_off, size_t* data_off, size_t* slot_stride);
+/* peer_base: host array [world] of the mapped arena bases (entry `rank` = the local arena) */
+DQRM_API int dqrm_p2p_allgather(void* const* peer_base, int world, int rank, size_t site_off, size_t slot_bytes,
+                                int32_t* status, void* stream);
+/* (a11) quantize_linear_grad / quantize_bias_grad for all tensors, scales summed in rank order from the gathered
+ * per-channel local scales (row r at r * scale_stride_elems), codes as int8 (bits <= 8) -- typically straight
+ * into this rank's slot of the codes site. */
+DQRM_API int dqrm_dense_grad_quant_gathered(const float* grad, const int64_t* chan_begin, int num_chan,
+                                            const float* gathered_scales, size_t scale_stride_elems, int world,
+                                            int bits, int8_t* codes, float* scale_mean, void* stream);
+/* (a11 + a9) param += (-lr * ((sum_r codes_r) * (1/world))) * scale_mean  (sgd...parallel_comm.py:925,642-643,
+ * 957,662-663); rank r's int8 codes at gathered_codes + r * code_stride_bytes. */
+DQRM_API int dqrm_dense_apply_gathered(float* param, const int8_t* gathered_codes, size_t code_stride_bytes, int world,
+                                       const int64_t* chan_begin, int num_chan, const float* scale_mean, float lr,
+                                       void* stream);
+/* (a1, row-sharded scan) absmax = max over ranks of the gathered per-shard maxima, then scale and 1/scale. */
+DQRM_API int dqrm_scale_from_absmax_gathered(int n_scales, const float* gathered_absmax, size_t stride_elems, int world,
+                                             int bits, float* absmax, float* scale, float* inv_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,120 @@
+"""GPU: the one-kernel NVLink exchange (csrc/p2p.cu) on ONE device -- W peer arenas inside this process, the W
+"ranks" on W streams (the kernels spin on each other's flags, so they must be co-resident; each is <= 64 small CTAs).
+Real multi-GPU coverage: tools/p2p_check.py under torchrun (bit-identical to the NCCL form, ranks identical)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _arenas(sites, world):
+    from deep_quantized_recommendation_model_dqrm_b200 import p2p
+    return p2p.PeerArena.local_group(sites, world, device="cuda")
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_allgather_protocol_replays(world):
+    sites = {"small": 26 * 4, "big": 66672, "odd": 1624 * 4 + 4}
+    arenas = _arenas(sites, world)
+    status = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for it in range(5):                                  # sequence numbers advance on the device
+        want = {}
+        for name in sites:
+            want[name] = []
+            for r, a in enumerate(arenas):
+                mine = a.my_slot(name)
+                mine.copy_(torch.randint(0, 255, mine.shape, device="cuda", dtype=torch.uint8, generator=g))
+                want[name].append(mine.clone())
+        torch.cuda.synchronize()
+        for name in sites:                               # >= 2 sites per round, same order on every rank
+            for r, a in enumerate(arenas):
+                with torch.cuda.stream(streams[r]):
+                    a.allgather(name, status[r])
+        torch.cuda.synchronize()
+        for name in sites:
+            for a in arenas:
+                got = a.slots(name)
+                for r in range(world):
+                    assert torch.equal(got[r], want[name][r]), (it, name, r)
+        assert all(int(s) == 0 for s in status)
+
+
+def test_allgather_gives_up_when_a_peer_is_missing():
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    arenas = _arenas({"x": 64, "y": 64}, 2)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    arenas[0].allgather("x", status)                     # rank 1 never calls: ~2 s, then the timeout bit
+    torch.cuda.synchronize()
+    assert int(status) == _lib.STATUS_P2P_TIMEOUT
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_gathered_dense_consumers_match_allreduce_form(world):
+    """quant(gathered scales) + apply(gathered int8 codes) == the all-reduce form: sum of scales in rank order,
+    fp32 sum of the integer codes, dqrm_dense_apply -- parameters bit-identical."""
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(2)
+    sizes = [(64, 13), (64,), (16, 64), (16,), (1, 16), (1,)]
+    chan, off = [0], 0
+    for s in sizes:
+        n = int(np.prod(s))
+        if len(s) == 2:
+            chan += [off + (r + 1) * s[1] for r in range(s[0])]
+        else:
+            chan.append(off + n)
+        off += n
+    total, C = off, len(chan) - 1
+    chan_t = torch.tensor(chan, dtype=torch.int64, device="cuda")
+    grads = [torch.tensor(rng.randn(total).astype(np.float32) * 10.0 ** rng.uniform(-4, 0), device="cuda") for _ in range(world)]
+    param0 = torch.tensor(rng.randn(total).astype(np.float32), device="cuda")
+    st = _lib.stream_ptr()
+    scales = torch.zeros((world, C + 3), dtype=torch.float32, device="cuda")          # padded stride
+    for r in range(world):
+        _lib.check(lib.dqrm_dense_grad_scale(grads[r].data_ptr(), chan_t.data_ptr(), C, 8, scales[r].data_ptr(), st), "scale")
+    # all-reduce form
+    ssum = scales[0, :C].clone()
+    for r in range(1, world):
+        ssum = ssum + scales[r, :C]
+    codes_f = torch.zeros((world, total), device="cuda")
+    mean_a = torch.zeros(C, device="cuda")
+    for r in range(world):
+        _lib.check(lib.dqrm_dense_grad_quant(grads[r].data_ptr(), chan_t.data_ptr(), C, ssum.data_ptr(), 1.0 / world, 8,
+                                             codes_f[r].data_ptr(), mean_a.data_ptr(), st), "quant")
+    csum = codes_f[0].clone()
+    for r in range(1, world):
+        csum = csum + codes_f[r]
+    pa = param0.clone()
+    _lib.check(lib.dqrm_dense_apply(pa.data_ptr(), csum.data_ptr(), chan_t.data_ptr(), C, mean_a.data_ptr(), 1.0 / world, 0.1, st), "apply")
+    # gathered form
+    stride = (total + 15) // 16 * 16 + 16
+    codes_i = torch.zeros((world, stride), dtype=torch.int8, device="cuda")
+    mean_b = torch.zeros(C, device="cuda")
+    for r in range(world):
+        _lib.check(lib.dqrm_dense_grad_quant_gathered(grads[r].data_ptr(), chan_t.data_ptr(), C, scales.data_ptr(),
+                                                      scales.stride(0), world, 8, codes_i[r].data_ptr(), mean_b.data_ptr(), st), "quant_g")
+    pb = param0.clone()
+    _lib.check(lib.dqrm_dense_apply_gathered(pb.data_ptr(), codes_i.data_ptr(), stride, world, chan_t.data_ptr(), C,
+                                             mean_b.data_ptr(), 0.1, st), "apply_g")
+    torch.cuda.synchronize()
+    assert torch.equal(mean_a, mean_b)
+    assert torch.equal(codes_i[:, :total].float(), codes_f)
+    assert torch.equal(pa, pb)
+
+
+def test_scale_from_gathered_absmax():
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    lib = _lib.load()
+    world, T = 8, 26
+    g = torch.rand((world, T + 6), device="cuda")
+    g[3, 5] = 0.0
+    am, sc, inv = (torch.zeros(T, device="cuda") for _ in range(3))
+    _lib.check(lib.dqrm_scale_from_absmax_gathered(T, g.data_ptr(), g.stride(0), world, 4, am.data_ptr(), sc.data_ptr(),
+                                                   inv.data_ptr(), _lib.stream_ptr()), "gathered")
+    want = g[:, :T].max(dim=0)[0]
+    sc2, inv2 = torch.zeros(T, device="cuda"), torch.zeros(T, device="cuda")
+    _lib.check(lib.dqrm_scale_from_absmax(T, want.data_ptr(), 4, sc2.data_ptr(), inv2.data_ptr(), _lib.stream_ptr()), "plain")
+    assert torch.equal(am, want) and torch.equal(sc, sc2) and torch.equal(inv, inv2)

@@ -11,7 +11,7 @@ from deep_quantized_recommendation_model_dqrm_b200.graph_step import GraphedTrai
 p = argparse.ArgumentParser()
 p.add_argument("--workload", default="kaggle"); p.add_argument("--batch", type=int, default=128)
 p.add_argument("--policy", default="pipelined"); p.add_argument("--no-graph", action="store_true")
-p.add_argument("--no-fuse-mlp", action="store_true"); p.add_argument("--rows", type=int, default=1000)
+p.add_argument("--dot", default=None, help="dump graph A as DOT to this path"); p.add_argument("--no-fuse-mlp", action="store_true"); p.add_argument("--rows", type=int, default=1000)
 a = p.parse_args()
 cfg = {"kaggle": synthetic.KAGGLE, "terabyte": synthetic.TERABYTE, "small": synthetic.RANDOM_SMALL}[a.workload]
 ln_top = synthetic.top_mlp_sizes(len(cfg["rows"]), cfg["dim"], cfg["ln_top_hidden"])
@@ -22,7 +22,15 @@ m = drv.DLRM_Net(cfg["dim"], np.array(cfg["rows"]), np.array(cfg["ln_bot"]), np.
 m._ensure_group().scale_policy = a.policy
 m.fuse_mlp = not a.no_fuse_mlp
 b = [t.cuda() for t in synthetic.criteo_batch(cfg["rows"], a.batch, seed=3)]
+if a.dot:
+    _orig = torch.cuda.CUDAGraph.capture_begin
+    def _cb(self, *x, **k):
+        self.enable_debug_mode()
+        return _orig(self, *x, **k)
+    torch.cuda.CUDAGraph.capture_begin = _cb
 step = GraphedTrainStep(m, *b, lr=0.1, use_graph=not a.no_graph)
+if a.dot and step.graph is not None:
+    step.graph.debug_dump(a.dot)
 with torch.cuda.stream(step.stream):
     for _ in range(5):
         step.run()
