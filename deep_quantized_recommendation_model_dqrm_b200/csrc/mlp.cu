@@ -149,3 +149,45 @@ extern "C" int dqrm_dense_apply(float* param, const float* code_sum, const int64
   DQRM_LAUNCH_CHECK("dense_apply_kernel");
   return 0;
 }
+
+// ---- BCE loss (mean) and its gradient in one launch ------------------------------------------------------------
+// Reference: loss_fn_wrap -> torch.nn.BCELoss(reduction="mean") (dlrm_s_pytorch_comm_grad.py:192-211) followed by
+// E.backward() (:1938): ATen runs 8 small kernels for it (bce forward, mean, ones_like, fills, bce backward, /N).
+//   loss = mean( (t - 1) * max(log1p(-z), -100) - t * max(log(z), -100) )
+//   dz   = ((z - t) / max((1 - z) * z, 1e-12)) * (1/N)                 (the value autograd hands to the sigmoid;
+//          ATen: bce backward with grad 1, then the mean's division as a multiply by the fp32 reciprocal)
+// One CTA, fixed summation order (deterministic); the loss agrees with ATen's tree reduction to fp32 rounding,
+// the gradient is evaluated in ATen's operation order.
+namespace dqrm {
+__global__ void __launch_bounds__(1024)
+bce_loss_grad_kernel(const float* __restrict__ z, const float* __restrict__ t, long long n, float inv_n,
+                     float* __restrict__ loss, float* __restrict__ dz) {
+  __shared__ float s_part[32];
+  float acc = 0.0f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float zi = z[i], ti = t[i];
+    const float l1 = fmaxf(log1pf(-zi), -100.0f), l0 = fmaxf(logf(zi), -100.0f);
+    acc = __fadd_rn(acc, __fsub_rn(__fmul_rn(__fsub_rn(ti, 1.0f), l1), __fmul_rn(ti, l0)));
+    if (dz) dz[i] = __fmul_rn(__fdiv_rn(__fsub_rn(zi, ti), fmaxf(__fmul_rn(__fsub_rn(1.0f, zi), zi), 1e-12f)), inv_n);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, o));
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) *loss = __fmul_rn(v, inv_n);
+  }
+}
+}  // namespace dqrm
+
+extern "C" int dqrm_bce_loss_grad(const float* z, const float* target, int64_t n, float* loss, float* dz, void* stream) {
+  DQRM_REQUIRE(z && target && loss && n >= 1, -EINVAL, "bce_loss_grad: bad argument");
+  const int threads = n >= 1024 ? 1024 : (int)((n + 31) / 32 * 32);
+  dqrm::bce_loss_grad_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(z, target, n, (float)(1.0 / (double)n),
+                                                                                  loss, dz);
+  DQRM_LAUNCH_CHECK("bce_loss_grad_kernel");
+  return 0;
+}

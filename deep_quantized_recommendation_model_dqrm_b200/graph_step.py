@@ -11,7 +11,18 @@ from __future__ import annotations
 
 import torch
 
+from . import _lib
 from . import dlrm_s_pytorch_comm_grad as drv
+
+
+def _packed_layout(X, lS_o, lS_i, T):
+    """Byte layout of one batch in a single staging buffer: X | lS_o | lS_i | T, each 16-byte aligned."""
+    lay, off = [], 0
+    for t in (X, lS_o, lS_i, T):
+        n = t.numel() * t.element_size()
+        lay.append((off, n, t.dtype, tuple(t.shape)))
+        off += (n + 15) // 16 * 16
+    return lay, off
 
 
 class GraphedTrainStep:
@@ -29,11 +40,16 @@ class GraphedTrainStep:
         self.mlp_layer_quantized = mlp_layer_quantized
         dev = next(dlrm.parameters()).device
         self.device = dev
-        self.X = X.to(dev).clone()
-        self.lS_o = lS_o.to(dev).clone()
-        self.lS_i = lS_i.to(dev).clone()
-        self.T = T.to(dev).clone()
+        # the static inputs are views of ONE staging buffer, so a host batch packed the same way (pack_host) arrives
+        # with a single H2D copy (load_packed); load() still accepts the four tensors separately
+        self._layout, nbytes = _packed_layout(X, lS_o, lS_i, T)
+        self._stage = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        views = [self._stage[o:o + n].view(dt).view(shape) for (o, n, dt, shape) in self._layout]
+        self.X, self.lS_o, self.lS_i, self.T = views
+        for v, src in zip(views, (X, lS_o, lS_i, T)):
+            v.copy_(src)
         self.loss = torch.zeros((), device=dev)
+        self.fused_loss = dlrm.loss_function == "bce" and not (0.0 < dlrm.loss_threshold < 1.0)
         self.group = dlrm._ensure_group()
         self.group.dp_world, self.group.dp_rank = world_size, rank
         self.pipelined = self.group.scale_policy == "pipelined"
@@ -83,13 +99,22 @@ class GraphedTrainStep:
     def _body_a(self):
         d = self.dlrm
         Z = d(self.X, self.lS_o, self.lS_i)
-        E = torch.nn.functional.binary_cross_entropy(Z, self.T)
-        drv.clear_gradients(d)
-        E.backward()
+        if self.fused_loss:
+            # BCELoss(mean) + the first backward step in ONE launch (ATen: 8 small kernels), loss written in place
+            Zd = Z.detach()
+            dZ = torch.empty_like(Zd)
+            _lib.check(_lib.load().dqrm_bce_loss_grad(Zd.data_ptr(), self.T.data_ptr(), Zd.numel(), self.loss.data_ptr(),
+                                                      dZ.data_ptr(), _lib.stream_ptr()), "dqrm_bce_loss_grad")
+            drv.clear_gradients(d)
+            Z.backward(dZ)
+        else:
+            E = torch.nn.functional.binary_cross_entropy(Z, self.T)
+            drv.clear_gradients(d)
+            E.backward()
+            self.loss.copy_(E.detach())
         drv.grad_update_parallel_comm(d, self.world, emb_grad_quantized=True, num_bits=self.grad_bits,
                                       ranking_range=False, rank_for_debug=self.rank,
                                       mlp_layer_quantized=self.mlp_layer_quantized)
-        self.loss.copy_(E.detach())
 
     def _body_b(self):
         drv.weight_update_parallel_comm(self.dlrm, self.lr, emb_grad_quantized=True, update_embedding=True,
@@ -109,6 +134,20 @@ class GraphedTrainStep:
         self.lS_i.copy_(lS_i, non_blocking=True)
         self.T.copy_(T, non_blocking=True)
 
+    def pack_host(self, X, lS_o, lS_i, T, pin=True):
+        """Collate one host batch into the staging layout (one pinned uint8 tensor) for load_packed()."""
+        buf = torch.zeros(self._stage.numel(), dtype=torch.uint8)
+        if pin:
+            buf = buf.pin_memory()
+        for (o, n, dt, shape), t in zip(self._layout, (X, lS_o, lS_i, T)):
+            assert tuple(t.shape) == shape and t.dtype == dt, "batch does not match the captured static shapes"
+            buf[o:o + n].view(dt).view(shape).copy_(t)
+        return buf
+
+    def load_packed(self, packed):
+        """Refill all static inputs with ONE (H2D or D2D) copy of a pack_host()-shaped buffer; asynchronous."""
+        self._stage.copy_(packed, non_blocking=True)
+
     def replay(self):
         """Everything after the scan launch, on the current stream."""
         if self.graph is None:
@@ -126,4 +165,4 @@ class GraphedTrainStep:
         return self.loss
 
     def input_bytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.X, self.lS_o, self.lS_i, self.T))
+        return int(self._stage.numel())

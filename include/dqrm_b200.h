@@ -348,6 +348,12 @@ DQRM_API int dqrm_dense_grad_quant(const float* grad, const int64_t* chan_begin,
 DQRM_API int dqrm_dense_apply(float* param, const float* code_sum, const int64_t* chan_begin, int num_chan,
                      const float* scale_mean, float inv_world, float lr, void* stream);
 
+/* BCE loss (mean reduction) and its gradient in one launch: torch.nn.BCELoss()(Z, T) + E.backward() of the
+ * reference loop (loss_fn_wrap, dlrm_s_pytorch_comm_grad.py:192-211; :1938).
+ *   *loss = mean((t-1)*max(log1p(-z),-100) - t*max(log z,-100));  dz = ((z-t) / max((1-z)*z, 1e-12)) * (1/n)
+ * z, target, dz: dev fp32 [n] (dz may be NULL); loss: dev fp32 scalar.  Deterministic summation order. */
+DQRM_API int dqrm_bce_loss_grad(const float* z, const float* target, int64_t n, float* loss, float* dz, void* stream);
+
 /* ------------------------------------------- exchange over NVLink peer memory --
  * One-kernel all-gathers that replace the step's collectives when world > 1 (the reference: Gloo all-reduces
  * per table / per tensor, sgd_quantized_gradients_parallel_comm.py:865,878,913,925,949,957; this library's

@@ -1,0 +1,67 @@
+"""GPU: the graph-replayed training step (graph_step.GraphedTrainStep: packed single-copy inputs, fused BCE loss +
+gradient kernel, CUDA graphs) against the eager reference-shaped iteration (drv.train_iteration: ATen BCELoss,
+autograd) that the oracle parity tests pin."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n", [1, 37, 128, 2048, 8192])
+def test_bce_loss_grad_kernel_matches_aten(n):
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    z = torch.rand((n, 1), device="cuda", generator=g)
+    if n > 4:
+        z[0], z[1], z[2] = 0.0, 1.0, 1e-30                     # the clamps: log -> -100, denominator -> 1e-12
+    t = torch.round(torch.rand((n, 1), device="cuda", generator=g))
+    zr = z.clone().requires_grad_(True)
+    E = torch.nn.functional.binary_cross_entropy(zr, t)
+    E.backward()
+    loss, dz = torch.zeros((), device="cuda"), torch.empty_like(z)
+    _lib.check(lib.dqrm_bce_loss_grad(z.data_ptr(), t.data_ptr(), n, loss.data_ptr(), dz.data_ptr(), _lib.stream_ptr()), "bce")
+    torch.testing.assert_close(loss, E.detach(), rtol=1e-6, atol=1e-7)        # tolerance: summation order only
+    assert torch.equal(dz, zr.grad)                                            # same operation order as ATen: bit-exact
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_graph_step_matches_eager_iteration(use_graph):
+    from helpers import C_SMALL, build_cuda_model
+    from deep_quantized_recommendation_model_dqrm_b200 import synthetic
+    from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
+    from deep_quantized_recommendation_model_dqrm_b200.graph_step import GraphedTrainStep
+    B = 32
+    batches = [synthetic.criteo_batch(C_SMALL["rows"], B, seed=40 + i, zipf=1.3 if i % 2 else None) for i in range(5)]
+    ref = build_cuda_model(C_SMALL, seed=9)
+    ref_losses = [float(drv.train_iteration(ref, *b, lr=0.2)) for b in batches]
+    ref._ensure_group().check_status()
+
+    m = build_cuda_model(C_SMALL, seed=9)
+    snapshot = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    step = GraphedTrainStep(m, *batches[0], lr=0.2, warmup=1, use_graph=use_graph)   # warm-up iterations train: rewind
+    with torch.no_grad():
+        for k, v in m.state_dict().items():
+            v.copy_(snapshot[k])
+    m.emb_group.scale_valid = False
+    losses = []
+    with torch.cuda.stream(step.stream):
+        for i, b in enumerate(batches):
+            if i % 2:
+                step.load_packed(step.pack_host(*b))             # one pinned H2D copy
+            else:
+                step.load(*b)
+            step.run()
+            losses.append(float(step.loss))
+    torch.cuda.synchronize()
+    m.emb_group.check_status()
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-6)
+    for a, b in zip(ref.emb_group.weights, m.emb_group.weights):
+        assert torch.equal(a, b)                                 # identical gradients -> identical tables
+    for (na, pa), (nb, pb) in zip(ref.named_parameters(), m.named_parameters()):
+        assert torch.equal(pa, pb), na
