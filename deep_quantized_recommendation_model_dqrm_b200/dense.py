@@ -82,7 +82,7 @@ class DenseArena:
         self.scale_mean = torch.zeros(self.num_chan, dtype=torch.float32, device=device)
         self.codes = torch.zeros(total, dtype=torch.float32, device=device)
         self.p2p = None                    # PeerArena of the NVLink exchange (world > 1, DQRM_EXCHANGE=p2p)
-        self.p2p_world = 1
+        self.slot_world = 0                # world size the exchange slots were built for (0: all-reduce form)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self._bind_scale_views()
 
@@ -138,54 +138,75 @@ class DenseArena:
         for l in self.layers:
             l._grad_dirty = False
 
-    def _ensure_p2p(self, world):
-        """Peer arena for the two MLP exchange sites (collective; first quantised exchange with world > 1)."""
-        if self.p2p is not None and self.p2p_world == world:
-            return self.p2p
+    def _ensure_slots(self, world):
+        """Per-rank slots of the two MLP exchange sites (channel scales fp32, codes int8): views of this rank's peer
+        arena (NVLink form, collective on first use) or plain device buffers gathered by NCCL.  Same layout, same
+        consumers, so the two transports give bit-identical updates."""
+        if self.slot_world == world:
+            return
         import torch.distributed as dist
         self.p2p = None
-        if world > 1 and _p2p.backend() == "p2p" and dist.is_available() and dist.is_initialized() \
-                and dist.get_world_size() == world:
+        live = dist.is_available() and dist.is_initialized() and dist.get_world_size() == world
+        if live and _p2p.backend() == "p2p":
             a = _p2p.PeerArena({"mlp_scale": self.num_chan * 4, "mlp_codes": self.total}, world, dist.get_rank(), self.device)
-            self.p2p, self.p2p_world = a, world
-            self.scale_local = a.my_slot("mlp_scale", torch.float32, self.num_chan)
+            self.p2p = a
             self._scale_slots = a.slots("mlp_scale", torch.float32)
             self._code_slots = a.slots("mlp_codes", torch.int8)
-            self._codes_mine = a.my_slot("mlp_codes", torch.int8, self.total)
-        return self.p2p
+            rank = a.rank
+        else:
+            pad = lambda n: (n + 15) // 16 * 16
+            self._scale_slots = torch.zeros((world, pad(self.num_chan * 4) // 4), dtype=torch.float32, device=self.device)
+            self._code_slots = torch.zeros((world, pad(self.total)), dtype=torch.int8, device=self.device)
+            rank = dist.get_rank() if live else 0
+        self.slot_world, self.slot_rank = world, rank
+        self.scale_local = self._scale_slots[rank, :self.num_chan]
+        self._codes_mine = self._code_slots[rank, :self.total]
+
+    def _allgather(self, site, slots, process_group):
+        if self.p2p is not None:
+            self.p2p.allgather(site, self.status)
+        else:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(slots.view(-1), slots[self.slot_rank], group=process_group)
 
     def quantize_exchange(self, world=1, process_group=None, bits=8, quantized=True):
         """quantize_linear_grad / quantize_bias_grad for every tensor at once
         (sgd_quantized_gradients_parallel_comm.py:892-961): local scales -> SUM over ranks ->
-        quantise with the mean scale -> SUM of the codes over ranks.  NVLink form (default): two one-kernel
-        all-gathers, sums taken in rank order by the consumers, codes travel as int8; NCCL form: two all-reduces."""
+        quantise with the mean scale -> SUM of the codes over ranks.  Both sums are taken in rank order by the
+        consumer kernels from all-gathered slots (deterministic, identical on every rank); the codes travel as
+        int8.  Transport: one-kernel NVLink all-gathers (default) or NCCL all-gathers (DQRM_EXCHANGE=nccl)."""
         if world > 1:
             import torch.distributed as dist
         self.join()
-        self.exchanged_p2p = False
+        self.exchanged_gathered = False
         if not quantized:
             self.codes.copy_(self.flat_grad)
             if world > 1:
                 dist.all_reduce(self.codes, group=process_group)
             return
-        if world > 1 and bits <= 8 and self._ensure_p2p(world) is not None:
-            a = self.p2p
+        live = world > 1 and dist.is_available() and dist.is_initialized() and dist.get_world_size() == world
+        if live and bits <= 8:
+            self._ensure_slots(world)
             self.local_scale(bits)                                  # -> this rank's slot of the scale site
-            a.allgather("mlp_scale", self.status)
+            self._allgather("mlp_scale", self._scale_slots, process_group)
             rc = self.lib.dqrm_dense_grad_quant_gathered(self.flat_grad.data_ptr(), self.chan_begin.data_ptr(),
                                                          self.num_chan, self._scale_slots.data_ptr(),
                                                          self._scale_slots.stride(0), world, bits,
                                                          self._codes_mine.data_ptr(), self.scale_mean.data_ptr(),
                                                          _lib.stream_ptr())
             _lib.check(rc, "dqrm_dense_grad_quant_gathered")
-            a.allgather("mlp_codes", self.status)
-            self.exchanged_p2p = True
+            self._allgather("mlp_codes", self._code_slots, process_group)
+            self.exchanged_gathered = True
             return
+        # single rank, emulated ranks (tests copy between replicas) or > 8-bit codes: the all-reduce form
+        if self.slot_world != 0:
+            self.scale_local = torch.zeros(self.num_chan, dtype=torch.float32, device=self.device)
+            self.slot_world = 0
         self.local_scale(bits)
-        if world > 1:
+        if world > 1 and live:
             dist.all_reduce(self.scale_local, group=process_group)
         self.quantize(world, bits)
-        if world > 1:
+        if world > 1 and live:
             dist.all_reduce(self.codes, group=process_group)
 
     def local_scale(self, bits=8):
@@ -204,7 +225,7 @@ class DenseArena:
     def apply(self, lr, world=1, quantized=True):
         """MLP half of weight_update_parallel_comm (sgd_quantized_gradients_parallel_comm.py:630-663)."""
         st = _lib.stream_ptr()
-        if quantized and getattr(self, "exchanged_p2p", False):
+        if quantized and getattr(self, "exchanged_gathered", False):
             rc = self.lib.dqrm_dense_apply_gathered(self.flat.data_ptr(), self._code_slots.data_ptr(),
                                                     self._code_slots.stride(0), world, self.chan_begin.data_ptr(),
                                                     self.num_chan, self.scale_mean.data_ptr(), float(lr), st)

@@ -43,10 +43,10 @@ def test_graph_step_matches_eager_iteration(use_graph):
     ref._ensure_group().check_status()
 
     m = build_cuda_model(C_SMALL, seed=9)
-    snapshot = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    snapshot = {k: v.detach().clone() for k, v in m.named_parameters()}
     step = GraphedTrainStep(m, *batches[0], lr=0.2, warmup=1, use_graph=use_graph)   # warm-up iterations train: rewind
     with torch.no_grad():
-        for k, v in m.state_dict().items():
+        for k, v in m.named_parameters():
             v.copy_(snapshot[k])
     m.emb_group.scale_valid = False
     losses = []

@@ -53,12 +53,9 @@ for backend in ("nccl", "p2p"):
     if rank == 0:
         print(f"{backend}: model digest {digest[:16]} identical across {world} ranks: {len(set(allh)) == 1}", flush=True)
     assert len(set(allh)) == 1, f"{backend}: replicas diverged"
-same = res["nccl"] == res["p2p"]
-# N = 2: a + b is order-free, the two forms must agree bit for bit.  N > 2: NCCL's all-reduce sums the MLP channel
-# scales in its own (ring/tree) order while the NVLink form sums in rank order, so a last-bit difference is legal.
-ok = same or world > 2
+ok = res["nccl"] == res["p2p"]       # same slots, same rank-ordered consumers: only the transport differs
 if rank == 0:
-    print(f"p2p == nccl (tables, MLP arena, scales bit-identical): {same} (world {world})", flush=True)
+    print(f"p2p == nccl (tables, MLP arena, scales bit-identical): {ok} (world {world})", flush=True)
 dist.barrier(); torch.cuda.synchronize()
 sys.stdout.flush()
 os._exit(0 if ok else 1)
