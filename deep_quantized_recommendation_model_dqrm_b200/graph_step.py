@@ -9,6 +9,8 @@ de-duplication, the two embedding all-gathers, the MLP all-reduces and all updat
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -53,6 +55,10 @@ class GraphedTrainStep:
         self.group = dlrm._ensure_group()
         self.group.dp_world, self.group.dp_rank = world_size, rank
         self.pipelined = self.group.scale_policy == "pipelined"
+        # multi-rank: launch the embedding exchange from inside the backward (side stream), overlapping the two
+        # all-gathers + pack with the bottom-MLP backward; grad_update_parallel_comm then only joins
+        self.group.eager_exchange = (world_size > 1 and self.group.grad_bit == grad_bits and not self.pipelined and
+                                     os.environ.get("DQRM_EAGER_EXCHANGE", "1") != "0")
         self.stream = torch.cuda.Stream(device=dev, priority=-1)
         if self.pipelined:
             # measured on B200: a graph with forked branches is not co-scheduled with the side-stream pass (its

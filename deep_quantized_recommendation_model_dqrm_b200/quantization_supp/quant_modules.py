@@ -48,6 +48,8 @@ class EmbBagGroupFunction(Function):
         ste_done = getattr(g, "ste_done_for", None) == dout.data_ptr()      # fused into the interaction backward
         g.ste_done_for = None
         g.backward(dout, world=g.dp_world, last=ctx.last, ste_done=ste_done)
+        if g.eager_exchange and g.dp_world > 1:
+            g.start_exchange()           # overlaps with the bottom-MLP backward that autograd runs next
         if g.materialize_grads:
             grads = tuple(g.sparse_grad(t) for t in range(g.T))
         else:

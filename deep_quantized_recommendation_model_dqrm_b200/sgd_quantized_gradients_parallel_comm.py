@@ -94,9 +94,12 @@ def grad_update_parallel_comm(model, number_of_gpus, emb_grad_quantized=True, nu
     with torch.no_grad():
         for g in _emb_groups(model):
             if emb_grad_quantized:
+                started = g.finish_exchange()        # already running on the side stream (graph_step eager mode)
                 if g.grad_bit != num_bits:
                     g.set_grad_bit(num_bits)
-                g.exchange(world=world, rank=rank)
+                    started = False
+                if not started:
+                    g.exchange(world=world, rank=rank)
                 if g.modules is not None:
                     for t, e in enumerate(g.modules):
                         e.emb_scaling_factor = g.grad_scale_mean[t:t + 1]

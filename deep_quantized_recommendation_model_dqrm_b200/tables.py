@@ -80,6 +80,9 @@ class EmbeddingTableGroup:
         self._bm_valid = False
         self._bm_wptrs = None
         self.p2p = None             # PeerArena of the NVLink exchange (world > 1, DQRM_EXCHANGE=p2p)
+        self.eager_exchange = False  # start the embedding exchange from inside the backward, on xchg_stream
+        self.xchg_stream = None
+        self.exchange_started = False
         self.dp_world, self.dp_rank = 1, 0
         self.fixed_capacity = None  # rows per table in the exchange slots (default: this step's largest table)
         self.keep_debug = False   # also emit updated_rows / qbar in merge (parity tests, .grad materialisation)
@@ -451,6 +454,25 @@ class EmbeddingTableGroup:
         if world > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.gathered, self.slot, group=process_group)
+
+    def start_exchange(self):
+        """Run exchange() on a side stream right after the de-duplicating backward, so the two all-gathers and
+        the pack overlap with the rest of the backward pass (the bottom MLP).  finish_exchange() joins."""
+        main = torch.cuda.current_stream()
+        if self.xchg_stream is None:
+            self.xchg_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.xchg_stream.wait_stream(main)
+        with torch.cuda.stream(self.xchg_stream):
+            self.exchange(world=self.world, rank=self.dp_rank)
+        self.exchange_started = True
+
+    def finish_exchange(self):
+        """True if an exchange started by start_exchange() was joined into the current stream."""
+        if not self.exchange_started:
+            return False
+        torch.cuda.current_stream().wait_stream(self.xchg_stream)
+        self.exchange_started = False
+        return True
 
     def stage_scale(self, rank=0):
         """Phase 1: this rank's 26 local gradient scales into row `rank` of gathered_scales."""
