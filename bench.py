@@ -301,7 +301,7 @@ def run_ours(args):
     final_loss = float(step.loss.item())
     exchange = "single GPU: no exchange" if world == 1 else (
         "one-kernel all-gathers over NVLink peer memory (csrc/p2p.cu), 5 per step, no NCCL call in the step"
-        if dlrm.emb_group.p2p is not None else "NCCL: 2 all-gathers + 3 all-reduces per step")
+        if dlrm.emb_group.p2p is not None else "NCCL: 4 all-gathers + 1 MAX all-reduce per step (same slots and consumer kernels as the NVLink form)")
     extras = {}
     if args.scale_policy == "full" and not args.no_extras and world == 1:
         # the same step with (a) the rescan overlapped with the step (block maxima on a side stream + fix-up of the

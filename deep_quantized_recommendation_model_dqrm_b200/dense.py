@@ -147,8 +147,14 @@ class DenseArena:
         import torch.distributed as dist
         self.p2p = None
         live = dist.is_available() and dist.is_initialized() and dist.get_world_size() == world
+        a = None
         if live and _p2p.backend() == "p2p":
-            a = _p2p.PeerArena({"mlp_scale": self.num_chan * 4, "mlp_codes": self.total}, world, dist.get_rank(), self.device)
+            try:
+                a = _p2p.PeerArena({"mlp_scale": self.num_chan * 4, "mlp_codes": self.total}, world, dist.get_rank(),
+                                   self.device)
+            except _p2p.P2PUnavailable as e:         # raised on every rank together
+                _p2p.fall_back_to_nccl(e)
+        if a is not None:
             self.p2p = a
             self._scale_slots = a.slots("mlp_scale", torch.float32)
             self._code_slots = a.slots("mlp_codes", torch.int8)

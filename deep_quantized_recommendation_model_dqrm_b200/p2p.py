@@ -23,6 +23,19 @@ def backend() -> str:
     return b
 
 
+class P2PUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank could not allocate / export / map a peer arena."""
+
+
+def fall_back_to_nccl(err):
+    """The NVLink transport is unavailable on this box: say so loudly and use the NCCL all-gathers (same slots,
+    same consumer kernels, bit-identical results).  Called on every rank after a P2PUnavailable."""
+    import sys
+    os.environ["DQRM_EXCHANGE"] = "nccl"
+    print(f"[dqrm-b200] WARNING: NVLink peer-memory exchange unavailable ({err}); using NCCL all-gathers instead",
+          file=sys.stderr, flush=True)
+
+
 class _RawCuda:
     """Minimal __cuda_array_interface__ carrier so torch can view memory this library allocated."""
 
@@ -52,24 +65,44 @@ class PeerArena:
         else:
             import torch.distributed as dist
             with torch.cuda.device(self.device):
-                ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
-                _lib.check(lib.dqrm_p2p_alloc(self.bytes, C.byref(ptr), handle), "dqrm_p2p_alloc")
+                # every step below is attempted on every rank and the outcomes are agreed on with a MIN all-reduce,
+                # so a failure on one rank raises P2PUnavailable on all of them (no rank is left in a collective)
+                ptr, handle, err = C.c_void_p(), (C.c_ubyte * 64)(), ""
+                try:
+                    if os.environ.get("DQRM_P2P_FAIL_RANK") == str(self.rank):      # failure injection (tests)
+                        raise _lib.DqrmLibraryError("injected failure")
+                    _lib.check(lib.dqrm_p2p_alloc(self.bytes, C.byref(ptr), handle), "dqrm_p2p_alloc")
+                except _lib.DqrmLibraryError as e:
+                    err = str(e)
                 self.base = ptr.value
-                mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
-                allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+                mine = torch.tensor(list(handle) + [0 if err else 1], dtype=torch.uint8, device=self.device)
+                allh = torch.empty(self.world * 65, dtype=torch.uint8, device=self.device)
                 dist.all_gather_into_tensor(allh, mine, group=process_group)
-                allh = allh.cpu().view(self.world, 64)
+                allh = allh.cpu().view(self.world, 65)
+                ok = bool(allh[:, 64].min().item())
                 bases = []
                 for r in range(self.world):
-                    if r == self.rank:
+                    if r == self.rank or not ok:
                         bases.append(self.base)
                         continue
-                    h = (C.c_ubyte * 64)(*allh[r].tolist())
+                    h = (C.c_ubyte * 64)(*allh[r, :64].tolist())
                     p = C.c_void_p()
-                    _lib.check(lib.dqrm_p2p_open(h, C.byref(p)), f"dqrm_p2p_open(rank {r})")
+                    rc = lib.dqrm_p2p_open(h, C.byref(p))
+                    if rc != 0:
+                        err, ok = f"dqrm_p2p_open(rank {r}): {_lib.last_error()}", False
+                        bases.append(None)
+                        continue
                     bases.append(p.value)
                     self._opened.append(p.value)
+                flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=process_group)
                 torch.cuda.synchronize()
+                if int(flag.item()) == 0:
+                    for q in self._opened:
+                        lib.dqrm_p2p_close(q)
+                    if self.base:
+                        lib.dqrm_p2p_free(self.base)
+                    raise P2PUnavailable(err or "a peer rank could not set up its arena")
                 dist.barrier(group=process_group)    # nobody signals into an arena that is not mapped and zeroed yet
         self.bases = bases
         self.ptrs = (C.c_void_p * self.world)(*bases)

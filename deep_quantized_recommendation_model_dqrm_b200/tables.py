@@ -357,8 +357,13 @@ class EmbeddingTableGroup:
         sb = int(self.lib.dqrm_slot_bytes(T, self.capacity, D, self.grad_bit))
         self.slot_bytes = sb
         self.p2p = None
+        a = None
         if world > 1 and _p2p.backend() == "p2p" and _dist_world() == world:
-            a = _p2p.PeerArena({"emb_scale": T * 4, "emb_slot": sb, "absmax": T * 4}, world, self.dp_rank, dev)
+            try:
+                a = _p2p.PeerArena({"emb_scale": T * 4, "emb_slot": sb, "absmax": T * 4}, world, self.dp_rank, dev)
+            except _p2p.P2PUnavailable as e:         # raised on every rank together
+                _p2p.fall_back_to_nccl(e)
+        if a is not None:
             self.p2p = a
             self.gathered_scales = a.slots("emb_scale", torch.float32)
             self.grad_scale_local = a.my_slot("emb_scale", torch.float32, T)
