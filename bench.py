@@ -187,6 +187,38 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
+def exchange_microbench(dlrm, world, barrier, iters=20):
+    """The two large exchange sites (embedding slots, MLP int8 codes) timed alone, outside the graph, with CUDA
+    events: bus GB/s = payload * (N-1) / time per rank, against 900 GB/s per direction.  Runs after all step
+    timings; every rank takes part (the kernels wait for each other).  Reported, never fatal."""
+    try:
+        g, d = dlrm.emb_group, dlrm._dense_arena
+        if g.p2p is None or d.p2p is None:
+            return {"transport": "nccl", "note": "NVLink peer arenas not in use"}
+        sites = (("emb_slot", g.p2p, g.status), ("mlp_codes", d.p2p, d.status))
+
+        def round_trip():
+            for name, arena, status in sites:
+                arena.allgather(name, status)
+        for _ in range(3):
+            round_trip()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            round_trip()
+        e1.record()
+        barrier()
+        us = 1000.0 * e0.elapsed_time(e1) / iters
+        payload = sum(arena.sites[name]["stride"] for name, arena, _ in sites)
+        return {"transport": "nvlink peer memory", "sites": [n for n, _, _ in sites], "bytes_per_rank": payload,
+                "us_per_pair_of_allgathers": us, "bus_gbs": payload * (world - 1) / (us * 1e-6) / 1e9,
+                "nominal_gbs_per_direction": 900.0,
+                "note": "two back-to-back one-kernel all-gathers incl. launch and flag round trip; latency-bound at these sizes"}
+    except Exception as e:                                        # pragma: no cover
+        return {"error": repr(e)}
+
+
 def finish(world):
     """Multi-rank exit.  destroy_process_group() with NCCL collectives captured in live CUDA graphs was seen
     to hang at N=8 (the processes never exited); leave the communicator to process teardown and exit hard
@@ -339,6 +371,7 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     algo_bytes = table_bytes / world if dlrm.shard_scan else table_bytes
     achieved = algo_bytes / (scan_ms / 1000.0) / 1e9
+    nvlink = exchange_microbench(dlrm, world, barrier) if world > 1 else None
     if rank != 0:
         finish(world)
         return
@@ -369,11 +402,14 @@ def run_ours(args):
                      "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_SCAN_TRAFFIC.get((args.workload, world, args.scale_policy)),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": scan_ms,
                      "share_of_step": scan_ms / (ms_dev / args.steps)},
         "clocks": clocks,
     }
     line.update(extras)
+    if nvlink is not None:
+        line["nvlink_exchange"] = nvlink
     if world == 1 and not args.no_cpu_baseline:
         del step, dlrm
         torch.cuda.empty_cache()

@@ -112,16 +112,22 @@ class PeerArena:
     def local_group(cls, sites, world, device="cuda"):
         """W arenas in this process (tests): returns [PeerArena for rank 0..W-1]."""
         lib = _lib.load()
-        sizer = cls.__new__(cls)
-        total = 0
-        for _, slot_bytes in sites.items():
-            total += (int(lib.dqrm_p2p_site_bytes(world, int(slot_bytes))) + 255) // 256 * 256
+        total = sum((int(lib.dqrm_p2p_site_bytes(world, int(b))) + 255) // 256 * 256 for b in sites.values())
         bufs = [torch.zeros(max(total, 256), dtype=torch.uint8, device=device) for _ in range(world)]
         arenas = [cls(sites, world, r, device, _local=[b.data_ptr() for b in bufs]) for r in range(world)]
         for a in arenas:
-            a._keep = bufs
-        del sizer
+            a._keep = bufs                           # the arenas alias these tensors
         return arenas
+
+    def close(self):
+        """Unmap the peers' arenas and free the local one (collective in spirit: call on every rank, after a
+        barrier, when no exchange is in flight).  Views handed out by slots()/my_slot() must not be used afterwards."""
+        for q in self._opened:
+            self.lib.dqrm_p2p_close(q)
+        self._opened = []
+        if getattr(self, "_keep", None) is None and self.base:
+            self.lib.dqrm_p2p_free(self.base)
+        self.base = None
 
     # ---- views of the LOCAL arena ---------------------------------------------------------------------------
     def slots(self, name, dtype=torch.uint8):

@@ -148,3 +148,32 @@ def test_world2_gloo_host_logic(tmp_path):
     for r in (r0, r1):
         assert torch.all(r["w"] == 1.5) and torch.all(r["b"] == 15.0)
         assert r["g"].tolist() == [0.0, 0.0, 1.0, 1.0]
+
+
+def test_p2p_site_layout_host_functions():
+    """Peer-arena site geometry (pure host code of the library): ctl | flags | slots, 16-byte aligned slots."""
+    import ctypes as C
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    lib = _lib.load()
+    for world in (1, 2, 8, 16):
+        for slot in (1, 104, 6496, 66672, 475985):
+            fo, do, st = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            assert lib.dqrm_p2p_site_layout(world, slot, C.byref(fo), C.byref(do), C.byref(st)) == 0
+            assert fo.value == 16 and do.value % 16 == 0 and do.value >= 16 + 4 * world
+            assert st.value % 16 == 0 and slot <= st.value < slot + 16
+            assert lib.dqrm_p2p_site_bytes(world, slot) == do.value + world * st.value
+    # argument checking happens on the host, before any launch
+    assert lib.dqrm_p2p_allgather(None, 2, 0, 0, 64, None, None) == -22
+    assert b"null" in lib.dqrm_last_error()
+
+
+def test_exchange_backend_env(monkeypatch):
+    from deep_quantized_recommendation_model_dqrm_b200 import p2p
+    monkeypatch.delenv("DQRM_EXCHANGE", raising=False)
+    assert p2p.backend() == "p2p"
+    monkeypatch.setenv("DQRM_EXCHANGE", "NCCL")
+    assert p2p.backend() == "nccl"
+    monkeypatch.setenv("DQRM_EXCHANGE", "gloo")
+    import pytest
+    with pytest.raises(ValueError):
+        p2p.backend()
