@@ -353,6 +353,23 @@ def sgd_sparse_spec(W: np.ndarray, rows, values, lr: float) -> None:
         W[r] = (W[r] + (v * a).astype(F32)).astype(F32)
 
 
+def rwsadagrad_rows_spec(W: np.ndarray, momentum: np.ndarray, rows, sums, lr: float, eps: float = 1e-10) -> None:
+    """(f-2) row-wise sparse Adagrad on COALESCED row gradients, optim/rwsadagrad.py:97-113:
+    ``m[row] += mean_d(g^2)``; ``std = sqrt(m[row]) + eps``; ``W[row] += (-clr) * (g / std)``.  In place.
+    (The mean over the row is a float32 sum / D; torch's reduction order inside a row is not a contract, so the
+    golden check allows fp32 rounding.)"""
+    rows = np.asarray(rows)
+    g = np.asarray(sums, dtype=F32)
+    D = F32(g.shape[1])
+    sq = (g * g).astype(F32)
+    acc = np.zeros(g.shape[0], dtype=F32)
+    for d in range(g.shape[1]):
+        acc = (acc + sq[:, d]).astype(F32)
+    momentum[rows] = (momentum[rows] + (acc / D).astype(F32)).astype(F32)
+    std = (np.sqrt(momentum[rows]).astype(F32) + F32(eps)).astype(F32)
+    W[rows] = (W[rows] + (F32(-lr) * (g / std[:, None]).astype(F32)).astype(F32)).astype(F32)
+
+
 def topk_rows_spec(uniq_rows, sums, k: int):
     """(a8) north-star extension, no DQRM reference semantics (parity
     unpinned).  Score = ||g_row||^2 / D as in the only top-k in the tree

@@ -20,6 +20,7 @@ Reference entry points exercised (file:line):
   clear_gradients, grad_update_parallel_comm, weight_update_parallel_comm, weight_syncc
                                                sgd_quantized_gradients_parallel_comm.py:714,257,601,963
   DLRM_Net.forward / interact_features         dlrm_s_pytorch_comm_grad.py:809,701
+  RWSAdagrad.step (sparse branch)              optim/rwsadagrad.py:97-113
 The only modification is the ``.cuda()`` no-op shim (quant_utils.py:336 hard-codes
 ``.cuda()``).
 """
@@ -157,7 +158,7 @@ def model_state(m):
     return d
 
 
-def dp_worker(rank, world, port, steps, multihot, out_path):
+def dp_worker(rank, world, port, steps, multihot, out_path, emb_q=True):
     """One rank of the reference's custom DP loop (drv:1909-1957) on CPU/Gloo."""
     import torch.distributed as dist
     qm, qu, sgd = import_reference()
@@ -188,16 +189,16 @@ def dp_worker(rank, world, port, steps, multihot, out_path):
         E = torch.nn.BCELoss(reduction="mean")(Z, T[sl])
         sgd.clear_gradients(m)
         E.backward()
-        sgd.grad_update_parallel_comm(m, world, emb_grad_quantized=True, num_bits=8, ranking_range=False,
+        sgd.grad_update_parallel_comm(m, world, emb_grad_quantized=emb_q, num_bits=8, ranking_range=False,
                                       rank_for_debug=rank, iteration_count=step)
         rec[f"loss{step}"] = float(E.detach())
         for k, Etab in enumerate(m.emb_l):
             g = Etab.embedding_bag.weight.grad.coalesce()
             rec[f"s{step}_emb{k}_rows"] = _np(g.indices()[0]).copy()
-            rec[f"s{step}_emb{k}_qbar"] = _np(g.values()).copy()
+            rec[f"s{step}_emb{k}_qbar"] = _np(g.values()).copy()     # emb_q=False: the averaged fp32 row gradients
             rec[f"s{step}_emb{k}_sbar"] = _np(Etab.emb_scaling_factor).copy()
             rec[f"s{step}_emb{k}_eb_scale"] = _np(Etab.eb_scaling_factor).copy()
-        sgd.weight_update_parallel_comm(m, lr, emb_grad_quantized=True, update_embedding=True, num_gpus=world,
+        sgd.weight_update_parallel_comm(m, lr, emb_grad_quantized=emb_q, update_embedding=True, num_gpus=world,
                                         rank_for_debug=rank)
     for k, v in model_state(m).items():
         rec["final_" + k] = v
@@ -205,10 +206,10 @@ def dp_worker(rank, world, port, steps, multihot, out_path):
     dist.destroy_process_group()
 
 
-def gen_dp(world, multihot, name, port):
+def gen_dp(world, multihot, name, port, emb_q=True):
     import torch.multiprocessing as mp
     tmp = os.path.join(GOLD, name + "_rank{rank}.npz")
-    mp.spawn(dp_worker, args=(world, port, 2, multihot, tmp), nprocs=world, join=True)
+    mp.spawn(dp_worker, args=(world, port, 2, multihot, tmp, emb_q), nprocs=world, join=True)
     # ranks must agree on everything except the per-rank loss; keep rank 0 + all losses
     recs = [dict(np.load(tmp.format(rank=r))) for r in range(world)]
     for r in range(1, world):
@@ -246,8 +247,38 @@ def gen_interact():
                             R=_np(R), dR=_np(dR), dx=_np(x.grad), dly=np.stack([_np(t.grad) for t in ly]))
 
 
+def gen_rwsadagrad():
+    """optim/rwsadagrad.py (the reference's CPU-only row-wise sparse Adagrad) on sparse gradients with
+    duplicate rows: 4 steps, state and weights after every step."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from optim.rwsadagrad import RWSAdagrad
+    rng = np.random.RandomState(41)
+    rows, dim, lr, eps = 60, 16, 0.05, 1e-10
+    W0 = synthetic.table_weights_numpy(rows, dim, rng)
+    W = torch.nn.Parameter(torch.tensor(W0))
+    opt = RWSAdagrad([W], lr=lr, eps=eps)
+    rec = dict(W_init=W0, rows=rows, dim=dim, lr=lr, eps=eps, steps=4)
+    for step in range(4):
+        idx = rng.randint(0, rows, size=24).astype(np.int64)
+        vals = (rng.randn(24, dim) * 10.0 ** rng.uniform(-3, 0)).astype(np.float32)
+        W.grad = torch.sparse_coo_tensor(torch.from_numpy(idx)[None], torch.from_numpy(vals), size=(rows, dim))
+        opt.step()
+        rec[f"idx{step}"], rec[f"vals{step}"] = idx, vals
+        rec[f"W{step}"] = _np(W.data).copy()
+        rec[f"m{step}"] = _np(opt.state[W]["momentum"]).copy()
+    np.savez_compressed(os.path.join(GOLD, "rwsadagrad_rows.npz"), **rec)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-rwsadagrad" in sys.argv:
+        gen_rwsadagrad()
+        return
+    if "--only-unquantized" in sys.argv:
+        import_reference()
+        gen_dp(2, False, "dp2_unquantized", 29615, emb_q=False)
+        return
     qm, qu, sgd = import_reference()
     gen_embeddings(qm)
     gen_linear(qm)
@@ -256,6 +287,8 @@ def main():
     gen_dp(2, False, "dp2_onehot", 29612)
     gen_dp(2, True, "dp2_multihot", 29613)
     gen_dp(4, False, "dp4_onehot", 29614)
+    gen_rwsadagrad()
+    gen_dp(2, False, "dp2_unquantized", 29615, emb_q=False)     # emb_grad_quantized=False (sgd:319-329, 626)
     tot = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print("golden files:", sorted(os.listdir(GOLD)), "total bytes:", tot)
 

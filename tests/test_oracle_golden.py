@@ -210,3 +210,47 @@ def test_int4_pack_roundtrip_and_onehot_equivalence():
     off = np.arange(40)
     _, _, out = O.embbag_forward_spec(W, idx, off, 4)
     assert np.array_equal(O.embbag_forward_int4_spec(packed, idx, off, s), out)            # one-index bags
+
+
+def test_rwsadagrad_rows_spec_vs_reference_optimizer():
+    """oracle.rwsadagrad_rows_spec (what dqrm_sgd_rows with momentum must reproduce) against 4 steps of the
+    reference's optim/rwsadagrad.py on sparse gradients with duplicate rows."""
+    g = load_golden("rwsadagrad_rows")
+    W = g["W_init"].copy()
+    m = np.zeros(int(g["rows"]), dtype=np.float32)
+    for step in range(int(g["steps"])):
+        rows, sums = O.coalesce_spec(g[f"idx{step}"], g[f"vals{step}"])[:2]
+        O.rwsadagrad_rows_spec(W, m, rows, sums, float(g["lr"]), float(g["eps"]))
+        np.testing.assert_allclose(m, g[f"m{step}"], rtol=2e-6, atol=1e-12)
+        np.testing.assert_allclose(W, g[f"W{step}"], rtol=1e-5, atol=1e-7)
+
+
+def test_dp_unquantized_exchange_vs_reference():
+    """emb_grad_quantized=False (sgd:319-329, 626): 2 Gloo ranks of the reference against the oracle replicas --
+    union rows exact, averaged fp32 row gradients, losses and final weights within 1e-5."""
+    g = load_golden("dp2_unquantized")
+    world = int(g["world"])
+    models = build_oracle_models(world, C_SMALL)
+    for step in range(2):
+        batches = [_shard(world, r, False, step, C_SMALL["rows"]) for r in range(world)]
+        losses = []
+        for m, (X, lS_o, lS_i, T) in zip(models, batches):
+            Z = m(X, lS_o, lS_i)
+            E = torch.nn.functional.binary_cross_entropy(Z, T)
+            O.clear_gradients_torch(m)
+            E.backward()
+            losses.append(float(E.detach()))
+        O.grad_update_torch(models, emb_grad_quantized=False)
+        for r in range(world):
+            assert abs(losses[r] - float(g[f"rank{r}_loss{step}"])) <= 1e-5 * abs(losses[r]) + 1e-7
+        for k, e in enumerate(models[0].emb_l):
+            assert np.array_equal(e.grad_rows.numpy(), g[f"s{step}_emb{k}_rows"]), (step, k)
+            np.testing.assert_allclose(e.grad_q.numpy(), g[f"s{step}_emb{k}_qbar"], rtol=RTOL, atol=1e-9)
+        for m in models:
+            O.weight_update_torch(m, 0.1, emb_grad_quantized=False)
+    m0 = models[0]
+    for k, e in enumerate(m0.emb_l):
+        np.testing.assert_allclose(e.embedding_bag.weight.data.numpy(), g[f"final_emb{k}"], rtol=RTOL, atol=1e-7)
+    for grp, layers in (("bot", m0.bot_l), ("top", m0.top_l)):
+        for i, l in enumerate(layers):
+            np.testing.assert_allclose(l.weight.data.numpy(), g[f"final_{grp}{i}_W"], rtol=RTOL, atol=1e-7)
