@@ -257,6 +257,7 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
 }
 
 // cluster size: enough K-slices to put >= ~128 CTAs on the chip, each slice >= 2 K-tiles
+// (DQRM_MLP_MAX_CLUSTER caps it -- a diagnostic knob: 1 = no cluster launch at all)
 static int pick_split(int tiles, int K) {
   static const int max_s = [] { const char* e = getenv("DQRM_MLP_MAX_CLUSTER"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   int S = 1;

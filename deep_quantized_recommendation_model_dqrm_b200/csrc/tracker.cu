@@ -396,33 +396,20 @@ extern "C" int dqrm_blockmax_scan(int num_tables, const float* const* weight, co
   const int cap = pipe_ctas_per_sm();
   if (cap > 0 && grid > (long long)cap * kSMs) grid = (long long)cap * kSMs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // The pass uses no shared memory, so the driver would configure the SMs it occupies for maximum L1 -- and a
-  // kernel of the step that needs shared memory could then not become co-resident until the pass has drained.
-  // Ask for the largest shared-memory carve-out instead (the pass streams with L1 no-allocate anyway).
+  // The pass uses no shared memory; ask for the largest shared-memory carve-out anyway so that the SMs it occupies
+  // stay configured for kernels of the step that do need shared memory (the pass streams with L1 no-allocate).
   static const bool carveout_set = [] {
-    const bool e = getenv("DQRM_PIPE_NO_CARVEOUT") != nullptr;
-    if (!e) {
-      cudaFuncSetAttribute(blockmax_scan_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
-      cudaFuncSetAttribute(blockmax_scan_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
-    }
+    cudaFuncSetAttribute(blockmax_scan_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(blockmax_scan_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     return true;
   }();
   (void)carveout_set;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kPipeThreads);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;           // experiment: dispatch the pass as a 1x1x1-cluster grid
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = getenv("DQRM_PIPE_CLUSTER") ? 1 : 0;
-  cudaError_t le;
-  if (wide) le = cudaLaunchKernelEx(&cfg, blockmax_scan_kernel<true>, a, dim / 8, block_rows, (int)bpu, (int)units);
-  else le = cudaLaunchKernelEx(&cfg, blockmax_scan_kernel<false>, a, dim / 4, block_rows, (int)bpu, (int)units);
-  DQRM_REQUIRE(le == cudaSuccess, -EIO, "blockmax_scan_kernel: %s", cudaGetErrorString(le));
+  if (wide)
+    blockmax_scan_kernel<true><<<(unsigned)grid, kPipeThreads, 0, st>>>(a, dim / 8, block_rows, (int)bpu, (int)units);
+  else
+    blockmax_scan_kernel<false><<<(unsigned)grid, kPipeThreads, 0, st>>>(a, dim / 4, block_rows, (int)bpu, (int)units);
   DQRM_LAUNCH_CHECK("blockmax_scan_kernel");
   return 0;
 }

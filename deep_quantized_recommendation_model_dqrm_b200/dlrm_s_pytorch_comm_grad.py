@@ -381,6 +381,23 @@ def make_parser():
     p.add_argument("--num-indices-per-lookup", type=int, default=10)
     p.add_argument("--num-indices-per-lookup-fixed", type=bool, default=False)
     p.add_argument("--max-ind-range", type=int, default=-1)
+    p.add_argument("--rand-data-dist", type=str, default="uniform")
+    p.add_argument("--rand-data-min", type=float, default=0)
+    p.add_argument("--rand-data-max", type=float, default=1)
+    p.add_argument("--rand-data-mu", type=float, default=-1)
+    p.add_argument("--rand-data-sigma", type=float, default=1)
+    p.add_argument("--data-trace-file", type=str, default="./input/dist_emb_j.log")
+    p.add_argument("--data-trace-enable-padding", type=bool, default=False)
+    p.add_argument("--data-set", type=str, default="kaggle")
+    p.add_argument("--raw-data-file", type=str, default="")
+    p.add_argument("--processed-data-file", type=str, default="")
+    p.add_argument("--data-randomize", type=str, default="total")
+    p.add_argument("--data-sub-sample-rate", type=float, default=0.0)
+    p.add_argument("--memory-map", action="store_true", default=False)
+    p.add_argument("--dataset-multiprocessing", action="store_true", default=False)
+    p.add_argument("--num-workers", type=int, default=0)
+    p.add_argument("--test-mini-batch-size", type=int, default=-1)
+    p.add_argument("--test-num-workers", type=int, default=-1)
     p.add_argument("--mini-batch-size", type=int, default=1)
     p.add_argument("--nepochs", type=int, default=1)
     p.add_argument("--learning-rate", type=float, default=0.01)
@@ -414,4 +431,82 @@ def parse_args(argv=None):
     if args.linear_channel:                      # dlrm_s_pytorch_comm_grad.py:1155-1156
         args.quantize_activation = False
     args.world_size = args.gpus * args.nodes     # :1158
+    if args.test_mini_batch_size < 0:            # :1370-1373
+        args.test_mini_batch_size = args.mini_batch_size
+    if args.test_num_workers < 0:
+        args.test_num_workers = args.num_workers
     return args
+
+
+def train(args, rank=0, world_size=1, device=None, log=print):
+    """The training loop of the reference's train() (dlrm_s_pytorch_comm_grad.py:1400-1995), hot-path subset:
+    build the loaders (random or pre-processed Criteo), the model, and run the custom-DP iteration for
+    --nepochs / --num-batches, printing the loss every --print-freq iterations.  Evaluation, checkpoints,
+    TensorBoard and LR schedules are outside the hot path.  Returns the list of per-iteration losses."""
+    from . import dlrm_data_pytorch as dp
+    if not torch.cuda.is_available():
+        raise _lib.DqrmLibraryError("train(): no CUDA device -- the product path has no CPU fallback")
+    device = torch.device(device if device is not None else ("cuda", rank % torch.cuda.device_count()))
+    torch.cuda.set_device(device)
+    np.random.seed(args.numpy_rand_seed)
+    torch.manual_seed(args.numpy_rand_seed)
+    ln_bot = np.fromstring(args.arch_mlp_bot, dtype=int, sep="-")
+    if args.data_generation == "dataset":
+        train_data, train_ld, _, _ = dp.make_criteo_data_and_loaders(args)
+        ln_emb = np.array(train_data.counts)
+        if args.max_ind_range > 0:               # :1476-1478
+            ln_emb = np.array([min(int(c), args.max_ind_range) for c in ln_emb])
+        m_den = train_data.m_den
+        ln_bot[0] = m_den
+    else:
+        ln_emb = np.fromstring(args.arch_embedding_size, dtype=int, sep="-")
+        m_den = ln_bot[0]
+        train_data, train_ld, _, _ = dp.make_random_data_and_loader(args, ln_emb, m_den)
+    m_spa = args.arch_sparse_feature_size
+    num_int = ln_emb.size + 1
+    n_pairs = num_int * (num_int + 1) // 2 if args.arch_interaction_itself else num_int * (num_int - 1) // 2
+    ln_top = np.fromstring(str(m_spa + n_pairs) + "-" + args.arch_mlp_top, dtype=int, sep="-")   # :1500-1519
+    if m_spa != ln_bot[-1]:
+        sys.exit("ERROR: arch-sparse-feature-size " + str(m_spa) + " does not match last dim of bottom mlp "
+                 + str(ln_bot[-1]))
+    global full_precision_flag
+    full_precision_flag = args.pretrain_and_quantize
+    dlrm = DLRM_Net(m_spa, ln_emb, ln_bot, ln_top, arch_interaction_op=args.arch_interaction_op,
+                    arch_interaction_itself=args.arch_interaction_itself, sigmoid_bot=-1, sigmoid_top=ln_top.size - 2,
+                    loss_threshold=args.loss_threshold, loss_function=args.loss_function,
+                    quantization_flag=args.quantization_flag, embedding_bit=args.embedding_bit,
+                    weight_bit=args.weight_bit, quantize_act_and_lin=args.quantize_act_and_lin,
+                    mlp_channelwise=args.linear_channel, quantize_activation=args.quantize_activation,
+                    device=device, table_seed=args.numpy_rand_seed)
+    dlrm._ensure_group().scale_policy = args.scale_policy
+    dlrm.scale_update_period = args.scale_update_period
+    dlrm.shard_scan = world_size > 1
+    losses, it = [], 0
+    for epoch in range(args.nepochs):
+        for X, lS_o, lS_i, T in train_ld:
+            if world_size > 1 and T.shape[0] % world_size != 0:       # ragged last batch is skipped (:1900-1905)
+                log("Warning: Skiping the batch %d with size %d" % (it, T.shape[0]))
+                continue
+            E = train_iteration(dlrm, X, lS_o, lS_i, T, args.learning_rate, world_size=world_size, rank=rank,
+                                device=device, quantize_embedding_bag_gradient=args.quantize_embedding_bag_gradient,
+                                embedding_bag_gradient_bit_num=args.embedding_bag_gradient_bit_num, args=args)   # :1940-1957
+            it += 1
+            if args.print_freq > 0 and it % args.print_freq == 0:
+                losses.append(float(E))                                # the reference syncs here too (:1928)
+                log("Finished training it {}/{} of epoch {}, loss {:.6f}".format(it, len(train_ld), epoch, losses[-1]))
+            if args.num_batches > 0 and it >= args.num_batches * (epoch + 1):
+                break
+    dlrm._ensure_group().check_status()
+    return losses
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    if args.world_size > 1:
+        raise SystemExit("multi-GPU runs are launched with torchrun through bench.py / GraphedTrainStep; "
+                         "this entry point is the single-process loop")
+    train(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,88 @@
+"""CPU: the input side of the hot path (deep_quantized_recommendation_model_dqrm_b200/dlrm_data_pytorch.py) against
+batches produced by the REFERENCE's dlrm_data_pytorch.py (oracle/make_golden_data.py): the random-data generator
+must reproduce the reference's batches bit for bit from the same numpy seed; the Criteo reader + collate must
+reproduce its splits, randomisation, index folding (max-ind-range) and tensors exactly."""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+from conftest import load_golden
+from deep_quantized_recommendation_model_dqrm_b200 import dlrm_data_pytorch as dp
+import make_golden_data as G
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", sorted(G.RANDOM_CASES))
+def test_random_dataset_reproduces_reference_batches(name):
+    ln_emb, m_den, mb, nb, P, fixed, rt, dist, seed = G.RANDOM_CASES[name]
+    g = load_golden(name)
+    args = SimpleNamespace(data_size=0, num_batches=nb, mini_batch_size=mb, num_indices_per_lookup=P,
+                           num_indices_per_lookup_fixed=fixed, round_targets=rt, data_generation="random",
+                           numpy_rand_seed=seed, **dist)
+    np.random.seed(999)                                   # the loader reseeds on access to item 0
+    train_data, train_loader, _, _ = dp.make_random_data_and_loader(args, np.array(ln_emb), m_den)
+    assert len(train_data) == nb
+    for epoch in range(2):                                # identical samples every epoch (reset_seed_on_access)
+        for j, (X, lS_o, lS_i, T) in enumerate(train_loader):
+            assert X.dtype == torch.float32 and lS_o.dtype == torch.int64 and T.shape == (mb, 1)
+            assert np.array_equal(X.numpy(), g[f"b{j}_X"]) and np.array_equal(T.numpy(), g[f"b{j}_T"])
+            assert np.array_equal(lS_o.numpy(), g[f"b{j}_lS_o"])
+            assert len(lS_i) == len(ln_emb)
+            for k, t in enumerate(lS_i):
+                assert t.dtype == torch.int64 and np.array_equal(t.numpy(), g[f"b{j}_lS_i{k}"]), (j, k)
+
+
+@pytest.mark.parametrize("split,randomize,mir", G.CRITEO_CASES)
+def test_criteo_dataset_and_collate_vs_reference(split, randomize, mir):
+    g = load_golden("data_criteo_tiny")
+    fix = os.path.join(GOLD, "criteo_tiny")
+    np.random.seed(31)
+    ds = dp.CriteoDataset("kaggle", mir, 0.0, randomize, split, os.path.join(fix, "train.txt"),
+                          os.path.join(fix, "kaggleAdDisplayChallenge_processed.npz"))
+    key = f"{split}_{randomize}_{mir}"
+    assert len(ds) == int(g[key + "_len"]) and ds.m_den == 13 and ds.n_emb == 26
+    loader = torch.utils.data.DataLoader(ds, batch_size=8, shuffle=False, collate_fn=dp.collate_wrapper_criteo_offset)
+    for j, (X, lS_o, lS_i, T) in enumerate(loader):
+        if j >= 2:
+            break
+        assert X.dtype == torch.float32 and lS_i.dtype == torch.int64 and lS_o.dtype == torch.int64
+        assert np.array_equal(X.numpy(), g[f"{key}_b{j}_X"])             # log(x + 1): the same torch op
+        assert np.array_equal(lS_o.numpy(), g[f"{key}_b{j}_lS_o"])
+        assert np.array_equal(lS_i.numpy(), g[f"{key}_b{j}_lS_i"])
+        assert np.array_equal(T.numpy(), g[f"{key}_b{j}_T"])
+        if mir > 0:
+            assert int(lS_i.max()) < mir
+
+
+def test_unsupported_inputs_raise():
+    with pytest.raises(ValueError):
+        dp.CriteoDataset("avazu", 0, 0.0, "total", "train", "x/train.txt", "nope.npz")
+    with pytest.raises(NotImplementedError):
+        dp.CriteoDataset("kaggle", 0, 0.0, "total", "train", "x/train.txt", "missing_processed.npz")
+    with pytest.raises(NotImplementedError):
+        dp.RandomDataset(13, [10], 1, 1, 1, 1, False, data_generation="synthetic")
+
+
+def test_packed_layout_matches_collate():
+    """The staging layout used by GraphedTrainStep.load_packed (graph_step._packed_layout) holds exactly the four
+    collated tensors, 16-byte aligned."""
+    from deep_quantized_recommendation_model_dqrm_b200.graph_step import _packed_layout
+    fix = os.path.join(GOLD, "criteo_tiny")
+    np.random.seed(31)
+    ds = dp.CriteoDataset("kaggle", 0, 0.0, "none", "train", os.path.join(fix, "train.txt"),
+                          os.path.join(fix, "kaggleAdDisplayChallenge_processed.npz"))
+    X, lS_o, lS_i, T = dp.collate_wrapper_criteo_offset(ds[0:8])
+    lay, nbytes = _packed_layout(X, lS_o, lS_i, T)
+    buf = torch.zeros(nbytes, dtype=torch.uint8)
+    for (o, n, dt, shape), t in zip(lay, (X, lS_o, lS_i, T)):
+        assert o % 16 == 0
+        buf[o:o + n].view(dt).view(shape).copy_(t)
+    for (o, n, dt, shape), t in zip(lay, (X, lS_o, lS_i, T)):
+        assert torch.equal(buf[o:o + n].view(dt).view(shape), t)
+    assert nbytes == sum((t.numel() * t.element_size() + 15) // 16 * 16 for t in (X, lS_o, lS_i, T))

@@ -177,3 +177,21 @@ def test_exchange_backend_env(monkeypatch):
     import pytest
     with pytest.raises(ValueError):
         p2p.backend()
+
+
+def test_driver_cli_data_flags_and_cpu_refusal():
+    """The reference's data / loader flags parse with its defaults (dlrm_s_pytorch_comm_grad.py:1039-1096,
+    1370-1373), and the training entry point refuses to run without a GPU instead of falling back."""
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
+    a = drv.parse_args(["--arch-sparse-feature-size=16", "--arch-embedding-size=10000-10000",
+                        "--arch-mlp-bot=13-512-256-64-16", "--arch-mlp-top=512-256-1", "--data-generation=random",
+                        "--mini-batch-size=128", "--num-batches=3", "--quantization_flag", "--embedding_bit=4",
+                        "--weight_bit=4", "--linear_channel", "--quantize_act_and_lin", "--loss-function=bce"])
+    assert (a.data_set, a.data_randomize, a.memory_map, a.num_workers) == ("kaggle", "total", False, 0)
+    assert a.test_mini_batch_size == 128 and a.test_num_workers == 0 and a.rand_data_dist == "uniform"
+    assert a.quantize_activation is False and a.world_size == 1
+    if not torch.cuda.is_available():
+        import pytest
+        with pytest.raises(_lib.DqrmLibraryError):
+            drv.train(a)
