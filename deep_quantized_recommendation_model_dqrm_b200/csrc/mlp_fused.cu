@@ -89,7 +89,11 @@ constexpr int APAD = BM + 4, BPAD = BN + 4;
 // CL = false: the same kernel with no cluster instruction at all (S = 1).  A grid that uses clusters was
 // measured not to become co-resident with a long-running non-cluster grid (the pipelined table rescan,
 // tracker.cu): the step's GEMMs waited for the whole pass.  See DESIGN.md "pipelined rescan".
-template <int MODE, bool CL = true>
+// NT > 0 (experimental, DQRM_GEMM_PREFETCH=1, not yet validated on hardware): the CTA's whole K-slice is at most NT
+// tiles; ALL of its global loads are issued before the first FMA, so the kernel pays one load latency instead of one
+// per K-tile (these GEMMs are latency-bound: ~4 dependent 0.7 us round trips per launch at Kaggle shape).  Same tile
+// order, same FMA order: bit-identical results.  NT = 0 (default): the register double-buffered loop, unchanged.
+template <int MODE, bool CL = true, int NT = 0>
 __global__ void __launch_bounds__(kGemmThreads)
 linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int, const float* __restrict__ b_int,
                    const float* __restrict__ s_row, const float* __restrict__ dout, const float* __restrict__ out,
@@ -166,7 +170,43 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
-  if (kbeg < kend) {
+  if constexpr (NT > 0) {
+    if (kbeg < kend) {                                                  // host guarantees kend - kbeg <= NT * BK
+      float a_all[NT][A_PER_THR], b_all[NT][B_PER_THR];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {                                    // every load of the slice in flight
+#pragma unroll
+        for (int i = 0; i < A_PER_THR; ++i) { int am, ak; a_coord(tid + i * kGemmThreads, am, ak); a_all[t][i] = A_at(m0 + am, kbeg + t * BK + ak); }
+#pragma unroll
+        for (int i = 0; i < B_PER_THR; ++i) { int bk, bn; b_coord(tid + i * kGemmThreads, bk, bn); b_all[t][i] = B_at(kbeg + t * BK + bk, n0 + bn); }
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (kbeg + t * BK < kend) {                                     // CTA-uniform
+          const int buf = t & 1;                                        // last read by tile t-2: every thread passed
+#pragma unroll                                                          // that before the barrier of tile t-1
+          for (int i = 0; i < A_PER_THR; ++i) {
+            int am, ak; a_coord(tid + i * kGemmThreads, am, ak); As[buf][ak][am] = a_all[t][i];
+            if (MODE == 2) db_part = __fadd_rn(db_part, a_all[t][i]);
+          }
+#pragma unroll
+          for (int i = 0; i < B_PER_THR; ++i) { int bk, bn; b_coord(tid + i * kGemmThreads, bk, bn); Bs[buf][bk][bn] = b_all[t][i]; }
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < BK; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
+            const float a[TM] = {av.x, av.y, av.z, av.w}, b[TN] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+              for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          }
+        }
+      }
+      __syncthreads();                                                  // Bs is reused for the partial tile below
+    }
+  } else if (kbeg < kend) {
     fetch(kbeg);
     stash(0);
     __syncthreads();
@@ -286,15 +326,30 @@ static int launch_gemm(const float* x, const float* W_int, const float* b_int, c
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
   cfg.attrs = attr;
   cfg.numAttrs = S > 1 ? 1 : 0;
+  // experimental: prefetch the whole K-slice when it is at most 4 tiles (see the kernel comment); off by default
+  static const bool prefetch = [] { const char* e = getenv("DQRM_GEMM_PREFETCH"); return e && atoi(e) != 0; }();
+  const int nt = (prefetch && kc <= 4 * BK) ? kc / BK : 0;
   cudaError_t e;
-  if (S > 1) {
-    e = cudaLaunchKernelEx(&cfg, linear_gemm_kernel<MODE, true>, x, W_int, b_int, s_row, dout, out, C, db, batch, out_f,
-                           in_f, act, kc, accumulate);
-  } else {
-    linear_gemm_kernel<MODE, false><<<cfg.gridDim, cfg.blockDim, 0, st>>>(x, W_int, b_int, s_row, dout, out, C, db, batch,
-                                                                          out_f, in_f, act, kc, accumulate);
-    e = cudaGetLastError();
+#define DQRM_GEMM_LAUNCH(NTV)                                                                                        \
+  do {                                                                                                               \
+    if (S > 1) {                                                                                                     \
+      e = cudaLaunchKernelEx(&cfg, linear_gemm_kernel<MODE, true, NTV>, x, W_int, b_int, s_row, dout, out, C, db,    \
+                             batch, out_f, in_f, act, kc, accumulate);                                               \
+    } else {                                                                                                         \
+      linear_gemm_kernel<MODE, false, NTV><<<cfg.gridDim, cfg.blockDim, 0, st>>>(x, W_int, b_int, s_row, dout, out,  \
+                                                                                 C, db, batch, out_f, in_f, act, kc, \
+                                                                                 accumulate);                        \
+      e = cudaGetLastError();                                                                                        \
+    }                                                                                                                \
+  } while (0)
+  switch (nt) {
+    case 1: DQRM_GEMM_LAUNCH(1); break;
+    case 2: DQRM_GEMM_LAUNCH(2); break;
+    case 3: DQRM_GEMM_LAUNCH(3); break;
+    case 4: DQRM_GEMM_LAUNCH(4); break;
+    default: DQRM_GEMM_LAUNCH(0); break;
   }
+#undef DQRM_GEMM_LAUNCH
   if (e != cudaSuccess) { set_error("linear_gemm_kernel<%d>: %s", MODE, cudaGetErrorString(e)); return -EIO; }
   return 0;
 }
