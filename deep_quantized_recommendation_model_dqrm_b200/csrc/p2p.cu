@@ -62,7 +62,10 @@ p2p_allgather_kernel(const __grid_constant__ PeerPtrs peers, int world, int rank
   __threadfence_system();                    // my remote stores are ordered before anything I signal later
   __syncthreads();
   __shared__ bool s_last;
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctl[1], 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence_system();                  // release side of the arrive counter, in the thread that bumps it
+    s_last = (atomicAdd(&ctl[1], 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();
