@@ -80,12 +80,41 @@ def gen_criteo(dp):
     np.savez_compressed(os.path.join(GOLD, "data_criteo_tiny.npz"), **rec)
 
 
+def gen_terabyte_bin():
+    """data_loader_terabyte.py: numpy_to_binary + CriteoBinDataset on two tiny 'day' files cut from the fixture."""
+    import data_loader_terabyte as dlt
+    with np.load(os.path.join(FIX, "kaggleAdDisplayChallenge_processed.npz")) as d:
+        X_int, X_cat, y = d["X_int"], d["X_cat"], d["y"]
+    days = []
+    for i, (a, b) in enumerate(((0, 33), (33, 70))):
+        path = os.path.join(FIX, f"day_{i}_reordered.npz")
+        np.savez_compressed(path, X_int=X_int[a:b], X_cat=X_cat[a:b], y=y[a:b])
+        days.append(path)
+    rec = {}
+    for split, files in (("train", days), ("test", days[1:]), ("val", days[1:])):
+        out = os.path.join(FIX, f"{split}_data.bin")
+        dlt.numpy_to_binary(files, out, split)
+        rec[f"{split}_bytes"] = np.frombuffer(open(out, "rb").read(), dtype=np.uint8)
+        for mir in (-1, 1000):
+            ds = dlt.CriteoBinDataset(out, os.path.join(FIX, "kaggleAdDisplayChallenge_processed.npz"), batch_size=16,
+                                      max_ind_range=mir)
+            rec[f"{split}_{mir}_len"] = len(ds)
+            for j in (0, len(ds) - 1):
+                X, lS_o, lS_i, T = ds[j]
+                rec[f"{split}_{mir}_b{j}_X"], rec[f"{split}_{mir}_b{j}_lS_o"] = X.numpy(), lS_o.numpy()
+                rec[f"{split}_{mir}_b{j}_lS_i"], rec[f"{split}_{mir}_b{j}_T"] = lS_i.numpy(), T.numpy()
+            del ds
+        os.remove(out)                       # the tests rebuild it with OUR writer and compare the bytes
+    np.savez_compressed(os.path.join(GOLD, "data_terabyte_bin.npz"), **rec)
+
+
 def main():
     sys.path.insert(0, REF)
     import dlrm_data_pytorch as dp
     gen_random(dp)
     write_criteo_fixture()
     gen_criteo(dp)
+    gen_terabyte_bin()
     print("ok")
 
 

@@ -86,3 +86,31 @@ def test_packed_layout_matches_collate():
     for (o, n, dt, shape), t in zip(lay, (X, lS_o, lS_i, T)):
         assert torch.equal(buf[o:o + n].view(dt).view(shape), t)
     assert nbytes == sum((t.numel() * t.element_size() + 15) // 16 * 16 for t in (X, lS_o, lS_i, T))
+
+
+@pytest.mark.parametrize("split", ["train", "test", "val"])
+def test_terabyte_binary_writer_and_reader_vs_reference(split, tmp_path):
+    """data_loader_terabyte: our numpy_to_binary writes the reference's bytes, and CriteoBinDataset returns the
+    reference's batches (first and short last batch, with and without max-ind-range folding)."""
+    from deep_quantized_recommendation_model_dqrm_b200 import data_loader_terabyte as dlt
+    g = load_golden("data_terabyte_bin")
+    fix = os.path.join(GOLD, "criteo_tiny")
+    days = [os.path.join(fix, f"day_{i}_reordered.npz") for i in range(2)]
+    out = str(tmp_path / f"{split}_data.bin")
+    dlt.numpy_to_binary(days if split == "train" else days[1:], out, split)
+    assert np.array_equal(np.frombuffer(open(out, "rb").read(), dtype=np.uint8), g[f"{split}_bytes"])
+    counts = os.path.join(fix, "kaggleAdDisplayChallenge_processed.npz")
+    for mir in (-1, 1000):
+        ds = dlt.CriteoBinDataset(out, counts, batch_size=16, max_ind_range=mir)
+        assert len(ds) == int(g[f"{split}_{mir}_len"]) and ds.m_den == 13 and len(ds.counts) == 26
+        for j in (0, len(ds) - 1):
+            X, lS_o, lS_i, T = ds[j]
+            assert X.dtype == torch.float32 and lS_i.dtype == torch.int64 and lS_o.dtype == torch.int64
+            assert np.array_equal(X.numpy(), g[f"{split}_{mir}_b{j}_X"])
+            assert np.array_equal(lS_o.numpy(), g[f"{split}_{mir}_b{j}_lS_o"])
+            assert np.array_equal(lS_i.numpy(), g[f"{split}_{mir}_b{j}_lS_i"])
+            assert np.array_equal(T.numpy(), g[f"{split}_{mir}_b{j}_T"])
+        with pytest.raises(IndexError):
+            ds[len(ds)]
+    with pytest.raises(ValueError):
+        dlt.numpy_to_binary(days, out, "test")
