@@ -320,6 +320,22 @@ class EmbeddingTableGroup:
         self.packed, self.packed_buf, self.packed_scale = views, buf, self.scale.clone()
         return views, self.packed_scale
 
+    def save_int4(self, path):
+        """pack_int4() (if not done yet) and write the tables + scales as one file (int4_checkpoint.py)."""
+        from . import int4_checkpoint
+        if getattr(self, "packed", None) is None:
+            self.pack_int4()
+        return int4_checkpoint.save(path, self.packed, self.packed_scale, self.dim)
+
+    def load_int4(self, path):
+        """Read an INT4 table file onto this group's device for forward_int4(); shapes must match the group."""
+        from . import int4_checkpoint
+        packed, scale, rows, dim = int4_checkpoint.load(path, device=self.device)
+        if rows != self.rows or dim != self.dim:
+            raise ValueError(f"{path}: tables {rows} x {dim} do not match this group ({self.rows} x {self.dim})")
+        self.packed, self.packed_scale = packed, scale
+        return packed, scale
+
     def forward_int4(self, indices, offsets, idx_begin, bags, packed=None, scale=None, out=None):
         """Gather + dequantise + sum-pool straight from the packed INT4 tables."""
         packed = packed if packed is not None else self.packed

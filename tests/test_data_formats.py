@@ -114,3 +114,38 @@ def test_terabyte_binary_writer_and_reader_vs_reference(split, tmp_path):
             ds[len(ds)]
     with pytest.raises(ValueError):
         dlt.numpy_to_binary(days, out, "test")
+
+
+def test_int4_table_file_roundtrip(tmp_path):
+    """int4_checkpoint: tables packed by the oracle spec (the bytes dqrm_table_pack_int4 produces, pinned on the GPU
+    by tests/test_gpu_parity.py) survive save -> load bit for bit, the layout is 256-byte aligned, and the serving
+    forward on the loaded file equals the one on the original arrays."""
+    import warnings
+    from oracle import dqrm_oracle as O
+    from deep_quantized_recommendation_model_dqrm_b200 import int4_checkpoint as ck, synthetic
+    rng = np.random.RandomState(4)
+    rows, dim = [3, 1000, 257], 16
+    Ws = [synthetic.table_weights_numpy(n, dim, rng) for n in rows]
+    scales = np.array([O.table_scale_spec(W, 4) for W in Ws], dtype=np.float32)
+    packed = [O.pack_int4_spec(W, s) for W, s in zip(Ws, scales)]
+    path = str(tmp_path / "tables.dqrm4")
+    total = ck.save(path, packed, scales, dim)
+    head, offs, want_total = ck.layout(rows, dim)
+    assert total == want_total == os.path.getsize(path) and all(o % 256 == 0 for o in offs) and head == offs[0]
+    assert total < sum(W.nbytes for W in Ws) // 7                      # ~8x smaller than fp32 (+ alignment)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                                # torch warns about the read-only map
+        got, sc, got_rows, got_dim = ck.load(path)
+    assert got_rows == rows and got_dim == dim and np.array_equal(sc.numpy(), scales)
+    for a, b in zip(packed, got):
+        assert np.array_equal(a, b.numpy())
+    idx = rng.randint(0, 1000, size=40)
+    off = np.arange(0, 40, 4)
+    assert np.array_equal(O.embbag_forward_int4_spec(got[1].numpy(), idx, off, sc[1].item()),
+                          O.embbag_forward_int4_spec(packed[1], idx, off, scales[1]))
+    with open(path, "r+b") as f:
+        f.write(b"NOTDQRM!")
+    with pytest.raises(ValueError):
+        ck.load(path)
+    with pytest.raises(ValueError):
+        ck.save(path, [packed[0].astype(np.int8)], scales[:1], dim)
