@@ -195,3 +195,33 @@ def test_driver_cli_data_flags_and_cpu_refusal():
         import pytest
         with pytest.raises(_lib.DqrmLibraryError):
             drv.train(a)
+
+
+def test_c_abi_rejects_bad_arguments_before_any_launch():
+    """Error convention of the boundary (include/dqrm_b200.h): bad arguments return -errno with a message in
+    dqrm_last_error() -- checked on the host, so this runs without a GPU."""
+    import ctypes as C
+    import errno
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
+    lib = _lib.load()
+    one = (C.c_void_p * 1)(16)
+    rows = (C.c_int64 * 1)(10)
+    cases = [
+        (lib.dqrm_table_absmax_scale(0, one, rows, 16, 4, 0, 1, 16, 16, 16, 16, None), -errno.E2BIG, b"num_tables"),
+        (lib.dqrm_table_absmax_scale(1, one, rows, 16, 4, 2, 2, 16, 16, 16, 16, None), -errno.EINVAL, b"shard"),
+        (lib.dqrm_table_absmax_scale(1, one, rows, 16, 1, 0, 1, 16, 16, 16, 16, None), -errno.EINVAL, b"bits"),
+        (lib.dqrm_scale_from_absmax(0, 16, 4, 16, 16, None), -errno.EINVAL, b"scale_from_absmax"),
+        (lib.dqrm_blockmax_scan(1, one, rows, 6, 64, one, 0, 1, None), -errno.EINVAL, b"multiple of 4"),
+        (lib.dqrm_blockmax_reduce(1, rows, 64, one, 0, 1, 4, 16, 16, None, 16, None), -errno.EINVAL, b"scale/inv_scale"),
+        (lib.dqrm_grad_pack(1, 16, None, None, None, 8, None, 1, 1, 8, None, None, None), -errno.EINVAL, b"null"),
+        (lib.dqrm_grad_pack(1, 16, 16, 16, 16, 8, 16, 0, 1, 8, 16, 16, None), -errno.EINVAL, b"scale_stride"),
+        (lib.dqrm_dense_grad_quant_gathered(16, 16, 4, 16, 4, 2, 16, 16, 16, None), -errno.EINVAL, b"int8"),
+        (lib.dqrm_bce_loss_grad(None, None, 4, None, None, None), -errno.EINVAL, b"bce_loss_grad"),
+        (lib.dqrm_p2p_allgather(one, 17, 0, 0, 64, 16, None), -errno.EINVAL, b"world"),
+    ]
+    for i, (rc, want, frag) in enumerate(cases):
+        assert rc == want, (i, rc, want)
+    assert lib.dqrm_grad_pack(1, 16, None, None, None, 8, None, 1, 1, 8, None, None, None) == -errno.EINVAL
+    assert b"null" in lib.dqrm_last_error()
+    assert lib.dqrm_blockmax_scan(1, one, rows, 6, 64, one, 0, 1, None) == -errno.EINVAL
+    assert b"multiple of 4" in lib.dqrm_last_error()
