@@ -402,6 +402,9 @@ def make_parser():
     p.add_argument("--nepochs", type=int, default=1)
     p.add_argument("--learning-rate", type=float, default=0.01)
     p.add_argument("--numpy-rand-seed", type=int, default=123)
+    p.add_argument("--lr-num-warmup-steps", type=int, default=0)
+    p.add_argument("--lr-decay-start-step", type=int, default=0)
+    p.add_argument("--lr-num-decay-steps", type=int, default=0)
     p.add_argument("--optimizer", type=str, default="sgd")
     p.add_argument("--use-gpu", action="store_true", default=False)
     p.add_argument("--print-freq", type=int, default=1)
@@ -436,6 +439,39 @@ def parse_args(argv=None):
     if args.test_num_workers < 0:
         args.test_num_workers = args.num_workers
     return args
+
+
+class LRPolicyScheduler:
+    """The learning rate the reference feeds into weight_update_parallel_comm: ``lr_scheduler.get_lr()[-1]`` of
+    its LRPolicyScheduler (dlrm_s_pytorch_comm_grad.py:221-255, used at :1738, :1957-1960) -- linear warm-up,
+    constant, quadratic decay, then frozen.  Stand-alone (no optimizer object: this path has none); ``step_count``
+    follows torch's _LRScheduler convention that the reference relies on: 1 after construction, +1 per step()."""
+
+    def __init__(self, base_lr, num_warmup_steps, decay_start_step, num_decay_steps):
+        if decay_start_step < num_warmup_steps:
+            sys.exit("Learning rate warmup must finish before the decay starts")
+        self.base_lrs = [float(base_lr)]
+        self.num_warmup_steps, self.decay_start_step = num_warmup_steps, decay_start_step
+        self.num_decay_steps, self.decay_end_step = num_decay_steps, decay_start_step + num_decay_steps
+        self._step_count = 0
+        self.last_lr = list(self.base_lrs)
+        self.step()                                   # _LRScheduler.__init__ performs the initial step
+
+    def get_lr(self):
+        n = self._step_count
+        if n < self.num_warmup_steps:
+            scale = 1.0 - (self.num_warmup_steps - n) / self.num_warmup_steps
+            self.last_lr = [b * scale for b in self.base_lrs]
+        elif self.decay_start_step <= n < self.decay_end_step:
+            scale = ((self.num_decay_steps - (n - self.decay_start_step)) / self.num_decay_steps) ** 2
+            self.last_lr = [max(0.0000001, b * scale) for b in self.base_lrs]
+        elif self.num_decay_steps <= 0:
+            return list(self.base_lrs)
+        return list(self.last_lr)
+
+    def step(self):
+        self._step_count += 1
+        self.get_lr()                                 # the base class evaluates get_lr() inside step()
 
 
 def train(args, rank=0, world_size=1, device=None, log=print):
@@ -481,15 +517,18 @@ def train(args, rank=0, world_size=1, device=None, log=print):
     dlrm._ensure_group().scale_policy = args.scale_policy
     dlrm.scale_update_period = args.scale_update_period
     dlrm.shard_scan = world_size > 1
+    lr_scheduler = LRPolicyScheduler(args.learning_rate, args.lr_num_warmup_steps, args.lr_decay_start_step,
+                                     args.lr_num_decay_steps)
     losses, it = [], 0
     for epoch in range(args.nepochs):
         for X, lS_o, lS_i, T in train_ld:
             if world_size > 1 and T.shape[0] % world_size != 0:       # ragged last batch is skipped (:1900-1905)
                 log("Warning: Skiping the batch %d with size %d" % (it, T.shape[0]))
                 continue
-            E = train_iteration(dlrm, X, lS_o, lS_i, T, args.learning_rate, world_size=world_size, rank=rank,
+            E = train_iteration(dlrm, X, lS_o, lS_i, T, lr_scheduler.get_lr()[-1], world_size=world_size, rank=rank,
                                 device=device, quantize_embedding_bag_gradient=args.quantize_embedding_bag_gradient,
                                 embedding_bag_gradient_bit_num=args.embedding_bag_gradient_bit_num, args=args)   # :1940-1957
+            lr_scheduler.step()                                        # :1960
             it += 1
             if args.print_freq > 0 and it % args.print_freq == 0:
                 losses.append(float(E))                                # the reference syncs here too (:1928)

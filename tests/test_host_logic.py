@@ -225,3 +225,20 @@ def test_c_abi_rejects_bad_arguments_before_any_launch():
     assert b"null" in lib.dqrm_last_error()
     assert lib.dqrm_blockmax_scan(1, one, rows, 6, 64, one, 0, 1, None) == -errno.EINVAL
     assert b"multiple of 4" in lib.dqrm_last_error()
+
+
+def test_lr_policy_scheduler_vs_reference_sequence():
+    """The lr handed to weight_update_parallel_comm every iteration: our stand-alone LRPolicyScheduler against 30
+    steps of the reference's (torch _LRScheduler based) class, tests/golden/lr_policy.json."""
+    import json
+    from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lr_policy.json")))
+    for name, g in gold.items():
+        sch = drv.LRPolicyScheduler(*g["args"])
+        got = []
+        for _ in range(len(g["lrs"])):
+            got.append(sch.get_lr()[-1])
+            sch.step()
+        assert got == g["lrs"], name
+    with pytest.raises(SystemExit):
+        drv.LRPolicyScheduler(0.1, 5, 2, 3)
