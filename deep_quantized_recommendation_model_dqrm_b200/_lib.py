@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqrm_b200.so")
 
 MAX_TABLES = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 BWD_CTA_MAX_LOOKUPS = 16384
 STATUS_INDEX_RANGE, STATUS_OFFSET_ORDER, STATUS_CAPACITY, STATUS_P2P_TIMEOUT = 1, 2, 4, 8
 
@@ -54,9 +54,9 @@ SIGNATURES = {
     "dqrm_linear_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "dqrm_linear_bwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p]),
     "dqrm_fake_quant": (_i32, [_p, _i64, _i64, _p, _i32, _i32, _p, _p, _p]),
-    "dqrm_dense_grad_scale": (_i32, [_p, _p, _i32, _i32, _p, _p]),
+    "dqrm_dense_grad_scale": (_i32, [_p, _p, _p, _i32, _i32, _p, _p]),
     "dqrm_dense_grad_quant": (_i32, [_p, _p, _i32, _p, _f32, _i32, _p, _p, _p]),
-    "dqrm_dense_apply": (_i32, [_p, _p, _p, _i32, _p, _f32, _f32, _p]),
+    "dqrm_dense_apply": (_i32, [_p, _p, _p, _i32, _p, _f32, _f32, _p, _p, _p]),
     "dqrm_bce_loss_grad": (_i32, [_p, _p, _i64, _p, _p, _p]),
     "dqrm_p2p_alloc": (_i32, [_sz, C.POINTER(_vp), _p]),
     "dqrm_p2p_open": (_i32, [_p, C.POINTER(_vp)]),
@@ -66,7 +66,7 @@ SIGNATURES = {
     "dqrm_p2p_site_layout": (_i32, [_i32, _sz, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "dqrm_p2p_allgather": (_i32, [_p, _i32, _i32, _sz, _sz, _p, _p]),
     "dqrm_dense_grad_quant_gathered": (_i32, [_p, _p, _i32, _p, _sz, _i32, _i32, _p, _p, _p]),
-    "dqrm_dense_apply_gathered": (_i32, [_p, _p, _sz, _i32, _p, _i32, _p, _f32, _p]),
+    "dqrm_dense_apply_gathered": (_i32, [_p, _p, _sz, _i32, _p, _i32, _p, _f32, _p, _p, _p]),
     "dqrm_scale_from_absmax_gathered": (_i32, [_i32, _p, _sz, _i32, _i32, _p, _p, _p, _p]),
 }
 

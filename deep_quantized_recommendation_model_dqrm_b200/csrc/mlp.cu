@@ -35,14 +35,18 @@ linear_fakequant_kernel(const float* __restrict__ W, const float* __restrict__ b
 }
 
 __global__ void __launch_bounds__(256)
-dense_grad_scale_kernel(const float* __restrict__ grad, const long long* __restrict__ chan_begin, int num_chan,
-                        int bits, float* __restrict__ scale_local) {
+dense_grad_scale_kernel(float* __restrict__ grad, const float* __restrict__ ec, const long long* __restrict__ chan_begin,
+                        int num_chan, int bits, float* __restrict__ scale_local) {
   const int lane = threadIdx.x & 31;
   const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= num_chan) return;
   const long long a = chan_begin[ch], e = chan_begin[ch + 1];
   unsigned m = 0u;
-  for (long long i = a + lane; i < e; i += 32) m = max(m, abs_bits(grad[i]));
+  for (long long i = a + lane; i < e; i += 32) {
+    float w = grad[i];
+    if (ec) { w = __fadd_rn(w, ec[i]); grad[i] = w; }                     // weight = grad + error_compensation  (:899-900,938-939)
+    m = max(m, abs_bits(w));
+  }
   m = warp_max_u32(m);
   if (lane == 0) scale_local[ch] = scale_of(__uint_as_float(m), bits);
 }
@@ -64,7 +68,8 @@ dense_grad_quant_kernel(const float* __restrict__ grad, const long long* __restr
 
 __global__ void __launch_bounds__(256)
 dense_apply_kernel(float* __restrict__ param, const float* __restrict__ code_sum, const long long* __restrict__ chan_begin,
-                   int num_chan, const float* __restrict__ scale_mean, float inv_world, float neg_lr) {
+                   int num_chan, const float* __restrict__ scale_mean, float inv_world, float neg_lr,
+                   const float* __restrict__ comp_grad, float* __restrict__ ec_out) {
   const int lane = threadIdx.x & 31;
   const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= num_chan) return;
@@ -75,6 +80,7 @@ dense_apply_kernel(float* __restrict__ param, const float* __restrict__ code_sum
     float u = __fmul_rn(neg_lr, g);                                       // (-lr * grad) ...
     if (scale_mean) u = __fmul_rn(u, s);                                  // ... * s          (:642-643)
     param[i] = __fadd_rn(param[i], u);
+    if (ec_out) ec_out[i] = __fsub_rn(comp_grad[i], __fmul_rn(g, s));     // weight - grad_up * s   (:926-927,958-959)
   }
 }
 
@@ -120,12 +126,12 @@ extern "C" int dqrm_linear_fakequant(const float* W, const float* b, int out_fea
   return 0;
 }
 
-extern "C" int dqrm_dense_grad_scale(const float* grad, const int64_t* chan_begin, int num_chan, int bits,
+extern "C" int dqrm_dense_grad_scale(float* grad, const float* error_comp, const int64_t* chan_begin, int num_chan, int bits,
                                      float* scale_local, void* stream) {
   DQRM_REQUIRE(grad && chan_begin && scale_local && num_chan >= 1, -EINVAL, "dense_grad_scale: bad argument");
   DQRM_REQUIRE(bits >= 2 && bits <= 16, -EINVAL, "dense_grad_scale: bits=%d outside [2,16]", bits);
   dense_grad_scale_kernel<<<(num_chan + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      grad, reinterpret_cast<const long long*>(chan_begin), num_chan, bits, scale_local);
+      grad, error_comp, reinterpret_cast<const long long*>(chan_begin), num_chan, bits, scale_local);
   DQRM_LAUNCH_CHECK("dense_grad_scale_kernel");
   return 0;
 }
@@ -142,10 +148,13 @@ extern "C" int dqrm_dense_grad_quant(const float* grad, const int64_t* chan_begi
 }
 
 extern "C" int dqrm_dense_apply(float* param, const float* code_sum, const int64_t* chan_begin, int num_chan,
-                                const float* scale_mean, float inv_world, float lr, void* stream) {
+                                const float* scale_mean, float inv_world, float lr, const float* comp_grad,
+                                float* error_comp_out, void* stream) {
   DQRM_REQUIRE(param && code_sum && chan_begin && num_chan >= 1, -EINVAL, "dense_apply: bad argument");
+  DQRM_REQUIRE(!error_comp_out || (comp_grad && scale_mean), -EINVAL, "dense_apply: error compensation needs comp_grad and scale_mean");
   dense_apply_kernel<<<(num_chan + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, code_sum, reinterpret_cast<const long long*>(chan_begin), num_chan, scale_mean, inv_world, -lr);
+      param, code_sum, reinterpret_cast<const long long*>(chan_begin), num_chan, scale_mean, inv_world, -lr, comp_grad,
+      error_comp_out);
   DQRM_LAUNCH_CHECK("dense_apply_kernel");
   return 0;
 }

@@ -84,6 +84,12 @@ class DenseArena:
         self.p2p = None                    # PeerArena of the NVLink exchange (world > 1, DQRM_EXCHANGE=p2p)
         self.slot_world = 0                # world size the exchange slots were built for (0: all-reduce form)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        # error compensation of the quantised MLP gradients (quantize_linear_grad / quantize_bias_grad with
+        # err_compensation=True, sgd...parallel_comm.py:899-900,926-927,938-939,958-959): the residual
+        # (grad + ec) - qbar * s_bar of every element, carried to the next step.  Off by default like every
+        # call site of the reference (:341,350); allocated on first use.
+        self.error_compensation = False
+        self.ec = None
         self._bind_scale_views()
 
     def _bind_scale_views(self):
@@ -215,10 +221,26 @@ class DenseArena:
         if world > 1 and live:
             dist.all_reduce(self.codes, group=process_group)
 
+    def _ec_ptr(self):
+        if not self.error_compensation:
+            return None
+        if self.ec is None:
+            self.ec = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+            off = 0
+            for l in self.layers:                         # the reference's per-layer buffers (qm:87,95) as views
+                o, i = l.weight.shape
+                l.error_compensation_weight = self.ec[off:off + o * i].view(o, i)
+                off += o * i
+                if l.bias is not None:
+                    l.error_compensation_bias = self.ec[off:off + o]
+                    off += o
+        return self.ec.data_ptr()
+
     def local_scale(self, bits=8):
+        """Per-channel local scales; with error compensation flat_grad becomes grad + ec in place first."""
         self.join()
-        _lib.check(self.lib.dqrm_dense_grad_scale(self.flat_grad.data_ptr(), self.chan_begin.data_ptr(), self.num_chan,
-                                                  bits, self.scale_local.data_ptr(), _lib.stream_ptr()),
+        _lib.check(self.lib.dqrm_dense_grad_scale(self.flat_grad.data_ptr(), self._ec_ptr(), self.chan_begin.data_ptr(),
+                                                  self.num_chan, bits, self.scale_local.data_ptr(), _lib.stream_ptr()),
                    "dqrm_dense_grad_scale")
 
     def quantize(self, world=1, bits=8):
@@ -231,12 +253,14 @@ class DenseArena:
     def apply(self, lr, world=1, quantized=True):
         """MLP half of weight_update_parallel_comm (sgd_quantized_gradients_parallel_comm.py:630-663)."""
         st = _lib.stream_ptr()
+        ec = self._ec_ptr() if quantized else None
+        comp = self.flat_grad.data_ptr() if ec is not None else None        # = grad + ec since local_scale()
         if quantized and getattr(self, "exchanged_gathered", False):
             rc = self.lib.dqrm_dense_apply_gathered(self.flat.data_ptr(), self._code_slots.data_ptr(),
                                                     self._code_slots.stride(0), world, self.chan_begin.data_ptr(),
-                                                    self.num_chan, self.scale_mean.data_ptr(), float(lr), st)
+                                                    self.num_chan, self.scale_mean.data_ptr(), float(lr), comp, ec, st)
             _lib.check(rc, "dqrm_dense_apply_gathered")
             return
         _lib.check(self.lib.dqrm_dense_apply(self.flat.data_ptr(), self.codes.data_ptr(), self.chan_begin.data_ptr(),
                                              self.num_chan, self.scale_mean.data_ptr() if quantized else None,
-                                             float(1.0 / world), float(lr), st), "dqrm_dense_apply")
+                                             float(1.0 / world), float(lr), comp, ec, st), "dqrm_dense_apply")

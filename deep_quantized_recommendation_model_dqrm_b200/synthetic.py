@@ -79,6 +79,54 @@ def criteo_batch(rows, batch: int, seed: int, zipf: float | None = None, dense: 
     return torch.from_numpy(X), torch.from_numpy(off), torch.from_numpy(idx), torch.from_numpy(T)
 
 
+def criteo_batch_nodup(rows, world: int, per_rank: int, seed: int, dense: int = 13):
+    """Criteo-shaped global batch of world*per_rank samples whose per-rank shards (contiguous, get_my_slice)
+    hold no duplicate index inside a table, while ranks may share rows: the case in which the reference's
+    coalesce() folds nothing, so its gradient scales and INT8 codes do not depend on a fold order."""
+    rng = np.random.RandomState(seed)
+    batch = world * per_rank
+    X = np.log(1.0 + rng.randint(0, 100, size=(batch, dense))).astype(np.float32)
+    idx = np.empty((len(rows), batch), dtype=np.int64)
+    for k, n in enumerate(rows):
+        for r in range(world):
+            idx[k, r * per_rank:(r + 1) * per_rank] = rng.choice(n, size=per_rank, replace=False)
+    off = np.tile(np.arange(batch, dtype=np.int64), (len(rows), 1))
+    T = np.round(rng.rand(batch, 1).astype(np.float32)).astype(np.float32)
+    return torch.from_numpy(X), torch.from_numpy(off), torch.from_numpy(idx), torch.from_numpy(T)
+
+
+# isolated exchange cases (tests/golden/xchg*.npz): gradients are INJECTED after the backward, so everything
+# downstream (scales, INT8 codes, merged rows, updated weights) is order-independent and bit-exact by contract
+XCHG = dict(rows=[600, 40, 300, 100], dim=16, per_rank=16, layers=[(13, 32), (32, 16)])
+
+
+def injected_grads(cfg, world: int, rank: int, step: int, seed: int = 700):
+    """Per-rank gradients for one exchange step: per table (unique unsorted rows [U], values [U, D]) and per
+    linear layer (dW [out, in], db [out]); magnitudes differ per rank / channel so the local scales differ."""
+    rng = np.random.RandomState(seed + 1000 * step + 10 * rank + world)
+    U, D = cfg["per_rank"], cfg["dim"]
+    emb = []
+    for n in cfg["rows"]:
+        idx = rng.choice(n, size=U, replace=False).astype(np.int64)
+        vals = (rng.randn(U, D) * 10.0 ** rng.uniform(-4, -1)).astype(np.float32)
+        emb.append((idx, vals))
+    mlp = []
+    for li, (n_in, n_out) in enumerate(cfg["layers"]):
+        gw = (rng.randn(n_out, n_in) * 10.0 ** rng.uniform(-4, -1, size=(n_out, 1))).astype(np.float32)
+        gb = (rng.randn(n_out) * 10.0 ** rng.uniform(-4, -1)).astype(np.float32)
+        if li == 0:
+            gw[0, :] = 0.0                       # an all-zero channel: scale = 1e-8 / 127 (quant_utils.py:213-214)
+        mlp.append((gw, gb))
+    return emb, mlp
+
+
+def xchg_weights(cfg, seed: int = 701):
+    rng = np.random.RandomState(seed)
+    emb = [table_weights_numpy(n, cfg["dim"], rng) for n in cfg["rows"]]
+    mlp = [mlp_params([a, b], rng)[0] for a, b in cfg["layers"]]
+    return emb, mlp
+
+
 def random_bags(rows: int, batch: int, p_max: int, rng: np.random.RandomState, fixed: bool = False):
     """Indices/offsets of one table, RandomDataset style (unique sorted per bag)."""
     offsets, indices, offset = [], [], 0

@@ -46,7 +46,7 @@ extern "C" {
 #define DQRM_API
 #endif
 
-#define DQRM_ABI_VERSION 2
+#define DQRM_ABI_VERSION 3
 #define DQRM_MAX_TABLES 64           /* tables per call (kernel-parameter descriptor size) */
 #define DQRM_BWD_CTA_MAX_LOOKUPS 16384 /* per-table lookups handled by the single-CTA sort path */
 
@@ -339,14 +339,21 @@ DQRM_API int dqrm_fake_quant(const float* x, int64_t rows, int64_t cols, const f
  *        (weight_update_parallel_comm :642-643 -- note the association differs from (a9))
  * chan_begin is dev int64 [num_chan+1]; codes are integer-valued fp32 so one
  * SUM all-reduce between quant and apply adds them exactly.
+ * Error compensation (quantize_linear_grad / quantize_bias_grad with err_compensation=True,
+ * sgd...parallel_comm.py:899-900,926-927,938-939,958-959; buffers error_compensation_weight/_bias,
+ * quant_modules_not_quantize_grad.py:87,95): pass `error_comp` (same layout as grad) to dqrm_dense_grad_scale and
+ * grad becomes grad + error_comp IN PLACE before the scale is taken; pass that compensated gradient and
+ * `error_comp_out` to dqrm_dense_apply(_gathered) and error_comp_out = comp_grad - (code_sum * inv_world) * s_bar.
+ * NULL = the reference's default (err_compensation=False).
  */
-DQRM_API int dqrm_dense_grad_scale(const float* grad, const int64_t* chan_begin, int num_chan, int bits,
+DQRM_API int dqrm_dense_grad_scale(float* grad, const float* error_comp, const int64_t* chan_begin, int num_chan, int bits,
                           float* scale_local, void* stream);
 DQRM_API int dqrm_dense_grad_quant(const float* grad, const int64_t* chan_begin, int num_chan,
                           const float* scale_sum, float inv_world, int bits,
                           float* codes, float* scale_mean, void* stream);
 DQRM_API int dqrm_dense_apply(float* param, const float* code_sum, const int64_t* chan_begin, int num_chan,
-                     const float* scale_mean, float inv_world, float lr, void* stream);
+                     const float* scale_mean, float inv_world, float lr, const float* comp_grad,
+                     float* error_comp_out, void* stream);
 
 /* BCE loss (mean reduction) and its gradient in one launch: torch.nn.BCELoss()(Z, T) + E.backward() of the
  * reference loop (loss_fn_wrap, dlrm_s_pytorch_comm_grad.py:192-211; :1938).
@@ -388,7 +395,7 @@ DQRM_API int dqrm_dense_grad_quant_gathered(const float* grad, const int64_t* ch
  * 957,662-663); rank r's int8 codes at gathered_codes + r * code_stride_bytes. */
 DQRM_API int dqrm_dense_apply_gathered(float* param, const int8_t* gathered_codes, size_t code_stride_bytes, int world,
                                        const int64_t* chan_begin, int num_chan, const float* scale_mean, float lr,
-                                       void* stream);
+                                       const float* comp_grad, float* error_comp_out, void* stream);
 /* (a1, row-sharded scan) absmax = max over ranks of the gathered per-shard maxima, then scale and 1/scale. */
 DQRM_API int dqrm_scale_from_absmax_gathered(int n_scales, const float* gathered_absmax, size_t stride_elems, int world,
                                              int bits, float* absmax, float* scale, float* inv_scale, void* stream);

@@ -296,7 +296,7 @@ def mean_scale_spec(scales, world: int) -> np.float32:
     return F32(acc * F32(1.0 / world))
 
 
-def exchange_emb_grad_spec(per_rank, bits: int, num_rows: int):
+def exchange_emb_grad_spec(per_rank, bits: int, num_rows: int, s_bar=None):
     """Reference quantize_emb_grad(parallel=True) over N ranks (sgd:850-890).
 
     per_rank: list of (uniq_rows, sums) from coalesce_spec, one per rank.
@@ -304,7 +304,8 @@ def exchange_emb_grad_spec(per_rank, bits: int, num_rows: int):
     ``qbar = (sum_r q_r) * (1/N)`` on the union of rows (sgd:878,885)."""
     world = len(per_rank)
     s_local = [grad_scale_spec(s, bits) for _, s in per_rank]
-    s_bar = mean_scale_spec(s_local, world)
+    if s_bar is None:          # (tests may pass the reference's own mean: Gloo's SUM order at N > 2 is backend-internal)
+        s_bar = mean_scale_spec(s_local, world)
     codes = [quantize_spec(s, bits, s_bar) for _, s in per_rank]
     all_rows = np.concatenate([r for r, _ in per_rank])
     all_codes = np.concatenate(codes, axis=0)
@@ -466,14 +467,16 @@ def bias_grad_scale_spec(g: np.ndarray, bits: int = 8) -> np.float32:
     return scale_from_absmax(max(abs(g.min()), abs(g.max())), bits)
 
 
-def exchange_dense_grad_spec(per_rank_grads, per_rank_scales, bits: int = 8):
+def exchange_dense_grad_spec(per_rank_grads, per_rank_scales, bits: int = 8, s_bar=None):
     """scale all-reduce-mean, quantise with the mean scale, code all-reduce,
     ``* 1/N`` (sgd:912-924, 948-956).  Returns (s_bar, qbar)."""
     world = len(per_rank_grads)
-    acc = np.asarray(per_rank_scales[0], dtype=F32).copy()
-    for s in per_rank_scales[1:]:
-        acc = (acc + np.asarray(s, dtype=F32)).astype(F32)
-    s_bar = (acc * F32(1.0 / world)).astype(F32)
+    if s_bar is None:
+        acc = np.asarray(per_rank_scales[0], dtype=F32).copy()
+        for s in per_rank_scales[1:]:
+            acc = (acc + np.asarray(s, dtype=F32)).astype(F32)
+        s_bar = (acc * F32(1.0 / world)).astype(F32)
+    s_bar = np.asarray(s_bar, dtype=F32)
     qsum = None
     for g in per_rank_grads:
         g = np.asarray(g, dtype=F32)
@@ -484,6 +487,22 @@ def exchange_dense_grad_spec(per_rank_grads, per_rank_scales, bits: int = 8):
             q = np.clip(np.rint((inv_scale(s_bar) * g).astype(F32)), -n - 1, n).astype(F32)
         qsum = q if qsum is None else (qsum + q).astype(F32)
     return s_bar, (qsum * F32(1.0 / world)).astype(F32)
+
+
+def exchange_dense_grad_ec_spec(per_rank_grads, per_rank_ec, bits: int = 8):
+    """quantize_linear_grad / quantize_bias_grad with err_compensation=True (sgd:899-900,926-927,938-939,958-959):
+    ``w_r = grad_r + ec_r``; scale from w_r; mean scale; q_r = Q(w_r); qbar = (sum_r q_r)/N;
+    ``ec_r' = w_r - qbar * s_bar`` (the GLOBAL averaged update is subtracted from the LOCAL compensated gradient).
+    Returns (s_bar, qbar, [ec_r'])."""
+    ws = [(np.asarray(g, dtype=F32) + np.asarray(e, dtype=F32)).astype(F32) for g, e in zip(per_rank_grads, per_rank_ec)]
+    if ws[0].ndim == 2:
+        scales = [linear_grad_scale_spec(w, bits) for w in ws]
+    else:
+        scales = [bias_grad_scale_spec(w, bits) for w in ws]
+    s_bar, qbar = exchange_dense_grad_spec(ws, scales, bits)
+    sb = np.asarray(s_bar, dtype=F32).reshape(-1, 1) if ws[0].ndim == 2 else F32(s_bar)
+    new_ec = [(w - (qbar * sb).astype(F32)).astype(F32) for w in ws]
+    return s_bar, qbar, new_ec
 
 
 def weight_update_linear_spec(W, b, qbar_w, s_w, qbar_b, s_b, lr: float) -> None:

@@ -122,6 +122,10 @@ def gen_linear(qm):
 
 # ---------------------------------------------------------------- full model / DP step
 C_SMALL = dict(rows=[50, 3, 1000, 200], dim=16, ln_bot=[13, 32, 16], ln_top_hidden=[32, 1])
+# duplicate-free shards (tables >> per-rank batch, indices drawn without replacement inside a rank, overlapping
+# between ranks): coalesce() has nothing to fold, so the reference's gradient scales and INT8 codes are
+# order-independent and must be reproduced BIT-EXACTLY (sgd_quantized_gradients_parallel_comm.py:861-869)
+C_NODUP = dict(rows=[1500, 40, 1000, 200], dim=16, ln_bot=[13, 32, 16], ln_top_hidden=[32, 1])
 
 
 def build_reference_model(cfg, seed, embedding_bit=4, weight_bit=4):
@@ -163,13 +167,17 @@ def dp_worker(rank, world, port, steps, multihot, out_path, emb_q=True):
     import torch.distributed as dist
     qm, qu, sgd = import_reference()
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    cfg = C_SMALL
+    nodup = multihot == "nodup"
+    multihot = multihot is True
+    cfg = C_NODUP if nodup else C_SMALL
     m = build_reference_model(cfg, seed=300)
     lr = 0.1
     rec = {}
     for step in range(steps):
         Bg = 16 * world
-        if multihot:
+        if nodup:
+            X, lS_o, lS_i, T = synthetic.criteo_batch_nodup(cfg["rows"], world, 16, seed=400 + step)
+        elif multihot:
             X, lS_o, lS_i, T = synthetic.random_batch(cfg["rows"], Bg, 4, seed=400 + step)
         else:
             X, lS_o, lS_i, T = synthetic.criteo_batch(cfg["rows"], Bg, seed=400 + step, zipf=1.3)
@@ -223,7 +231,104 @@ def gen_dp(world, multihot, name, port, emb_q=True):
                 out[f"rank{r}_{k}"] = recs[r][k]
         os.remove(tmp.format(rank=r))
     out["world"] = world
-    out["multihot"] = multihot
+    out["multihot"] = multihot is True
+    out["nodup"] = multihot == "nodup"
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+
+
+def xchg_worker(rank, world, port, steps, ec, out_path):
+    """The exchange + update half of the reference's iteration on injected gradients (no forward/backward, so
+    no GEMM rounding enters): sgd...parallel_comm.py grad_update_parallel_comm :257 + weight_update_parallel_comm
+    :601 on CPU/Gloo.  ec=True: the MLP tensors go through quantize_linear_grad / quantize_bias_grad with
+    err_compensation=True (:899-900,926-927,938-939,958-959) in the way grad_update_parallel_comm calls them."""
+    import torch.distributed as dist
+    qm, qu, sgd = import_reference()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    cfg = synthetic.XCHG
+    emb_w, mlp_w = synthetic.xchg_weights(cfg)
+
+    class Model(torch.nn.Module):
+        pass
+    m = Model()
+    m.emb_l = torch.nn.ModuleList()
+    for n, W in zip(cfg["rows"], emb_w):
+        E = qm.QuantEmbeddingBagTwo(n, cfg["dim"], 4, embedding_id=len(m.emb_l))
+        E.embedding_bag.weight.data = torch.tensor(W)
+        m.emb_l.append(E)
+    m.bot_l = torch.nn.ModuleList()
+    for (n_in, n_out), (W, b) in zip(cfg["layers"], mlp_w):
+        LL = torch.nn.Linear(n_in, n_out)
+        LL.weight.data, LL.bias.data = torch.tensor(W), torch.tensor(b)
+        Q = qm.QuantLinear(weight_bit=4, bias_bit=4, per_channel=True)
+        Q.set_param(LL)
+        m.bot_l.append(Q)
+    m.top_l = torch.nn.ModuleList()
+    lr, rec = 0.1, {}
+    for step in range(steps):
+        emb_g, mlp_g = synthetic.injected_grads(cfg, world, rank, step)
+        for E, (idx, vals), n in zip(m.emb_l, emb_g, cfg["rows"]):
+            E.embedding_bag.weight.grad = torch.sparse_coo_tensor(torch.from_numpy(idx)[None], torch.from_numpy(vals),
+                                                                  size=(n, cfg["dim"]))
+        for Q, (gw, gb) in zip(m.bot_l, mlp_g):
+            Q.weight.grad, Q.bias.grad = torch.from_numpy(gw.copy()), torch.from_numpy(gb.copy())
+        if not ec:
+            sgd.grad_update_parallel_comm(m, world, emb_grad_quantized=True, num_bits=8, ranking_range=False,
+                                          rank_for_debug=rank, iteration_count=step)
+        else:
+            mlp_saved = [(Q.weight.grad.clone(), Q.bias.grad.clone()) for Q in m.bot_l]
+            bot, m.bot_l = m.bot_l, torch.nn.ModuleList()           # embeddings through the stock entry point
+            sgd.grad_update_parallel_comm(m, world, emb_grad_quantized=True, num_bits=8, ranking_range=False,
+                                          rank_for_debug=rank, iteration_count=step)
+            m.bot_l = bot
+            with torch.no_grad():
+                for Q in m.bot_l:                                   # the body of :341-356 with err_compensation=True
+                    upd, sc = sgd.quantize_linear_grad(Q, num_bits=8, parallel=True, num_gpus=world, err_compensation=True)
+                    Q.weight_scaling_factor = sc
+                    Q.weight.grad.zero_(); Q.weight.grad.add_(upd)
+                    upd, sc = sgd.quantize_bias_grad(Q, num_bits=8, parallel=True, num_gpus=world, err_compensation=True)
+                    Q.bias_scaling_factor = sc
+                    Q.bias.grad.zero_(); Q.bias.grad.add_(upd)
+        for k, E in enumerate(m.emb_l):
+            g = E.embedding_bag.weight.grad.coalesce()
+            rec[f"s{step}_emb{k}_rows"] = _np(g.indices()[0]).copy()
+            rec[f"s{step}_emb{k}_qbar"] = _np(g.values()).copy()
+            rec[f"s{step}_emb{k}_sbar"] = _np(E.emb_scaling_factor).copy()
+        for i, Q in enumerate(m.bot_l):
+            rec[f"s{step}_lin{i}_qbar_w"] = _np(Q.weight.grad).copy()
+            rec[f"s{step}_lin{i}_qbar_b"] = _np(Q.bias.grad).copy()
+            rec[f"s{step}_lin{i}_s_w"] = _np(Q.weight_scaling_factor).copy()
+            rec[f"s{step}_lin{i}_s_b"] = _np(Q.bias_scaling_factor).reshape(-1).copy()
+            if ec:
+                rec[f"s{step}_lin{i}_ec_w"] = _np(Q.error_compensation_weight).copy()
+                rec[f"s{step}_lin{i}_ec_b"] = _np(Q.error_compensation_bias).copy()
+        sgd.weight_update_parallel_comm(m, lr, emb_grad_quantized=True, update_embedding=True, num_gpus=world,
+                                        rank_for_debug=rank)
+    for k, E in enumerate(m.emb_l):
+        rec[f"final_emb{k}"] = _np(E.embedding_bag.weight.data).copy()
+    for i, Q in enumerate(m.bot_l):
+        rec[f"final_lin{i}_W"], rec[f"final_lin{i}_b"] = _np(Q.weight.data).copy(), _np(Q.bias.data).copy()
+    np.savez_compressed(out_path.format(rank=rank), **rec)
+    dist.destroy_process_group()
+
+
+def gen_xchg(world, name, port, ec=False, steps=2):
+    import torch.multiprocessing as mp
+    tmp = os.path.join(GOLD, name + "_rank{rank}.npz")
+    mp.spawn(xchg_worker, args=(world, port, steps, ec, tmp), nprocs=world, join=True)
+    recs = [dict(np.load(tmp.format(rank=r))) for r in range(world)]
+    for r in range(1, world):
+        for k in recs[0]:
+            if "_ec_" in k:
+                continue          # the residual is per rank (local grad - global update): keep every rank's
+            assert np.array_equal(recs[0][k], recs[r][k]), (name, r, k)
+    out = dict(recs[0])
+    for r in range(world):
+        for k in recs[r]:
+            if "_ec_" in k:
+                out[f"rank{r}_{k}"] = recs[r][k]
+        os.remove(tmp.format(rank=r))
+    out = {k: v for k, v in out.items() if "_ec_" not in k or k.startswith("rank")}
+    out["world"], out["ec"], out["steps"] = world, ec, steps
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
 
 
@@ -275,6 +380,17 @@ def main():
     if "--only-rwsadagrad" in sys.argv:
         gen_rwsadagrad()
         return
+    if "--only-nodup" in sys.argv:
+        import_reference()
+        gen_dp(2, "nodup", "dp2_nodup", 29616)
+        return
+    if "--only-xchg" in sys.argv:
+        import_reference()
+        gen_xchg(1, "xchg1", 29620)
+        gen_xchg(2, "xchg2", 29618)
+        gen_xchg(4, "xchg4", 29619)
+        gen_xchg(2, "xchg2_ec", 29621, ec=True, steps=3)
+        return
     if "--only-unquantized" in sys.argv:
         import_reference()
         gen_dp(2, False, "dp2_unquantized", 29615, emb_q=False)
@@ -289,6 +405,11 @@ def main():
     gen_dp(4, False, "dp4_onehot", 29614)
     gen_rwsadagrad()
     gen_dp(2, False, "dp2_unquantized", 29615, emb_q=False)     # emb_grad_quantized=False (sgd:319-329, 626)
+    gen_dp(2, "nodup", "dp2_nodup", 29616)
+    gen_xchg(1, "xchg1", 29620)
+    gen_xchg(2, "xchg2", 29618)
+    gen_xchg(4, "xchg4", 29619)
+    gen_xchg(2, "xchg2_ec", 29621, ec=True, steps=3)
     tot = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print("golden files:", sorted(os.listdir(GOLD)), "total bytes:", tot)
 

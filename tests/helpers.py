@@ -80,6 +80,16 @@ def emulated_dp_step(models, batches, lr, device="cuda", keep_debug=True):
         E.backward()
         losses.append(E.detach())
     groups = [m.emb_group for m in models]
+    arenas = [sgd._dense_arena(m) for m in models]
+    emulated_exchange(groups, arenas)
+    for m in models:
+        sgd.weight_update_parallel_comm(m, lr, emb_grad_quantized=True, update_embedding=True, num_gpus=world)
+    return [float(l) for l in losses]
+
+
+def emulated_exchange(groups, arenas):
+    """The collectives of grad_update_parallel_comm between W replicas on one GPU, as explicit copies."""
+    world = len(groups)
     # collective 1: all-gather of the per-table local scales
     for r, g in enumerate(groups):
         g.stage_scale(r)
@@ -95,7 +105,6 @@ def emulated_dp_step(models, batches, lr, device="cuda", keep_debug=True):
             if g2 is not g:
                 g.gathered[r2 * sb:(r2 + 1) * sb].copy_(g2.gathered[r2 * sb:(r2 + 1) * sb])
     # MLP: SUM all-reduce of scales, then of codes (rank order)
-    arenas = [sgd._dense_arena(m) for m in models]
     for a in arenas:
         a.local_scale(8)
     ssum = arenas[0].scale_local.clone()
@@ -109,6 +118,3 @@ def emulated_dp_step(models, batches, lr, device="cuda", keep_debug=True):
         csum = csum + a.codes
     for a in arenas:
         a.codes.copy_(csum)
-    for m in models:
-        sgd.weight_update_parallel_comm(m, lr, emb_grad_quantized=True, update_embedding=True, num_gpus=world)
-    return [float(l) for l in losses]

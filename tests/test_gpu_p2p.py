@@ -74,7 +74,7 @@ def test_gathered_dense_consumers_match_allreduce_form(world):
     st = _lib.stream_ptr()
     scales = torch.zeros((world, C + 3), dtype=torch.float32, device="cuda")          # padded stride
     for r in range(world):
-        _lib.check(lib.dqrm_dense_grad_scale(grads[r].data_ptr(), chan_t.data_ptr(), C, 8, scales[r].data_ptr(), st), "scale")
+        _lib.check(lib.dqrm_dense_grad_scale(grads[r].data_ptr(), None, chan_t.data_ptr(), C, 8, scales[r].data_ptr(), st), "scale")
     # all-reduce form
     ssum = scales[0, :C].clone()
     for r in range(1, world):
@@ -88,7 +88,7 @@ def test_gathered_dense_consumers_match_allreduce_form(world):
     for r in range(1, world):
         csum = csum + codes_f[r]
     pa = param0.clone()
-    _lib.check(lib.dqrm_dense_apply(pa.data_ptr(), csum.data_ptr(), chan_t.data_ptr(), C, mean_a.data_ptr(), 1.0 / world, 0.1, st), "apply")
+    _lib.check(lib.dqrm_dense_apply(pa.data_ptr(), csum.data_ptr(), chan_t.data_ptr(), C, mean_a.data_ptr(), 1.0 / world, 0.1, None, None, st), "apply")
     # gathered form
     stride = (total + 15) // 16 * 16 + 16
     codes_i = torch.zeros((world, stride), dtype=torch.int8, device="cuda")
@@ -98,7 +98,7 @@ def test_gathered_dense_consumers_match_allreduce_form(world):
                                                       scales.stride(0), world, 8, codes_i[r].data_ptr(), mean_b.data_ptr(), st), "quant_g")
     pb = param0.clone()
     _lib.check(lib.dqrm_dense_apply_gathered(pb.data_ptr(), codes_i.data_ptr(), stride, world, chan_t.data_ptr(), C,
-                                             mean_b.data_ptr(), 0.1, st), "apply_g")
+                                             mean_b.data_ptr(), 0.1, None, None, st), "apply_g")
     torch.cuda.synchronize()
     assert torch.equal(mean_a, mean_b)
     assert torch.equal(codes_i[:, :total].float(), codes_f)

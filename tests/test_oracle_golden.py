@@ -254,3 +254,62 @@ def test_dp_unquantized_exchange_vs_reference():
     for grp, layers in (("bot", m0.bot_l), ("top", m0.top_l)):
         for i, l in enumerate(layers):
             np.testing.assert_allclose(l.weight.data.numpy(), g[f"final_{grp}{i}_W"], rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["xchg1", "xchg2", "xchg4", "xchg2_ec"])
+def test_exchange_on_injected_gradients_bit_exact(name):
+    """The exchange + update half of the iteration on INJECTED gradients (no forward/backward, so no GEMM or
+    duplicate-fold rounding enters): the reference's grad_update_parallel_comm + weight_update_parallel_comm on
+    1/2/4 Gloo ranks (oracle/make_golden.py xchg_worker) vs the oracle spec -- gradient scales, INT8 codes,
+    merged row sets, MLP channel scales / codes, error-compensation residuals and every updated weight BIT-EXACT."""
+    from deep_quantized_recommendation_model_dqrm_b200 import synthetic
+    g = load_golden(name)
+    world, ec, steps = int(g["world"]), bool(g["ec"]), int(g["steps"])
+    cfg = synthetic.XCHG
+    emb_w, mlp_w = synthetic.xchg_weights(cfg)
+    emb_w = [w.copy() for w in emb_w]
+    mlp_w = [(W.copy(), b.copy()) for W, b in mlp_w]
+    ec_w = [[np.zeros_like(W) for W, _ in mlp_w] for _ in range(world)]
+    ec_b = [[np.zeros_like(b) for _, b in mlp_w] for _ in range(world)]
+    for step in range(steps):
+        inj = [synthetic.injected_grads(cfg, world, r, step) for r in range(world)]
+        for k, n in enumerate(cfg["rows"]):
+            per_rank = [O.coalesce_spec(*inj[r][0][k]) for r in range(world)]
+            ex = O.exchange_emb_grad_spec(per_rank, 8, n)
+            want_s = g[f"s{step}_emb{k}_sbar"].astype(np.float32)
+            if world <= 2:
+                assert np.float32(ex["s_bar"]).tobytes() == want_s.tobytes()
+            else:       # Gloo's fp32 SUM order over > 2 ranks is backend-internal: <= 1 ulp, then pin the rest on ITS mean
+                np.testing.assert_allclose(ex["s_bar"], want_s[0], rtol=2.5e-7)
+                ex = O.exchange_emb_grad_spec(per_rank, 8, n, s_bar=want_s[0])
+            assert np.array_equal(ex["union_rows"], g[f"s{step}_emb{k}_rows"])
+            assert np.array_equal(ex["qbar"], g[f"s{step}_emb{k}_qbar"])         # integer codes / N (-0.0 == 0.0)
+            O.weight_update_emb_spec(emb_w[k], ex["union_rows"], ex["qbar"], ex["s_bar"], 0.1)
+        for i in range(len(cfg["layers"])):
+            gws = [inj[r][1][i][0] for r in range(world)]
+            gbs = [inj[r][1][i][1] for r in range(world)]
+            if ec:
+                s_w, q_w, new_w = O.exchange_dense_grad_ec_spec(gws, [ec_w[r][i] for r in range(world)])
+                s_b, q_b, new_b = O.exchange_dense_grad_ec_spec(gbs, [ec_b[r][i] for r in range(world)])
+                for r in range(world):
+                    ec_w[r][i], ec_b[r][i] = new_w[r], new_b[r]
+                    assert new_w[r].tobytes() == g[f"rank{r}_s{step}_lin{i}_ec_w"].tobytes()
+                    assert new_b[r].tobytes() == g[f"rank{r}_s{step}_lin{i}_ec_b"].tobytes()
+            else:
+                s_w, q_w = O.exchange_dense_grad_spec(gws, [O.linear_grad_scale_spec(x) for x in gws])
+                s_b, q_b = O.exchange_dense_grad_spec(gbs, [O.bias_grad_scale_spec(x) for x in gbs])
+                if world > 2:
+                    np.testing.assert_allclose(s_w, g[f"s{step}_lin{i}_s_w"], rtol=2.5e-7)
+                    np.testing.assert_allclose(s_b, g[f"s{step}_lin{i}_s_b"][0], rtol=2.5e-7)
+                    s_w, q_w = O.exchange_dense_grad_spec(gws, None, s_bar=g[f"s{step}_lin{i}_s_w"])
+                    s_b, q_b = O.exchange_dense_grad_spec(gbs, None, s_bar=g[f"s{step}_lin{i}_s_b"][0])
+            assert np.asarray(s_w, np.float32).tobytes() == g[f"s{step}_lin{i}_s_w"].tobytes()
+            assert np.asarray(s_b, np.float32).reshape(-1).tobytes() == g[f"s{step}_lin{i}_s_b"].tobytes()
+            assert np.array_equal(q_w, g[f"s{step}_lin{i}_qbar_w"])
+            assert np.array_equal(q_b, g[f"s{step}_lin{i}_qbar_b"])
+            O.weight_update_linear_spec(mlp_w[i][0], mlp_w[i][1], q_w, s_w, q_b, s_b, 0.1)
+    for k in range(len(cfg["rows"])):
+        assert emb_w[k].tobytes() == g[f"final_emb{k}"].tobytes()
+    for i in range(len(cfg["layers"])):
+        assert mlp_w[i][0].tobytes() == g[f"final_lin{i}_W"].tobytes()
+        assert mlp_w[i][1].tobytes() == g[f"final_lin{i}_b"].tobytes()
