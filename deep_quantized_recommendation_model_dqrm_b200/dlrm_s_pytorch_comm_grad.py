@@ -482,7 +482,7 @@ def train(args, rank=0, world_size=1, device=None, log=print):
     from . import dlrm_data_pytorch as dp
     if not torch.cuda.is_available():
         raise _lib.DqrmLibraryError("train(): no CUDA device -- the product path has no CPU fallback")
-    device = torch.device(device if device is not None else ("cuda", rank % torch.cuda.device_count()))
+    device = torch.device(device) if device is not None else torch.device("cuda", rank % torch.cuda.device_count())
     torch.cuda.set_device(device)
     np.random.seed(args.numpy_rand_seed)
     torch.manual_seed(args.numpy_rand_seed)

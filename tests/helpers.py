@@ -11,6 +11,7 @@ from deep_quantized_recommendation_model_dqrm_b200 import sgd_quantized_gradient
 from oracle import dqrm_oracle as O
 
 C_SMALL = dict(rows=[50, 3, 1000, 200], dim=16, ln_bot=[13, 32, 16], ln_top_hidden=[32, 1])
+C_NODUP = dict(rows=[1500, 40, 1000, 200], dim=16, ln_bot=[13, 32, 16], ln_top_hidden=[32, 1])   # oracle/make_golden.py
 C1 = synthetic.RANDOM_SMALL
 
 
@@ -48,6 +49,10 @@ def shard(world, rank, multihot, step, rows, per_rank=16):
     """The batch shard of tests/golden dp*: same generator calls as oracle/make_golden.py."""
     Bg = per_rank * world
     sl = slice(rank * per_rank, (rank + 1) * per_rank)
+    if multihot == "nodup":
+        X, lS_o, lS_i, T = synthetic.criteo_batch_nodup(rows, world, per_rank, seed=400 + step)
+        lS_i = lS_i[:, sl]
+        return X[sl], lS_o[:, 0:lS_i.shape[1]], lS_i, T[sl]
     if multihot:
         X, lS_o, lS_i, T = synthetic.random_batch(rows, Bg, 4, seed=400 + step)
         li, lo = [], []

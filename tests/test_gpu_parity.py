@@ -312,6 +312,33 @@ def test_sgd_rows_and_rwsadagrad():
         np.testing.assert_allclose(cpu(g.weights[t]), Wn, rtol=1e-5, atol=1e-7)
 
 
+def test_rwsadagrad_rows_vs_reference_golden():
+    """dqrm_sgd_rows with momentum against 4 steps of the REFERENCE's optim/rwsadagrad.py:97-113
+    (tests/golden/rwsadagrad_rows.npz: sparse gradients with duplicate rows, state and weights after every step)."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    gd = load_golden("rwsadagrad_rows")
+    rows, dim, B = int(gd["rows"]), int(gd["dim"]), 24
+    g = tables.EmbeddingTableGroup([torch.tensor(gd["W_init"], device="cuda")], embedding_bit=4)
+    mom = [torch.zeros(rows, device="cuda")]
+    off = torch.arange(B, dtype=torch.int64, device="cuda").view(1, B)
+    for step in range(int(gd["steps"])):
+        idx = torch.tensor(gd[f"idx{step}"], device="cuda")
+        g.scan_scales()
+        g.forward(idx, off, [0, B], B, full_precision=True)
+        g.backward(torch.tensor(gd[f"vals{step}"], device="cuda").view(1, B, dim), world=1)   # coalesce (dedup + fold)
+        g.sgd_apply(float(gd["lr"]), momentum=mom, eps=float(gd["eps"]))
+        g.check_status()
+        np.testing.assert_allclose(cpu(mom[0]), gd[f"m{step}"], rtol=2e-6, atol=1e-12)
+        np.testing.assert_allclose(cpu(g.weights[0]), gd[f"W{step}"], rtol=1e-5, atol=1e-7)
+        # and the kernel against the oracle spec that the CPU suite pins on the same golden
+    W, m = gd["W_init"].copy(), np.zeros(rows, dtype=np.float32)
+    for step in range(int(gd["steps"])):
+        r, sums = O.coalesce_spec(gd[f"idx{step}"], gd[f"vals{step}"])[:2]
+        O.rwsadagrad_rows_spec(W, m, r, sums, float(gd["lr"]), float(gd["eps"]))
+    np.testing.assert_allclose(cpu(mom[0]), m, rtol=2e-6, atol=1e-12)
+    np.testing.assert_allclose(cpu(g.weights[0]), W, rtol=1e-5, atol=1e-7)
+
+
 # ------------------------------------------------------------------------------------------ (a14)
 @pytest.mark.parametrize("name", ["interact_kaggle", "interact_tb", "interact_small"])
 def test_interact_vs_golden(name):
@@ -349,6 +376,36 @@ def test_quant_linear_vs_golden(name):
     np.testing.assert_allclose(cpu(x.grad), g["dx"], rtol=RTOL, atol=1e-5)
     np.testing.assert_allclose(cpu(Q.weight.grad), g["dW"], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(cpu(Q.bias.grad), g["db"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["linear_13_64", "linear_367_32", "linear_64_1"])
+def test_fused_quant_linear_vs_golden(name):
+    """The kernels the training step actually runs (dqrm_mlp_fakequant_all + dqrm_linear_fwd / dqrm_linear_bwd through
+    QuantLinear.forward_fused) against the reference's QuantLinear forward/backward (qm:105-211): scales and integer
+    weights bit-exact; y, dx, dW, db within 1e-5 (relative to the tensor's largest magnitude for the gradients,
+    whose entries are sums with cancellation)."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    from deep_quantized_recommendation_model_dqrm_b200.dense import DenseArena
+    g = load_golden(name)
+    LL = torch.nn.Linear(g["W"].shape[1], g["W"].shape[0])
+    LL.weight.data, LL.bias.data = torch.tensor(g["W"]), torch.tensor(g["b"])
+    Q = qm.QuantLinear(weight_bit=int(g["bits"]), bias_bit=int(g["bits"]), per_channel=True)
+    Q.set_param(LL)
+    Q = Q.cuda()
+    arena = DenseArena([Q], torch.device("cuda"))
+    assert arena.fused_ok
+    arena.fakequant_all()
+    assert bits_equal(cpu(Q.fc_scaling_factor), g["scale"])
+    assert np.array_equal(cpu(Q.weight_integer), g["W_int"]) and np.array_equal(cpu(Q.bias_integer), g["b_int"])
+    x = torch.tensor(g["x"], device="cuda", requires_grad=True)
+    arena.zero_grad()
+    y = Q.forward_fused(x, 0)
+    np.testing.assert_allclose(cpu(y), g["y"], rtol=RTOL, atol=1e-5 * np.abs(g["y"]).max())
+    y.backward(torch.tensor(g["dy"], device="cuda"))
+    arena.join()
+    torch.cuda.synchronize()
+    for got, want in ((x.grad, g["dx"]), (Q.weight.grad, g["dW"]), (Q.bias.grad, g["db"])):
+        np.testing.assert_allclose(cpu(got), want, rtol=RTOL, atol=1e-5 * np.abs(want).max())
 
 
 def test_symmetric_quant_function_api():

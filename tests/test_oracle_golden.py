@@ -89,6 +89,10 @@ def test_interact(name):
 def _shard(world, rank, multihot, step, rows):
     Bg = 16 * world
     sl = slice(rank * 16, (rank + 1) * 16)
+    if multihot == "nodup":
+        X, lS_o, lS_i, T = synthetic.criteo_batch_nodup(rows, world, 16, seed=400 + step)
+        lS_i = lS_i[:, sl]
+        return X[sl], lS_o[:, 0:lS_i.shape[1]], lS_i, T[sl]
     if multihot:
         X, lS_o, lS_i, T = synthetic.random_batch(rows, Bg, 4, seed=400 + step)
         li, lo = [], []
@@ -118,16 +122,22 @@ def build_oracle_models(world, cfg, seed=300):
 C_SMALL = dict(rows=[50, 3, 1000, 200], dim=16, ln_bot=[13, 32, 16], ln_top_hidden=[32, 1])
 
 
-@pytest.mark.parametrize("name", ["dp1_onehot", "dp2_onehot", "dp2_multihot", "dp4_onehot"])
+C_NODUP = dict(rows=[1500, 40, 1000, 200], dim=16, ln_bot=[13, 32, 16], ln_top_hidden=[32, 1])
+
+
+@pytest.mark.parametrize("name", ["dp1_onehot", "dp2_onehot", "dp2_multihot", "dp4_onehot", "dp2_nodup"])
 def test_dp_train_steps(name):
     """Two iterations of the reference's custom-DP loop (N Gloo ranks) against
     the oracle's in-process replicas: union rows, averaged codes and scales
     bit-exact; losses and final weights within 1e-5."""
     g = load_golden(name)
     world, multihot = int(g["world"]), bool(g["multihot"])
-    models = build_oracle_models(world, C_SMALL)
+    cfg = C_SMALL
+    if "nodup" in g and bool(g["nodup"]):
+        multihot, cfg = "nodup", C_NODUP
+    models = build_oracle_models(world, cfg)
     for step in range(2):
-        batches = [_shard(world, r, multihot, step, C_SMALL["rows"]) for r in range(world)]
+        batches = [_shard(world, r, multihot, step, cfg["rows"]) for r in range(world)]
         scales_before = None
         losses = O.train_step_torch(models, batches, lr=0.1) if False else None
         # run the step in two halves so the exchanged artefacts can be inspected
