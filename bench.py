@@ -1,32 +1,39 @@
 #!/usr/bin/env python
-"""bench.py -- DQRM hot-path benchmark (contract: see the task statement / DESIGN.md "Measurement").
+"""bench.py -- DQRM hot-path benchmark (contract: the task statement / DESIGN.md "Measurement").
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference]
 
 Metric (BASELINE.json): train samples/sec, Criteo-Kaggle shape (26 tables at the Kaggle cardinalities,
 dim 16, bot 13-512-256-64-16, top 512-256-1), INT4 embedding + MLP QAT, INT8 quantised sparse gradient
-exchange, batch 128 per GPU, synthetic data.  A "step" is one full iteration of the reference hot loop
+exchange, synthetic data.  A "step" is one full iteration of the reference hot loop
 (dlrm_s_pytorch_comm_grad.py:1909-1957): scale scan of all tables, forward, loss, backward with row
 de-duplication, quantised exchange, SGD update of tables and MLPs.
 
+Headline (top-level keys) = BASELINE configs[1]: batch 128 per GPU (weak scaling at N > 1).
   value    samples/s with the step's inputs already resident in HBM (device-to-device refill of the
            static buffers + scan launch + CUDA-graph replay), CUDA events, max over ranks.
-  e2e      same step through the public API with HOST (pinned) inputs: H2D copy of X/lS_o/lS_i/T and a
-           D2H read of the loss inside every timed step.
+  e2e      same step through the public API with HOST (pinned) inputs: one packed H2D copy and a D2H
+           read of the loss inside every timed step.
   roofline the dominant kernel is the table max-abs scan (HBM-bound): algorithmic bytes = sum(rows)*D*4
            per launch (/N when row-sharded), duration = CUDA events around every scan launch inside the
            timed region.
+  step_ms  median / min / max / p95 of the individual step durations inside the timed region (one CUDA
+           event per step), so the spread of the K steps is visible.
   cpu_baseline / --impl reference: the oracle port of the reference's CPU path (torch CPU ops in the
            reference's order), all host threads, same config.
-Multi-GPU: one process per GPU (torchrun), batch-sharded DP, weak scaling (128 samples per GPU); the
-table scan is row-sharded 1/N per rank + MAX all-reduce (replicas are bit-identical).
+Beside the headline, the same JSON line carries the other BASELINE configs measured the same way:
+  "configs2_kaggle_global2048"   configs[2]: FIXED global batch 2048 split over the N GPUs (strong scaling)
+  "configs3_terabyte_global8192" configs[3]: Terabyte shape (48 GB of tables, dim 64), fixed global batch 8192
+and, at N = 1, the scale-policy variants (pipelined rescan, exact incremental tracker).
+Multi-GPU: one process per GPU (torchrun), batch-sharded DP; the table scan is row-sharded 1/N per rank;
+after the timed region every rank's tables / MLP parameters / scales are digested on the device and compared
+("replicas_bit_identical").
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -50,7 +57,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", type=str, default="kaggle", choices=["kaggle", "terabyte", "small"])
-    p.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
+    p.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch of the headline config")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-steps", type=int, default=5)
@@ -59,7 +66,8 @@ def parse():
                         "the same rescan overlapped with the step on a side stream; incremental = exact block-max "
                         "tracker (reads only the touched blocks)")
     p.add_argument("--no-extras", "--no-incremental-extra", dest="no_extras", action="store_true",
-                   help="skip the additional measurements (serial rescan, incremental tracker) reported beside the headline")
+                   help="skip everything but the headline config (scale-policy variants, configs[2], configs[3])")
+    p.add_argument("--only", type=str, default="", help="comma list out of {variants,c2,c3}: which extras to run")
     return p.parse_args()
 
 
@@ -71,6 +79,15 @@ def workload_cfg(name):
 def mlp_sizes(cfg):
     from deep_quantized_recommendation_model_dqrm_b200 import synthetic
     return synthetic.top_mlp_sizes(len(cfg["rows"]), cfg["dim"], cfg["ln_top_hidden"])
+
+
+def config_block(workload, cfg, per_gpu_batch, world):
+    """The `config` object -- built by this one function for BOTH arms, so the driver's same_config holds."""
+    table_bytes = sum(cfg["rows"]) * cfg["dim"] * 4
+    return {"workload": f"{workload}-shape DQRM: {len(cfg['rows'])} tables ({sum(cfg['rows'])} rows, "
+                        f"{table_bytes / 1e9:.3f} GB fp32), dim {cfg['dim']}, INT4 emb+MLP QAT, INT8 grad exchange, "
+                        f"batch {per_gpu_batch}/GPU x {world}",
+            "global_batch": per_gpu_batch * world, "per_gpu_batch": per_gpu_batch, "n_gpus": world}
 
 
 # --------------------------------------------------------------------------------------------
@@ -165,22 +182,21 @@ def oracle_arm(cfg, batch, steps, warmup):
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (its oracle port: the reference is pure
+    Python and /root/reference does not exist on the GPU box), all host threads, on the SAME config / steps /
+    warm-up as our arm.  Under torchrun rank 0 alone runs; the other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = workload_cfg(args.workload)
     gbatch = args.batch * args.gpus
-    steps = min(args.steps, 40)                               # ~1.4 s per step at Kaggle shape on 8 cores
-    warm = min(args.warmup, 1)
-    val, ms, cores, build_s = oracle_arm(cfg, gbatch, steps, warm)
-    sample = (f"{steps} full train steps (of --steps {args.steps}) after {warm} warm-up, global batch {gbatch}, "
-              f"oracle port of the reference CPU path, single process, {cores} threads; tables built in {build_s:.1f}s")
+    val, ms, cores, build_s = oracle_arm(cfg, gbatch, args.steps, args.warmup)
+    sample = (f"{args.steps} full train steps after {args.warmup} warm-up, global batch {gbatch}, oracle port of the "
+              f"reference CPU path, single process, {cores} threads; tables built in {build_s:.1f}s")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-shape DQRM, {len(cfg['rows'])} tables, dim {cfg['dim']}, "
-                                   f"batch {args.batch}/GPU x {args.gpus}", "global_batch": gbatch,
-                       "parallelism": "cpu-1proc"},
+            "config": config_block(args.workload, cfg, args.batch, args.gpus),
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -232,12 +248,167 @@ def finish(world):
         os._exit(0)
 
 
+def device_digest(tensors):
+    """Order-sensitive 2 x int64 checksum of the raw bits of `tensors`, computed on the device in chunks (the
+    Terabyte arena is 48 GB: it never goes to the host)."""
+    s1 = torch.zeros((), dtype=torch.int64, device=tensors[0].device)
+    s2 = torch.zeros_like(s1)
+    chunk = 1 << 26
+    w = (torch.arange(chunk, device=tensors[0].device, dtype=torch.int64) % 8191) + 1
+    for t in tensors:
+        v = t.detach().reshape(-1).view(torch.int32)
+        for a in range(0, v.numel(), chunk):
+            c = v[a:a + chunk].to(torch.int64)
+            s1 += c.sum()
+            s2 += (c * w[:c.numel()]).sum() + (a // chunk)
+    return torch.stack([s1, s2])
+
+
+class Runner:
+    """Everything bench.py measures for ONE (workload, per-GPU batch) configuration on this rank's GPU."""
+
+    def __init__(self, args, workload, per_gpu_batch, world, rank, dev):
+        from deep_quantized_recommendation_model_dqrm_b200 import synthetic
+        from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
+        self.args, self.workload, self.B, self.world, self.rank, self.dev = args, workload, per_gpu_batch, world, rank, dev
+        self.cfg = cfg = workload_cfg(workload)
+        ln_top = mlp_sizes(cfg)
+        np.random.seed(123)                                       # identical MLP init on every rank
+        self.dlrm = drv.DLRM_Net(cfg["dim"], np.array(cfg["rows"]), np.array(cfg["ln_bot"]), np.array(ln_top),
+                                 arch_interaction_op="dot", sigmoid_bot=-1, sigmoid_top=len(ln_top) - 2,
+                                 loss_function="bce", quantization_flag=True, embedding_bit=4, weight_bit=4,
+                                 quantize_act_and_lin=True, mlp_channelwise=True, quantize_activation=False,
+                                 device=dev, table_seed=1234)
+        self.dlrm.shard_scan = self.shard_scan = world > 1
+        self.table_bytes = sum(cfg["rows"]) * cfg["dim"] * 4
+        # a pool of distinct local batches, pinned on the host and resident on the device
+        self.pool = 8
+        self.host, self.devb = [], []
+        for i in range(self.pool):
+            X, lS_o, lS_i, T = synthetic.criteo_batch(cfg["rows"], per_gpu_batch, seed=10_000 + 97 * rank + i)
+            hb = tuple(t.pin_memory() for t in (X, lS_o, lS_i, T))
+            self.host.append(hb)
+            self.devb.append(tuple(t.to(dev) for t in hb))
+        self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_step(self, policy):
+        from deep_quantized_recommendation_model_dqrm_b200.graph_step import GraphedTrainStep
+        g = self.dlrm._ensure_group()
+        g.scale_policy, g.scale_valid = policy, False
+        return GraphedTrainStep(self.dlrm, *self.devb[0], lr=LR, world_size=self.world, rank=self.rank, grad_bits=8,
+                                warmup=3, use_graph=not self.args.no_graph)
+
+    def launches_per_step(self, step):
+        from deep_quantized_recommendation_model_dqrm_b200 import _lib
+        n0 = _lib.total_launches()                                # count OUR kernel launches of one step: one more
+        with torch.cuda.stream(step.stream):
+            step.scan(); step._body()                             # eager iteration (the graphs replay the same list)
+        torch.cuda.synchronize()
+        return _lib.total_launches() - n0
+
+    def timed(self, step, K, W, from_host):
+        with torch.cuda.stream(step.stream):                      # high-priority stream of the step (graph_step.py)
+            return self._timed_on_stream(step, K, W, from_host)
+
+    def _timed_on_stream(self, step, K, W, from_host):
+        import torch.distributed as dist
+        dev, pool, host, loss_host = self.dev, self.pool, self.host, self.loss_host
+        ev_scan = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        ev_step = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        # e2e: packed pinned host batches -> one H2D copy per step; the loss of every step is read back to pinned host
+        # memory asynchronously and the host waits for step i-1's loss while step i runs (one step in flight)
+        src = [step.pack_host(*hb) for hb in host] if from_host else [step.pack_host(*hb, pin=False).to(dev) for hb in host]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        for i in range(W):
+            step.load_packed(src[i % pool]); step.run()
+            if from_host:
+                loss_host[i % 2].copy_(step.loss, non_blocking=True); torch.cuda.current_stream().synchronize()
+        self.barrier()
+        ev_step[0].record()
+        for i in range(K):
+            step.load_packed(src[(W + i) % pool])
+            step.run(events=ev_scan[i])                          # scan launch (event-bracketed on ITS stream) + replay
+            if from_host:                                        # the reference reads the loss every step (:1928)
+                loss_host[i % 2].copy_(step.loss, non_blocking=True)
+                done[i % 2].record()
+                if i >= 1:
+                    done[(i - 1) % 2].synchronize()
+            ev_step[i + 1].record()
+        if from_host:
+            done[(K - 1) % 2].synchronize()
+        self.barrier()
+        ms = ev_step[0].elapsed_time(ev_step[K])                 # EXACTLY the K steps, first record to last record
+        per = np.array([ev_step[i].elapsed_time(ev_step[i + 1]) for i in range(K)])
+        scan_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_scan]))
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        spread = {"median": float(np.median(per)), "min": float(per.min()), "max": float(per.max()),
+                  "p95": float(np.percentile(per, 95)), "n": int(K)}
+        return float(t.item()), scan_ms, spread
+
+    def measure(self, policy, K, W):
+        """Device-resident and end-to-end timings of one scale policy -> result dict (global numbers)."""
+        step = self.make_step(policy)
+        launches = self.launches_per_step(step)
+        ms_dev, scan_ms, spread = self.timed(step, K, W, from_host=False)
+        ms_e2e, _, spread_e2e = self.timed(step, K, W, from_host=True)
+        self.dlrm.emb_group.check_status()
+        self.dlrm._dense_arena.check_status()
+        gbatch = self.B * self.world
+        res = {"value": gbatch * K / (ms_dev / 1000.0), "unit": "samples/s", "ms_per_step": ms_dev / K,
+               "step_ms": spread, "scan_kernel_ms": scan_ms,
+               "e2e": {"value": gbatch * K / (ms_e2e / 1000.0), "unit": "samples/s", "ms_per_step": ms_e2e / K,
+                       "step_ms": spread_e2e, "h2d_bytes_per_step": step.input_bytes(), "d2h_bytes_per_step": 4},
+               "gpu_launches_per_step": launches, "final_loss": float(step.loss.item()),
+               "cuda_graph": step.graph is not None}
+        return res, step
+
+    def roofline(self, policy, scan_ms, ms_per_step, peaks):
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        algo = self.table_bytes / self.world if self.shard_scan else self.table_bytes
+        achieved = algo / (scan_ms / 1000.0) / 1e9
+        return {"kernel": {"pipelined": "blockmax_scan_kernel", "full": "table_absmax_kernel",
+                           "incremental": "table_absmax_kernel (block maxima)"}[policy], "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                # DRAM bytes of THIS run are not measurable outside a profiler: null here; the ncu capture of the same
+                # kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch) is committed under profiles/
+                "traffic": None,
+                "traffic_ncu": "profiles/r01_scan_kernel_ncu_full.txt: 2.1686e9 B per unsharded Kaggle launch = 1.004 x algorithmic",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_launch": algo,
+                "avg_launch_ms": scan_ms, "share_of_step": scan_ms / ms_per_step}
+
+    def replicas_identical(self):
+        """Digest of every table, the MLP parameters and the scales on each rank; equal on all ranks?"""
+        import torch.distributed as dist
+        d = device_digest([self.dlrm.table_arena, self.dlrm._dense_arena.flat, self.dlrm.emb_group.scale])
+        if self.world == 1:
+            return None
+        alld = [torch.zeros_like(d) for _ in range(self.world)]
+        dist.all_gather(alld, d)
+        return bool(all(torch.equal(alld[0], x) for x in alld[1:]))
+
+    def close(self):
+        """Free this configuration's model (collective: closes the peer arenas behind a barrier)."""
+        self.dlrm.emb_group.release()
+        self.dlrm._dense_arena.release()
+        self.dlrm = None
+        self.host = self.devb = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
 def run_ours(args):
-    import torch.distributed as dist
-    from deep_quantized_recommendation_model_dqrm_b200 import _lib, synthetic
-    from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib
     from deep_quantized_recommendation_model_dqrm_b200 import extend_distributed as ext_dist
-    from deep_quantized_recommendation_model_dqrm_b200.graph_step import GraphedTrainStep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
@@ -250,181 +421,123 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     _lib.load()
-
-    cfg = workload_cfg(args.workload)
-    ln_top = mlp_sizes(cfg)
-    B = args.batch
-    np.random.seed(123)                                       # identical MLP init on every rank
-    dlrm = drv.DLRM_Net(cfg["dim"], np.array(cfg["rows"]), np.array(cfg["ln_bot"]), np.array(ln_top),
-                        arch_interaction_op="dot", sigmoid_bot=-1, sigmoid_top=len(ln_top) - 2, loss_function="bce",
-                        quantization_flag=True, embedding_bit=4, weight_bit=4, quantize_act_and_lin=True,
-                        mlp_channelwise=True, quantize_activation=False, device=dev, table_seed=1234)
-    dlrm.shard_scan = world > 1
-    table_bytes = sum(cfg["rows"]) * cfg["dim"] * 4
-
-    # a pool of distinct local batches, pinned on the host and resident on the device
-    pool = 8
-    host, devb = [], []
-    for i in range(pool):
-        X, lS_o, lS_i, T = synthetic.criteo_batch(cfg["rows"], B, seed=10_000 + 97 * rank + i)
-        hb = tuple(t.pin_memory() for t in (X, lS_o, lS_i, T))
-        host.append(hb)
-        devb.append(tuple(t.to(dev) for t in hb))
-    dlrm._ensure_group().scale_policy = args.scale_policy
-    step = GraphedTrainStep(dlrm, *devb[0], lr=LR, world_size=world, rank=rank, grad_bits=8, warmup=3,
-                            use_graph=not args.no_graph)
-    n0 = _lib.total_launches()                                # count OUR kernel launches of one step: one more
-    with torch.cuda.stream(step.stream):
-        step.scan(); step._body()                             # eager iteration (the graphs replay the same list)
-    torch.cuda.synchronize()
-    launches_per_step = _lib.total_launches() - n0
-    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step, K, W, from_host):
-        with torch.cuda.stream(step.stream):                 # high-priority stream of the step (graph_step.py)
-            return timed_on_stream(step, K, W, from_host)
-
-    def timed_on_stream(step, K, W, from_host):
-        ev_scan = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # e2e: packed pinned host batches -> one H2D copy per step; the loss of every step is read back to pinned host
-        # memory asynchronously and the host waits for step i-1's loss while step i runs (one step in flight)
-        src = [step.pack_host(*hb) for hb in host] if from_host else [step.pack_host(*hb, pin=False).to(dev) for hb in host]
-        done = [torch.cuda.Event(), torch.cuda.Event()]
-        for i in range(W):
-            step.load_packed(src[i % pool]); step.run()
-            if from_host:
-                loss_host[i % 2].copy_(step.loss, non_blocking=True); torch.cuda.current_stream().synchronize()
-        barrier()
-        e0.record()
-        for i in range(K):
-            step.load_packed(src[(W + i) % pool])
-            step.run(events=ev_scan[i])                      # scan launch (event-bracketed on ITS stream) + replay
-            if from_host:                                    # the reference reads the loss every step (:1928)
-                loss_host[i % 2].copy_(step.loss, non_blocking=True)
-                done[i % 2].record()
-                if i >= 1:
-                    done[(i - 1) % 2].synchronize()
-        if from_host:
-            done[(K - 1) % 2].synchronize()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        scan_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_scan]))
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), scan_ms
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    t_begin = time.perf_counter()
-    ms_dev, scan_ms = timed(step, args.steps, args.warmup, from_host=False)
-    ms_e2e, _ = timed(step, args.steps, args.warmup, from_host=True)
-    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
-    dlrm.emb_group.check_status()
-    dlrm._dense_arena.check_status()
-    final_loss = float(step.loss.item())
-    exchange = "single GPU: no exchange" if world == 1 else (
-        "one-kernel all-gathers over NVLink peer memory (csrc/p2p.cu), 5 per step, no NCCL call in the step"
-        if dlrm.emb_group.p2p is not None else "NCCL: 4 all-gathers + 1 MAX all-reduce per step (same slots and consumer kernels as the NVLink form)")
-    extras = {}
-    if args.scale_policy == "full" and not args.no_extras and world == 1:
-        # the same step with (a) the rescan overlapped with the step (block maxima on a side stream + fix-up of the
-        # updated blocks) and (b) the exact incremental tracker; reported beside the headline, never instead of it
-        variants = [("pipelined_rescan", "pipelined",
-                     "same full rescan (every table byte read once per step), overlapped with the step on a low-priority "
-                     "stream; scales bit-identical (tests/test_gpu_tracker.py)"),
-                    ("incremental_scale_tracker", "incremental",
-                     "exact block-max tracker: reads only the touched blocks; scales bit-identical to the "
-                     "rescan (SURVEY.md 8 f-1); not the headline because the reference rescans every step")]
-        for key, policy, note in variants:
-            dlrm.emb_group.scale_policy = policy
-            dlrm.emb_group.scale_valid = False
-            step2 = GraphedTrainStep(dlrm, *devb[0], lr=LR, world_size=world, rank=rank, grad_bits=8, warmup=3,
-                                     use_graph=not args.no_graph)
-            ms2, scan2 = timed(step2, args.steps, args.warmup, from_host=False)
-            ms2_e2e, _ = timed(step2, args.steps, args.warmup, from_host=True)
-            dlrm.emb_group.check_status()
-            extras[key] = {"value": B * world * args.steps / (ms2 / 1000.0), "unit": "samples/s",
-                           "ms_per_step": ms2 / args.steps,
-                           "e2e_value": B * world * args.steps / (ms2_e2e / 1000.0),
-                           "scan_kernel_ms": scan2, "note": note}
-            del step2
-        dlrm.emb_group.scale_policy = args.scale_policy
-        dlrm.emb_group.scale_valid = False
-
-    gbatch = B * world
-    value = gbatch * args.steps / (ms_dev / 1000.0)
-    e2e = gbatch * args.steps / (ms_e2e / 1000.0)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    algo_bytes = table_bytes / world if dlrm.shard_scan else table_bytes
-    achieved = algo_bytes / (scan_ms / 1000.0) / 1e9
-    nvlink = exchange_microbench(dlrm, world, barrier) if world > 1 else None
+    only = set(x for x in args.only.split(",") if x) or {"variants", "c2", "c3"}
+    if args.no_extras:
+        only = set()
+    K, W = args.steps, args.warmup
+
+    # ---------------- headline: BASELINE configs[1] (weak scaling: --batch per GPU) ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    run = Runner(args, args.workload, args.batch, world, rank, dev)
+    cfg = run.cfg
+    t_begin = time.perf_counter()
+    head, step = run.measure(args.scale_policy, K, W)
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
+    exchange = "single GPU: no exchange" if world == 1 else (
+        "one-kernel all-gathers over NVLink peer memory (csrc/p2p.cu), no NCCL call in the step"
+        if run.dlrm.emb_group.p2p is not None else "NCCL all-gathers (same slots and consumer kernels as the NVLink form)")
+    nvlink = exchange_microbench(run.dlrm, world, run.barrier) if world > 1 else None
+    identical = run.replicas_identical()
+    extras = {}
+    if "variants" in only and args.scale_policy == "full" and world == 1:
+        # the same step with (a) the rescan overlapped with the step (block maxima on a side stream + fix-up of the
+        # updated blocks) and (b) the exact incremental tracker; reported beside the headline, never instead of it
+        notes = {"pipelined": "same full rescan (every table byte read once per step), overlapped with the step on a "
+                              "low-priority stream; scales bit-identical (tests/test_gpu_tracker.py)",
+                 "incremental": "exact block-max tracker: reads only the touched blocks; scales bit-identical to the "
+                                "rescan (SURVEY.md 8 f-1); not the headline because the reference rescans every step"}
+        for key, policy in (("pipelined_rescan", "pipelined"), ("incremental_scale_tracker", "incremental")):
+            del step
+            r2, step = run.measure(policy, K, W)
+            extras[key] = {"value": r2["value"], "unit": "samples/s", "ms_per_step": r2["ms_per_step"],
+                           "step_ms": r2["step_ms"], "e2e_value": r2["e2e"]["value"],
+                           "scan_kernel_ms": r2["scan_kernel_ms"], "note": notes[policy]}
+    del step
+    head_roofline = run.roofline(args.scale_policy, head["scan_kernel_ms"], head["ms_per_step"], peaks)
+    run.close()
+
+    # ---------------- BASELINE configs[2] / configs[3]: FIXED global batch (strong scaling) ----------------
+    def fixed_global(key, workload, gbatch, what):
+        if gbatch % world:
+            extras[key] = {"skipped": f"global batch {gbatch} not divisible by {world} ranks"}
+            return
+        try:
+            r = Runner(args, workload, gbatch // world, world, rank, dev)
+            kk = K if workload != "terabyte" else max(5, min(K, 20))
+            res, st = r.measure("full", kk, max(3, min(W, 5)))
+            res["roofline"] = r.roofline("full", res["scan_kernel_ms"], res["ms_per_step"], peaks)
+            res["config"] = config_block(workload, r.cfg, gbatch // world, world)
+            res["scaling"] = "strong"
+            res["steps"] = kk
+            res["what"] = what
+            ident = r.replicas_identical()
+            if ident is not None:
+                res["replicas_bit_identical"] = ident
+            extras[key] = res
+            del st
+            r.close()
+        except Exception as e:                                    # an extra must never take the headline down
+            if world > 1:
+                raise                                             # (but ranks must not diverge: fail together)
+            extras[key] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+
+    if "c2" in only and args.workload == "kaggle":
+        fixed_global("configs2_kaggle_global2048", "kaggle", 2048,
+                     "BASELINE configs[2]: Kaggle shape, full INT4 (embeddings + MLP QAT), FIXED global batch 2048 split "
+                     "over the GPUs, quantised sparse gradient exchange; strong scaling: compare `value` across N")
+    if "c3" in only and args.workload == "kaggle":
+        fixed_global("configs3_terabyte_global8192", "terabyte", 8192,
+                     "BASELINE configs[3]: Terabyte shape (26 tables, 40M-row cap, 48.07 GB fp32 per replica, dim 64, bot "
+                     "13-512-256-64, top 512-512-256-1), FIXED global batch 8192 split over the GPUs; strong scaling")
+
     if rank != 0:
         finish(world)
         return
+    gbatch = args.batch * world
+    config = config_block(args.workload, cfg, args.batch, world)
     line = {
-        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-shape DQRM: {len(cfg['rows'])} tables ({sum(cfg['rows'])} rows, "
-                               f"{table_bytes / 1e9:.3f} GB fp32), dim {cfg['dim']}, INT4 emb+MLP QAT, INT8 grad exchange, "
-                               f"batch {B}/GPU", "global_batch": gbatch, "parallelism": f"dp{world}",
-                   "scale_scan": ({"incremental": "exact incremental block-max tracker",
-                                   "full": "full rescan every step (reference period-1 semantics), serialised before the forward",
-                                   "pipelined": "full rescan every step (every table byte read once per step, reference "
-                                                "period-1 semantics), overlapped with the step on a low-priority stream; "
-                                                "blocks holding updated rows are re-read after the update"}[args.scale_policy] +
-                                  (", row-sharded 1/N + MAX all-reduce" if dlrm.shard_scan else "")),
-                   "exchange": exchange,
-                   "l2": f"table arena ({table_bytes / 1e9:.2f} GB) is {table_bytes / 126e6:.0f}x the 126 MB L2: inputs larger than L2, no flush needed",
-                   "cuda_graph": step.graph is not None, "final_loss": final_loss},
-        "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": step.input_bytes(), "d2h_bytes_per_step": 4,
-                "pipeline": "one packed pinned H2D copy per step; loss D2H asynchronous, host waits for step i-1 while "
-                            "step i runs"},
-        "gpu_launches": launches_per_step * args.steps,
-        "gpu_launches_per_step": launches_per_step,
-        "roofline": {"kernel": {"pipelined": "blockmax_scan_kernel", "full": "table_absmax_kernel",
-                                "incremental": "table_absmax_kernel (block maxima)"}[args.scale_policy], "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_SCAN_TRAFFIC.get((args.workload, world, args.scale_policy)),
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                     "frac_of_nominal_8TBs": achieved / 8000.0,
-                     "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": scan_ms,
-                     "share_of_step": scan_ms / (ms_dev / args.steps)},
+        "metric": METRIC, "value": head["value"], "unit": "samples/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "details": {"scale_scan": ({"incremental": "exact incremental block-max tracker",
+                                    "full": "full rescan every step (reference period-1 semantics), serialised before the forward",
+                                    "pipelined": "full rescan every step (every table byte read once per step, reference "
+                                                 "period-1 semantics), overlapped with the step on a low-priority stream; "
+                                                 "blocks holding updated rows are re-read after the update"}[args.scale_policy] +
+                                   (", row-sharded 1/N, maxima combined over NVLink" if world > 1 else "")),
+                    "exchange": exchange,
+                    "l2": f"table arena ({run.table_bytes / 1e9:.2f} GB) is {run.table_bytes / 126e6:.0f}x the 126 MB L2: inputs larger than L2, no flush needed",
+                    "cuda_graph": head["cuda_graph"], "final_loss": head["final_loss"]},
+        "step_ms": head["step_ms"],
+        "e2e": dict(head["e2e"], pipeline="one packed pinned H2D copy per step; loss D2H asynchronous, host waits for "
+                                          "step i-1 while step i runs"),
+        "gpu_launches": head["gpu_launches_per_step"] * K,
+        "gpu_launches_per_step": head["gpu_launches_per_step"],
+        "roofline": head_roofline,
         "clocks": clocks,
     }
+    if identical is not None:
+        line["replicas_bit_identical"] = identical
     line.update(extras)
     if nvlink is not None:
         line["nvlink_exchange"] = nvlink
     if world == 1 and not args.no_cpu_baseline:
-        del step, dlrm
         torch.cuda.empty_cache()
-        val, ms, cores, build_s = oracle_arm(cfg, B, args.cpu_steps, 1)
+        val, ms, cores, build_s = oracle_arm(cfg, args.batch, args.cpu_steps, 1)
         line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
                                 "ms_per_step": ms,
-                                "sample": f"{args.cpu_steps} full train steps after 1 warm-up, batch {B}, same "
+                                "sample": f"{args.cpu_steps} full train steps after 1 warm-up, batch {args.batch}, same "
                                           f"{args.workload}-shape model on the host ({build_s:.0f}s to build tables)"}
     print(json.dumps(line), flush=True)
     finish(world)
-
-
-# DRAM traffic of one table_absmax_kernel launch from `ncu --set full` (dram__bytes_read.sum +
-# dram__bytes_write.sum, profiles/r01_scan_kernel_ncu_full.txt); valid for the full (unsharded) Kaggle scan.
-NCU_SCAN_TRAFFIC = {("kaggle", 1, "full"): 2.1647e9 + 3.9e6}
 
 
 def main():

@@ -151,7 +151,7 @@ class DenseArena:
         if self.slot_world == world:
             return
         import torch.distributed as dist
-        self.p2p = None
+        self.release()
         live = dist.is_available() and dist.is_initialized() and dist.get_world_size() == world
         a = None
         if live and _p2p.backend() == "p2p":
@@ -173,6 +173,21 @@ class DenseArena:
         self.slot_world, self.slot_rank = world, rank
         self.scale_local = self._scale_slots[rank, :self.num_chan]
         self._codes_mine = self._code_slots[rank, :self.total]
+
+    def release(self):
+        """Close the MLP exchange arena (barrier first: no rank may still be storing into it).  Collective."""
+        a, self.p2p = self.p2p, None
+        if a is None:
+            return
+        import torch.distributed as dist
+        live = dist.is_available() and dist.is_initialized()
+        torch.cuda.synchronize()
+        if live:
+            dist.barrier()
+        self._scale_slots = self._code_slots = self._codes_mine = None
+        self.scale_local = torch.zeros(self.num_chan, dtype=torch.float32, device=self.device)
+        self.slot_world = 0
+        a.close(dist.barrier if live else None)
 
     def _allgather(self, site, slots, process_group):
         if self.p2p is not None:

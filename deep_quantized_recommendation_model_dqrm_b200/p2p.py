@@ -119,12 +119,16 @@ class PeerArena:
             a._keep = bufs                           # the arenas alias these tensors
         return arenas
 
-    def close(self):
+    def close(self, barrier=None):
         """Unmap the peers' arenas and free the local one (collective in spirit: call on every rank, after a
-        barrier, when no exchange is in flight).  Views handed out by slots()/my_slot() must not be used afterwards."""
+        barrier, when no exchange is in flight).  `barrier` (a callable) runs between the unmap and the free, so no
+        exporter frees memory a peer still has mapped.  Views handed out by slots()/my_slot() must not be used
+        afterwards."""
         for q in self._opened:
             self.lib.dqrm_p2p_close(q)
         self._opened = []
+        if barrier is not None:
+            barrier()
         if getattr(self, "_keep", None) is None and self.base:
             self.lib.dqrm_p2p_free(self.base)
         self.base = None

@@ -372,7 +372,7 @@ class EmbeddingTableGroup:
         dev, T, D, world = self.device, self.T, self.dim, self.world
         sb = int(self.lib.dqrm_slot_bytes(T, self.capacity, D, self.grad_bit))
         self.slot_bytes = sb
-        self.p2p = None
+        self.release()                       # an arena of another geometry: unmap + free it first (collective)
         a = None
         if world > 1 and _p2p.backend() == "p2p" and _dist_world() == world:
             try:
@@ -392,6 +392,35 @@ class EmbeddingTableGroup:
                 self.grad_scale_local = torch.zeros(T, dtype=torch.float32, device=dev)
             self.gathered_scales = torch.zeros((world, T), dtype=torch.float32, device=dev)
             self.gathered = torch.zeros(world * sb, dtype=torch.uint8, device=dev)
+
+    def release(self):
+        """Close this group's peer arena (after a barrier, so no rank still stores into it) and drop the views of
+        it.  Collective when an arena exists: every rank gets here at the same point (geometry change, teardown)."""
+        a, self.p2p = self.p2p, None
+        if a is None:
+            return
+        import torch.distributed as dist
+        live = dist.is_available() and dist.is_initialized()
+        torch.cuda.synchronize()
+        if live:
+            dist.barrier()
+        self.gathered_scales = self.gathered = self.slot = None
+        self._absmax_slots = self._absmax_mine = None
+        self.grad_scale_local = torch.zeros(self.T, dtype=torch.float32, device=self.device)
+        a.close(dist.barrier if live else None)
+
+    def _agree_capacity(self, cap):
+        """All ranks must carve identical exchange slots: with real ranks and no caller-fixed capacity, take the
+        MAX of the first step's per-table lookup counts over the ranks once (host sync, outside any capture) and
+        keep it; a later step that needs more raises instead of silently re-creating arenas of another geometry."""
+        import torch.distributed as dist
+        if self.fixed_capacity is not None or not (dist.is_available() and dist.is_initialized()) \
+                or dist.get_world_size() == 1 or self.dp_world != dist.get_world_size():
+            return cap
+        t = torch.tensor([cap], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        self.fixed_capacity = int(t.item())
+        return self.fixed_capacity
 
     def _allreduce_absmax_to_scale(self, process_group):
         """Row-sharded scan: per-shard maxima in the absmax out-buffer -> MAX over ranks -> scale, 1/scale."""
@@ -418,6 +447,8 @@ class EmbeddingTableGroup:
         indices, offsets, idx_begin, ib, bags, full_precision = last if last is not None else self.last
         cap = max(idx_begin[k + 1] - idx_begin[k] for k in range(self.T))
         cap = max(cap, 1)
+        if world > 1 and self.fixed_capacity is None:
+            cap = self._agree_capacity(cap)
         if self.fixed_capacity is not None:
             # all ranks must agree on the slot capacity; with one index per bag (Criteo) it is simply the
             # local batch, with ragged multi-hot bags the caller fixes a common upper bound
