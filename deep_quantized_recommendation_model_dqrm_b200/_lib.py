@@ -51,8 +51,8 @@ SIGNATURES = {
     "dqrm_interact_bwd": (_i32, [_p, _p, _i64, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _i64, _i64, _p, _p]),
     "dqrm_linear_fakequant": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "dqrm_mlp_fakequant_all": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p]),
-    "dqrm_linear_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
-    "dqrm_linear_bwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p]),
+    "dqrm_linear_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _i32, _p]),
+    "dqrm_linear_bwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p]),
     "dqrm_fake_quant": (_i32, [_p, _i64, _i64, _p, _i32, _i32, _p, _p, _p]),
     "dqrm_dense_grad_scale": (_i32, [_p, _p, _p, _i32, _i32, _p, _p]),
     "dqrm_dense_grad_quant": (_i32, [_p, _p, _i32, _p, _f32, _i32, _p, _p, _p]),
@@ -69,6 +69,10 @@ SIGNATURES = {
     "dqrm_dense_apply_gathered": (_i32, [_p, _p, _sz, _i32, _p, _i32, _p, _f32, _p, _p, _p]),
     "dqrm_scale_from_absmax_gathered": (_i32, [_i32, _p, _sz, _i32, _i32, _p, _p, _p, _p]),
 }
+
+LINEAR_AUTO, LINEAR_FFMA, LINEAR_TC = 0, 1, 2
+# contraction engine of the fused QuantLinear kernels (include/dqrm_b200.h DQRM_LINEAR_*); env DQRM_MLP_PATH=ffma|tc|auto
+linear_path = {"auto": LINEAR_AUTO, "ffma": LINEAR_FFMA, "tc": LINEAR_TC}[os.environ.get("DQRM_MLP_PATH", "auto").lower()]
 
 _lib = None
 

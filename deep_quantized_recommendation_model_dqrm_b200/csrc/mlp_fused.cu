@@ -354,6 +354,20 @@ static int launch_gemm(const float* x, const float* W_int, const float* b_int, c
   return 0;
 }
 
+// mlp_tc.cu: the same three layer kernels with the contraction on tcgen05 tensor cores (TF32 split, fp32 parity)
+int launch_gemm_tc(int mode, const float* x, const float* W_int, const float* b_int, const float* s_row,
+                   const float* dout, const float* out, float* C, float* db, int batch, int out_f, int in_f, int act,
+                   int accumulate, cudaStream_t st);
+
+// path: DQRM_LINEAR_AUTO / _FFMA / _TC.  AUTO: tensor cores from DQRM_MLP_TC_MIN_BATCH rows (default 256) -- below
+// that a layer is a handful of tiles and the cluster split-K FFMA kernel's shorter prologue wins.
+static bool use_tc(int path, int batch) {
+  static const int min_batch = [] { const char* e = getenv("DQRM_MLP_TC_MIN_BATCH"); return e ? atoi(e) : 256; }();
+  if (path == DQRM_LINEAR_FFMA) return false;
+  if (path == DQRM_LINEAR_TC) return true;
+  return batch >= min_batch;
+}
+
 }  // namespace dqrm
 
 using namespace dqrm;
@@ -383,23 +397,36 @@ extern "C" int dqrm_mlp_fakequant_all(int num_layers, const float* const* W, con
 }
 
 extern "C" int dqrm_linear_fwd(const float* x, const float* W_int, const float* b_int, const float* scale_row,
-                               int batch, int out_features, int in_features, int act, float* out, void* stream) {
+                               int batch, int out_features, int in_features, int act, float* out, int path, void* stream) {
   DQRM_REQUIRE(x && W_int && scale_row && out, -EINVAL, "linear_fwd: null argument");
   DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_fwd: bad shape/act");
+  DQRM_REQUIRE(path >= 0 && path <= 2, -EINVAL, "linear_fwd: path=%d", path);
+  if (use_tc(path, batch))
+    return launch_gemm_tc(0, x, W_int, b_int, scale_row, nullptr, nullptr, out, nullptr, batch, out_features, in_features,
+                          act, 0, static_cast<cudaStream_t>(stream));
   return launch_gemm<0>(x, W_int, b_int, scale_row, nullptr, nullptr, out, nullptr, batch, out_features, in_features, act,
                         0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dqrm_linear_bwd(const float* x, const float* W_int, const float* scale_row, const float* dout,
                                const float* out, int batch, int out_features, int in_features, int act,
-                               float* dx, float* dW, float* db, int accumulate, void* stream) {
+                               float* dx, float* dW, float* db, int accumulate, int path, void* stream) {
   DQRM_REQUIRE(x && W_int && scale_row && dout && out && (dW || dx), -EINVAL, "linear_bwd: null argument");
   DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_bwd: bad shape/act");
+  DQRM_REQUIRE(path >= 0 && path <= 2, -EINVAL, "linear_bwd: path=%d", path);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dx)
-    if (int rc = launch_gemm<1>(x, W_int, nullptr, scale_row, dout, out, dx, nullptr, batch, out_features, in_features, act, 0, st))
-      return rc;
+  const bool tcp = use_tc(path, batch);
+  if (dx) {
+    const int rc = tcp ? launch_gemm_tc(1, x, W_int, nullptr, scale_row, dout, out, dx, nullptr, batch, out_features,
+                                        in_features, act, 0, st)
+                       : launch_gemm<1>(x, W_int, nullptr, scale_row, dout, out, dx, nullptr, batch, out_features,
+                                        in_features, act, 0, st);
+    if (rc) return rc;
+  }
   if (!dW) return 0;                                      // dx only (the caller runs dW on another stream)
+  if (tcp)
+    return launch_gemm_tc(2, x, W_int, nullptr, scale_row, dout, out, dW, db, batch, out_features, in_features, act,
+                          accumulate ? 1 : 0, st);
   return launch_gemm<2>(x, W_int, nullptr, scale_row, dout, out, dW, db, batch, out_features, in_features, act,
                         accumulate ? 1 : 0, st);
 }

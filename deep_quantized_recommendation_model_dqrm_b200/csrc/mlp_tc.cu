@@ -1,0 +1,467 @@
+// (a15) QuantLinear contractions on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+// Reference: QuantLinear.forward, quantization_supp/quant_modules_not_quantize_grad.py:209 (F.linear on the
+//            integer-valued weights) and its autograd (addmm backward + the STE of SymmetricQuantFunction, qu:363).
+//
+// Same three fused layer kernels as mlp_fused.cu (fwd / dx / dW+db with their prologues and epilogues), but the
+// contraction runs as tcgen05.mma instead of FFMA.  fp32 parity (1e-5 against the fp32 reference) is kept by
+// splitting every fp32 operand into TF32 terms inside the kernel while it is staged into shared memory:
+//     v = hi + lo (+ 2^-22 |v|),  hi = tf32(v),  lo = tf32(v - hi)
+//   * the fake-quantised weights W_int are integers in [-2^(b-1), 2^(b-1)-1]: EXACT in TF32, one term;
+//   * fwd  x W_int^t   and  dx  g W_int : (hi + lo) x W        -> 2 MMAs per K-step   ("2xTF32")
+//   * dW   g^t x                        : hi.hi + hi.lo + lo.hi -> 3 MMAs per K-step   ("3xTF32")
+// All products are exact in the tensor core (11 x 11 significant bits) and accumulate in fp32 in TMEM.
+//
+// One CTA = one 128 x BN output tile.  Operands are NOT loaded by TMA: every element has to pass through
+// registers anyway (the TF32 split; for dx / dW the operand g = dout * act'(out) * s_row is generated on the fly),
+// so 256 threads load 16-byte vectors, split, and store them straight into the UMMA canonical (no-swizzle) core
+// matrix layout -- K-major for x / g / W_int^t of the forward and dx, MN-major for the transposed operands of dW
+// and for W_int in dx, so no operand is ever transposed in shared memory.  Two shared-memory stages; thread 0
+// issues the MMAs of a stage and commits them to that stage's mbarrier, which is what frees the stage for
+// re-use (register prefetch of the next K-chunk overlaps the MMAs).  The epilogue reads the accumulators with
+// tcgen05.ld (thread = tile row) and applies bias / per-row scale / activation / STE division.
+// Small batches leave few tiles: K is split across a thread-block cluster (<= 8 CTAs) and the partial tiles are
+// reduced through distributed shared memory in fixed rank order -- deterministic, no atomics, no workspace.
+#include <cooperative_groups.h>
+
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace dqrm {
+namespace tc {
+
+constexpr int BM = 128, BK = 32, kThreads = 256;
+constexpr int A_TILE_BYTES = BM * BK * 4;                       // 16 KiB per TF32 term
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// A commit that never arrives must abort the kernel (sticky launch error on the host), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, SWIZZLE_NONE ("interleaved" 8 x 16 B core matrices), version 1 (sm_100):
+// start address, leading-dimension byte offset, stride-dimension byte offset, each >> 4.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// kind::tf32 instruction descriptor: D = f32, A = B = tf32, majors, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+  lo = make_float4(to_tf32(__fsub_rn(v.x, hi.x)), to_tf32(__fsub_rn(v.y, hi.y)), to_tf32(__fsub_rn(v.z, hi.z)),
+                   to_tf32(__fsub_rn(v.w, hi.w)));
+}
+
+// 4 consecutive elements of row `row` starting at column `col` (col % 4 == 0) of a row-major [nrows, ncols] matrix;
+// out-of-range elements read as 0.  `vec`: the matrix allows 16-byte loads (ld % 4 == 0, base 16-byte aligned).
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p, int row, int col, int nrows, int ncols, int ld, bool vec) {
+  if (row >= nrows || col >= ncols) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* q = p + (long long)row * ld + col;
+  if (vec && col + 3 < ncols) return __ldg(reinterpret_cast<const float4*>(q));
+  float4 r = make_float4(__ldg(q), 0.f, 0.f, 0.f);
+  if (col + 1 < ncols) r.y = __ldg(q + 1);
+  if (col + 2 < ncols) r.z = __ldg(q + 2);
+  if (col + 3 < ncols) r.w = __ldg(q + 3);
+  return r;
+}
+
+__device__ __forceinline__ float act_bwd(float dout, float out, int act) {
+  if (act == 1) return out > 0.0f ? dout : 0.0f;                        // threshold_backward
+  if (act == 2) return dout * ((1.0f - out) * out);                     // sigmoid_backward
+  return dout;
+}
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == 1) return fmaxf(z, 0.0f);
+  if (act == 2) return 1.0f / (1.0f + expf(-z));
+  return z;
+}
+
+// MODE 0 (fwd): C[b, n]  = act((sum_k x[b,k] W[n,k] + b_int[n]) * s[n])     M = batch, N = out, K = in
+// MODE 1 (dx) : C[b, i]  = sum_o g[b,o] W[o,i],  g = dout * act'(out) * s    M = batch, N = in,  K = out
+// MODE 2 (dW) : C[o, i] (+)= (sum_b g[b,o] x[b,i]) / s[o] ; db[o] (+)= (sum_b g[b,o]) / s[o]
+//                                                                            M = out,   N = in,  K = batch
+template <int MODE, int BN, bool CL>
+__global__ void __launch_bounds__(kThreads)
+linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, const float* __restrict__ b_int,
+                 const float* __restrict__ s_row, const float* __restrict__ dout, const float* __restrict__ out,
+                 float* __restrict__ C, float* __restrict__ db, int batch, int out_f, int in_f, int act, int kc,
+                 int accumulate, int vec_x, int vec_w, int vec_g) {
+  namespace cg = cooperative_groups;
+  constexpr int B_TILE_BYTES = BN * BK * 4;
+  constexpr int B_TERMS = MODE == 2 ? 2 : 1;
+  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + B_TERMS * B_TILE_BYTES;
+  constexpr int NA = BM * (BK / 4) / kThreads;                         // 16-byte slots per thread: A (4)
+  constexpr int NB = BN * (BK / 4) / kThreads;                         //                            B (BN / 32)
+  constexpr int RED_LD = BN + 1;                                       // padded partial-tile row (bank-conflict free)
+  static_assert(BM * RED_LD * 4 <= 2 * STAGE_BYTES, "partial tile must fit in the stage buffers");
+  constexpr uint32_t IDESC = umma_idesc(BM, BN, MODE == 2, MODE != 0);
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_stage[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ float db_s[8][BM];
+  __shared__ float db_cta[BM];
+
+  int S = 1, rank = 0;
+  if constexpr (CL) {
+    cg::cluster_group cluster = cg::this_cluster();
+    S = (int)cluster.num_blocks();
+    rank = (int)cluster.block_rank();
+  }
+  const int M = MODE == 2 ? out_f : batch;
+  const int N = MODE == 0 ? out_f : in_f;
+  const int K = MODE == 0 ? in_f : (MODE == 1 ? out_f : batch);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kbeg = rank * kc, kend = min(K, kbeg + kc);
+  const int nchunks = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
+
+  if (tid == 0) {
+    mbar_init(&bar_stage[0], 1);
+    mbar_init(&bar_stage[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = s_tmem;
+
+  // ---- operand staging -------------------------------------------------------------------------------------------
+  // 16-byte slot e of a [R x BK] tile.  K-major: 8 consecutive lanes = 8 rows of one 4-element K-chunk (a 128-byte
+  // core matrix); MN-major: 8 consecutive lanes = 8 k of one 4-element MN-chunk.  Either way a warp reads 8 global
+  // rows x 64 B and writes 4 whole core matrices: sector-exact global loads, conflict-free shared stores.
+  float4 ra0[NA], ra1[NA], rb[NB];
+  const bool do_db = MODE == 2 && db != nullptr && blockIdx.x == 0;
+  float4 db_part = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto load_chunk = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int e = tid + i * kThreads;
+      if (MODE == 0) {                                                   // x[m, k], K-major
+        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
+        ra0[i] = ld4(x, m0 + r, k0 + kq * 4, M, kend, in_f, vec_x);
+      } else if (MODE == 1) {                                            // g[b = m, o = k], K-major
+        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
+        ra0[i] = ld4(dout, m0 + r, k0 + kq * 4, M, kend, out_f, vec_g);
+        ra1[i] = ld4(out, m0 + r, k0 + kq * 4, M, kend, out_f, vec_g);
+      } else {                                                           // g[b = k, o = m], MN-major
+        const int k = (e & 7) + ((e >> 8) << 3), c = (e >> 3) & 31;
+        ra0[i] = ld4(dout, k0 + k, m0 + c * 4, kend, M, out_f, vec_g);
+        ra1[i] = ld4(out, k0 + k, m0 + c * 4, kend, M, out_f, vec_g);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int e = tid + i * kThreads;
+      if (MODE == 0) {                                                   // W_int[n, k], K-major
+        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
+        rb[i] = ld4(W_int, n0 + r, k0 + kq * 4, N, kend, in_f, vec_w);
+      } else {                                                           // W_int[o = k, i = n] / x[b = k, i = n], MN-major
+        const int k = (e & 7) + (e / (2 * BN)) * 8, c = (e >> 3) & (BN / 4 - 1);
+        rb[i] = ld4(MODE == 1 ? W_int : x, k0 + k, n0 + c * 4, kend, N, in_f, MODE == 1 ? vec_w : vec_x);
+      }
+    }
+  };
+
+  auto store_chunk = [&](int stage, int k0) {
+    unsigned char* a_hi = smem + stage * STAGE_BYTES;
+    unsigned char* a_lo = a_hi + A_TILE_BYTES;
+    unsigned char* b_hi = a_lo + A_TILE_BYTES;
+    unsigned char* b_lo = b_hi + B_TILE_BYTES;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int e = tid + i * kThreads;
+      float4 v = ra0[i];
+      int off;
+      if (MODE == 0) {
+        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
+        off = kq * (BM * 16) + r * 16;
+      } else if (MODE == 1) {
+        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
+        off = kq * (BM * 16) + r * 16;
+        const int o = k0 + kq * 4;                                       // g = dout * act'(out) * s_row[o]
+        v.x = __fmul_rn(act_bwd(v.x, ra1[i].x, act), o + 0 < kend ? __ldg(s_row + o + 0) : 0.f);
+        v.y = __fmul_rn(act_bwd(v.y, ra1[i].y, act), o + 1 < kend ? __ldg(s_row + o + 1) : 0.f);
+        v.z = __fmul_rn(act_bwd(v.z, ra1[i].z, act), o + 2 < kend ? __ldg(s_row + o + 2) : 0.f);
+        v.w = __fmul_rn(act_bwd(v.w, ra1[i].w, act), o + 3 < kend ? __ldg(s_row + o + 3) : 0.f);
+      } else {
+        const int k = (e & 7) + ((e >> 8) << 3), c = (e >> 3) & 31;
+        off = (k >> 3) * (BM * 32) + c * 128 + (k & 7) * 16;
+        const int o = m0 + c * 4;
+        v.x = __fmul_rn(act_bwd(v.x, ra1[i].x, act), o + 0 < M ? __ldg(s_row + o + 0) : 0.f);
+        v.y = __fmul_rn(act_bwd(v.y, ra1[i].y, act), o + 1 < M ? __ldg(s_row + o + 1) : 0.f);
+        v.z = __fmul_rn(act_bwd(v.z, ra1[i].z, act), o + 2 < M ? __ldg(s_row + o + 2) : 0.f);
+        v.w = __fmul_rn(act_bwd(v.w, ra1[i].w, act), o + 3 < M ? __ldg(s_row + o + 3) : 0.f);
+        if (do_db) {                                                     // column sums of g: this thread's 4 channels
+          db_part.x = __fadd_rn(db_part.x, v.x); db_part.y = __fadd_rn(db_part.y, v.y);
+          db_part.z = __fadd_rn(db_part.z, v.z); db_part.w = __fadd_rn(db_part.w, v.w);
+        }
+      }
+      float4 hi, lo;
+      split4(v, hi, lo);
+      *reinterpret_cast<float4*>(a_hi + off) = hi;
+      *reinterpret_cast<float4*>(a_lo + off) = lo;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int e = tid + i * kThreads;
+      int off;
+      if (MODE == 0) {
+        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
+        off = kq * (BN * 16) + r * 16;
+      } else {
+        const int k = (e & 7) + (e / (2 * BN)) * 8, c = (e >> 3) & (BN / 4 - 1);
+        off = (k >> 3) * (BN * 32) + c * 128 + (k & 7) * 16;
+      }
+      if (MODE == 2) {
+        float4 hi, lo;
+        split4(rb[i], hi, lo);
+        *reinterpret_cast<float4*>(b_hi + off) = hi;
+        *reinterpret_cast<float4*>(b_lo + off) = lo;
+      } else {
+        *reinterpret_cast<float4*>(b_hi + off) = rb[i];                  // small integers: exact in TF32 as they are
+      }
+    }
+  };
+
+  // ---- main loop: two stages, the commit of a stage's MMAs frees it ------------------------------------------------
+  if (nchunks) load_chunk(kbeg);
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c & 1;
+    if (c >= 2) mbar_wait(&bar_stage[st], ((c >> 1) - 1) & 1);           // MMAs of chunk c-2 have read this stage
+    store_chunk(st, kbeg + c * BK);
+    fence_proxy_async();                                                 // generic-proxy stores -> visible to the MMA
+    __syncthreads();
+    if (c + 1 < nchunks) load_chunk(kbeg + (c + 1) * BK);                // in flight while the MMAs run
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
+      const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+      // K-major tile of R rows:  LBO (K-chunk stride) = R*16, SBO (8-row group stride) = 128; one K=8 step = 2 chunks
+      // MN-major tile of R cols: SBO (4-element MN-chunk stride) = 128, LBO (8-k group stride) = R*32
+      // either way the next K-step starts R*32 bytes further
+      constexpr uint32_t A_LBO = MODE == 2 ? BM * 32 : BM * 16, B_LBO = MODE == 0 ? BN * 16 : BN * 32;
+#pragma unroll
+      for (int j = 0; j < BK / 8; ++j) {
+        const uint64_t dah = umma_desc(a_hi + j * BM * 32, A_LBO, 128), dal = umma_desc(a_lo + j * BM * 32, A_LBO, 128);
+        const uint64_t dbh = umma_desc(b_hi + j * BN * 32, B_LBO, 128);
+        umma_tf32(tmem_d, dah, dbh, IDESC, (c | j) != 0);
+        umma_tf32(tmem_d, dal, dbh, IDESC, 1);
+        if (MODE == 2) umma_tf32(tmem_d, dah, umma_desc(b_lo + j * BN * 32, B_LBO, 128), IDESC, 1);
+      }
+      umma_commit(&bar_stage[st]);
+    }
+  }
+  if (nchunks) {
+    const int last = nchunks - 1;
+    mbar_wait(&bar_stage[last & 1], (last >> 1) & 1);                    // MMAs execute in order: all are complete
+  }
+  tc_fence_after();
+
+  // ---- epilogue ------------------------------------------------------------------------------------------------------
+  const int q = warp & 3, h = warp >> 2;                                 // TMEM lane quarter, column half
+  const int row = q * 32 + lane;                                         // tile row owned by this thread
+  constexpr int CW = BN / 2;                                             // columns per warp
+  auto epilogue = [&](int m, int n, float v) {
+    if (m >= M || n >= N) return;
+    if (MODE == 0) {
+      const float z = __fmul_rn(__fadd_rn(v, b_int ? __ldg(b_int + n) : 0.0f), __ldg(s_row + n));
+      C[(long long)m * out_f + n] = act_fwd(z, act);
+    } else if (MODE == 1) {
+      C[(long long)m * in_f + n] = v;
+    } else {
+      float* dst = C + (long long)m * in_f + n;
+      const float gq = __fdiv_rn(v, __ldg(s_row + m));
+      *dst = accumulate ? __fadd_rn(*dst, gq) : gq;
+    }
+  };
+  if (do_db) db_s[tid & 7][(tid >> 3) * 4 + 0] = db_part.x, db_s[tid & 7][(tid >> 3) * 4 + 1] = db_part.y,
+             db_s[tid & 7][(tid >> 3) * 4 + 2] = db_part.z, db_s[tid & 7][(tid >> 3) * 4 + 3] = db_part.w;
+  float* red = reinterpret_cast<float*>(smem);                           // [BM][RED_LD] partial tile (split-K only)
+#pragma unroll
+  for (int cb = 0; cb < CW; cb += 32) {
+    float v[32];
+    if (nchunks) {
+      tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * CW + cb), v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+    }
+    if (S == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) epilogue(m0 + row, n0 + h * CW + cb + i, v[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) red[row * RED_LD + h * CW + cb + i] = v[i];
+    }
+  }
+  __syncthreads();
+  if (do_db && tid < BM) {
+    float t = db_s[0][tid];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) t = __fadd_rn(t, db_s[j][tid]);
+    db_cta[tid] = t;
+  }
+  if (S == 1) {
+    if (do_db && tid < BM && m0 + tid < M) {
+      const float gq = __fdiv_rn(db_cta[tid], __ldg(s_row + m0 + tid));
+      db[m0 + tid] = accumulate ? __fadd_rn(db[m0 + tid], gq) : gq;
+    }
+  } else if constexpr (CL) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    const int rows_per = BM / S;                                         // S in {2, 4, 8}
+    for (int e = tid; e < rows_per * BN; e += kThreads) {
+      const int r = rank * rows_per + e / BN, cc = e % BN;
+      float part[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p)                                        // all DSMEM loads in flight, then a fixed-order sum
+        part[p] = p < S ? cluster.map_shared_rank(red, p)[r * RED_LD + cc] : 0.0f;
+      float v = part[0];
+#pragma unroll
+      for (int p = 1; p < 8; ++p) if (p < S) v = __fadd_rn(v, part[p]);
+      epilogue(m0 + r, n0 + cc, v);
+    }
+    if (do_db && rank == 0 && tid < BM && m0 + tid < M) {
+      float t = db_cta[tid];
+      for (int p = 1; p < S; ++p) t = __fadd_rn(t, cluster.map_shared_rank(db_cta, p)[tid]);
+      const float gq = __fdiv_rn(t, __ldg(s_row + m0 + tid));
+      db[m0 + tid] = accumulate ? __fadd_rn(db[m0 + tid], gq) : gq;
+    }
+    cluster.sync();                                                      // peers must not exit while being read
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+}
+
+static int pick_split(int tiles, int K) {
+  static const int max_s = [] { const char* e = getenv("DQRM_MLP_MAX_CLUSTER"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+  int S = 1;
+  while (S < max_s && tiles * S < 128 && K / (S * 2) >= BK) S *= 2;     // every K-slice keeps >= 1 full chunk
+  return S;
+}
+
+template <int MODE, int BN>
+static int launch(const float* x, const float* W_int, const float* b_int, const float* s_row, const float* dout,
+                  const float* out, float* C, float* db, int batch, int out_f, int in_f, int act, int accumulate,
+                  cudaStream_t st) {
+  const int M = MODE == 2 ? out_f : batch;
+  const int N = MODE == 0 ? out_f : in_f;
+  const int K = MODE == 0 ? in_f : (MODE == 1 ? out_f : batch);
+  const int gx = (N + BN - 1) / BN, gy = (M + BM - 1) / BM;
+  const int S = pick_split(gx * gy, K);
+  int kc = (K + S - 1) / S;
+  kc = ((kc + BK - 1) / BK) * BK;
+  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + (MODE == 2 ? 2 : 1) * BN * BK * 4;
+  const size_t smem = 2 * (size_t)STAGE_BYTES;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const int vec_x = (in_f % 4 == 0) && al16(x), vec_w = (in_f % 4 == 0) && al16(W_int);
+  const int vec_g = (out_f % 4 == 0) && (!dout || al16(dout)) && (!out || al16(out));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, gy, S);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+  cfg.attrs = attr;
+  cfg.numAttrs = S > 1 ? 1 : 0;
+  cudaError_t e;
+  if (S > 1) {
+    auto kern = linear_tc_kernel<MODE, BN, true>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaLaunchKernelEx(&cfg, kern, x, W_int, b_int, s_row, dout, out, C, db, batch, out_f, in_f, act, kc, accumulate,
+                             vec_x, vec_w, vec_g);
+  } else {
+    auto kern = linear_tc_kernel<MODE, BN, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaLaunchKernelEx(&cfg, kern, x, W_int, b_int, s_row, dout, out, C, db, batch, out_f, in_f, act, kc, accumulate,
+                             vec_x, vec_w, vec_g);
+  }
+  if (e != cudaSuccess) { set_error("linear_tc_kernel<%d,%d>: %s", MODE, BN, cudaGetErrorString(e)); return -EIO; }
+  return 0;
+}
+
+}  // namespace tc
+
+// Entry used by dqrm_linear_fwd / dqrm_linear_bwd (mlp_fused.cu).  BN = 64 when the output is narrow or the grid
+// would otherwise be small, else 128.
+int launch_gemm_tc(int mode, const float* x, const float* W_int, const float* b_int, const float* s_row,
+                   const float* dout, const float* out, float* C, float* db, int batch, int out_f, int in_f, int act,
+                   int accumulate, cudaStream_t st) {
+  const int M = mode == 2 ? out_f : batch;
+  const int N = mode == 0 ? out_f : in_f;
+  const bool narrow = N <= 64 || ((N + 127) / 128) * ((M + 127) / 128) < 64;
+#define DQRM_TC(MODE)                                                                                                  \
+  (narrow ? tc::launch<MODE, 64>(x, W_int, b_int, s_row, dout, out, C, db, batch, out_f, in_f, act, accumulate, st)    \
+          : tc::launch<MODE, 128>(x, W_int, b_int, s_row, dout, out, C, db, batch, out_f, in_f, act, accumulate, st))
+  if (mode == 0) return DQRM_TC(0);
+  if (mode == 1) return DQRM_TC(1);
+  return DQRM_TC(2);
+#undef DQRM_TC
+}
+
+}  // namespace dqrm

