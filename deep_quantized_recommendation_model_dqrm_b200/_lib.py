@@ -66,7 +66,7 @@ SIGNATURES = {
     "dqrm_p2p_site_layout": (_i32, [_i32, _sz, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "dqrm_p2p_allgather": (_i32, [_p, _i32, _i32, _sz, _sz, _p, _p]),
     "dqrm_dense_grad_quant_gathered": (_i32, [_p, _p, _i32, _p, _sz, _i32, _i32, _p, _p, _p]),
-    "dqrm_dense_apply_gathered": (_i32, [_p, _p, _sz, _i32, _p, _i32, _p, _f32, _p, _p, _p]),
+    "dqrm_dense_apply_gathered": (_i32, [_p, _p, _sz, _i32, _p, _i32, _p, _f32, _p, _p, _p, _p]),
     "dqrm_scale_from_absmax_gathered": (_i32, [_i32, _p, _sz, _i32, _i32, _p, _p, _p, _p]),
 }
 

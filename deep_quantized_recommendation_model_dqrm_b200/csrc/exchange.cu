@@ -98,6 +98,7 @@ grad_merge_apply_kernel(const __grid_constant__ TableSet ts, int dim4, int group
                         int* __restrict__ updated_rows, int* __restrict__ updated_count, float* __restrict__ qbar,
                         int* __restrict__ status) {
   using C4 = typename Code4<CodeT>::type;
+  if (*status & DQRM_STATUS_P2P_TIMEOUT) return;                         // an exchange timed out: never apply stale slots
   const int t = blockIdx.z, r = blockIdx.y;
   const unsigned char* my = gathered + (size_t)r * lay.bytes;
   const int U = reinterpret_cast<const int*>(my)[t];

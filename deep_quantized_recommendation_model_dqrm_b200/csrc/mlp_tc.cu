@@ -13,9 +13,9 @@
 //
 // One CTA = one 128 x BN output tile.  Operands are NOT loaded by TMA: every element has to pass through
 // registers anyway (the TF32 split; for dx / dW the operand g = dout * act'(out) * s_row is generated on the fly),
-// so 256 threads load 16-byte vectors, split, and store them straight into the UMMA canonical (no-swizzle) core
-// matrix layout -- K-major for x / g / W_int^t of the forward and dx, MN-major for the transposed operands of dW
-// and for W_int in dx, so no operand is ever transposed in shared memory.  Two shared-memory stages; thread 0
+// so 256 threads load, split, and store straight into the UMMA canonical no-swizzle K-major core-matrix layout
+// (kind::tf32 takes MN-major operands only in the 128B_BASE32B swizzle, so the operands whose K is not contiguous
+// in global memory -- W_int in dx, g and x in dW -- are transposed by the store pattern).  Two stages; thread 0
 // issues the MMAs of a stage and commits them to that stage's mbarrier, which is what frees the stage for
 // re-use (register prefetch of the next K-chunk overlaps the MMAs).  The epilogue reads the accumulators with
 // tcgen05.ld (thread = tile row) and applies bias / per-row scale / activation / STE division.
@@ -143,16 +143,14 @@ linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, c
   constexpr int B_TILE_BYTES = BN * BK * 4;
   constexpr int B_TERMS = MODE == 2 ? 2 : 1;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + B_TERMS * B_TILE_BYTES;
-  constexpr int NA = BM * (BK / 4) / kThreads;                         // 16-byte slots per thread: A (4)
-  constexpr int NB = BN * (BK / 4) / kThreads;                         //                            B (BN / 32)
   constexpr int RED_LD = BN + 1;                                       // padded partial-tile row (bank-conflict free)
   static_assert(BM * RED_LD * 4 <= 2 * STAGE_BYTES, "partial tile must fit in the stage buffers");
-  constexpr uint32_t IDESC = umma_idesc(BM, BN, MODE == 2, MODE != 0);
+  constexpr uint32_t IDESC = umma_idesc(BM, BN, 0, 0);                 // both operands K-major
 
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_stage[2];
   __shared__ uint32_t s_tmem;
-  __shared__ float db_s[8][BM];
+  __shared__ float db_s[4][BM];
   __shared__ float db_cta[BM];
 
   int S = 1, rank = 0;
@@ -184,39 +182,68 @@ linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, c
   const uint32_t tmem_d = s_tmem;
 
   // ---- operand staging -------------------------------------------------------------------------------------------
-  // 16-byte slot e of a [R x BK] tile.  K-major: 8 consecutive lanes = 8 rows of one 4-element K-chunk (a 128-byte
-  // core matrix); MN-major: 8 consecutive lanes = 8 k of one 4-element MN-chunk.  Either way a warp reads 8 global
-  // rows x 64 B and writes 4 whole core matrices: sector-exact global loads, conflict-free shared stores.
-  float4 ra0[NA], ra1[NA], rb[NB];
+  // Every operand is staged K-major (the only no-swizzle layout kind::tf32 accepts for either major-ness is K-major;
+  // MN-major TF32 needs the 128B_BASE32B swizzle), i.e. as [K/4][rows][4 floats]: a 128-byte core matrix = 8 rows x
+  // 4 consecutive k.
+  //  * operand already K-contiguous in global memory (x and W_int in fwd, g in dx): "V" staging -- 16-byte slots,
+  //    8 consecutive lanes = 8 rows of one K-chunk: a warp reads 8 global rows x 64 B and writes 4 whole core
+  //    matrices with conflict-free 16-byte stores.
+  //  * operand contiguous along M/N in global memory (W_int in dx, g and x in dW, whose K is the batch): "T" staging
+  //    -- scalar slots, a warp covers 8 consecutive m x 4 consecutive k: 4 fully used 32-byte sectors per load
+  //    instruction, and the transposing 4-byte shared stores hit 32 distinct banks.
+  constexpr int NAV = BM * (BK / 4) / kThreads;                        // V slots per thread: A (4)
+  constexpr int NBV = BN * (BK / 4) / kThreads;                        //                     B (BN / 32)
+  constexpr int NAT = BM * BK / kThreads;                              // T slots per thread: A (16)
+  constexpr int NBT = BN * BK / kThreads;                              //                     B (BN / 8)
+  float4 va0[MODE == 2 ? 1 : NAV], va1[MODE == 1 ? NAV : 1], vb[MODE == 0 ? NBV : 1];
+  float ta0[MODE == 2 ? NAT : 1], ta1[MODE == 2 ? NAT : 1], tb[MODE == 0 ? 1 : NBT];
   const bool do_db = MODE == 2 && db != nullptr && blockIdx.x == 0;
-  float4 db_part = make_float4(0.f, 0.f, 0.f, 0.f);
+  float db_part[2] = {0.f, 0.f};
+  const int lane_m8 = lane & 7, lane_k4 = lane >> 3;
+
+  // V slot e of an [R x BK] tile: row, K-chunk
+  auto v_slot = [](int e, int& r, int& kq) { r = (e & 7) + ((e >> 6) << 3); kq = (e >> 3) & 7; };
+  // T slot i of this thread in an [R x BK] tile: m (0..R), k (0..BK)
+  auto t_slot = [&](int i, int R, int& m, int& k) {
+    const int w = warp + (kThreads / 32) * i, groups = R / 8;
+    m = (w % groups) * 8 + lane_m8;
+    k = (w / groups) * 4 + lane_k4;
+  };
+  auto ld1 = [](const float* __restrict__ p, int row, int col, int nrows, int ncols, int ld) -> float {
+    return (row < nrows && col < ncols) ? __ldg(p + (long long)row * ld + col) : 0.0f;
+  };
 
   auto load_chunk = [&](int k0) {
+    if constexpr (MODE != 2) {
 #pragma unroll
-    for (int i = 0; i < NA; ++i) {
-      const int e = tid + i * kThreads;
-      if (MODE == 0) {                                                   // x[m, k], K-major
-        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
-        ra0[i] = ld4(x, m0 + r, k0 + kq * 4, M, kend, in_f, vec_x);
-      } else if (MODE == 1) {                                            // g[b = m, o = k], K-major
-        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
-        ra0[i] = ld4(dout, m0 + r, k0 + kq * 4, M, kend, out_f, vec_g);
-        ra1[i] = ld4(out, m0 + r, k0 + kq * 4, M, kend, out_f, vec_g);
-      } else {                                                           // g[b = k, o = m], MN-major
-        const int k = (e & 7) + ((e >> 8) << 3), c = (e >> 3) & 31;
-        ra0[i] = ld4(dout, k0 + k, m0 + c * 4, kend, M, out_f, vec_g);
-        ra1[i] = ld4(out, k0 + k, m0 + c * 4, kend, M, out_f, vec_g);
+      for (int i = 0; i < NAV; ++i) {
+        int r, kq; v_slot(tid + i * kThreads, r, kq);
+        if (MODE == 0) {
+          va0[i] = ld4(x, m0 + r, k0 + kq * 4, M, kend, in_f, vec_x);                    // x[m, k]
+        } else {
+          va0[i] = ld4(dout, m0 + r, k0 + kq * 4, M, kend, out_f, vec_g);                // g[b = m, o = k]
+          va1[i] = ld4(out, m0 + r, k0 + kq * 4, M, kend, out_f, vec_g);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NAT; ++i) {                                                    // g[b = k, o = m]
+        int m, k; t_slot(i, BM, m, k);
+        ta0[i] = ld1(dout, k0 + k, m0 + m, kend, M, out_f);
+        ta1[i] = ld1(out, k0 + k, m0 + m, kend, M, out_f);
       }
     }
+    if constexpr (MODE == 0) {
 #pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      const int e = tid + i * kThreads;
-      if (MODE == 0) {                                                   // W_int[n, k], K-major
-        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
-        rb[i] = ld4(W_int, n0 + r, k0 + kq * 4, N, kend, in_f, vec_w);
-      } else {                                                           // W_int[o = k, i = n] / x[b = k, i = n], MN-major
-        const int k = (e & 7) + (e / (2 * BN)) * 8, c = (e >> 3) & (BN / 4 - 1);
-        rb[i] = ld4(MODE == 1 ? W_int : x, k0 + k, n0 + c * 4, kend, N, in_f, MODE == 1 ? vec_w : vec_x);
+      for (int i = 0; i < NBV; ++i) {
+        int r, kq; v_slot(tid + i * kThreads, r, kq);
+        vb[i] = ld4(W_int, n0 + r, k0 + kq * 4, N, kend, in_f, vec_w);                   // W_int[n, k]
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NBT; ++i) {                                                    // W_int[o = k, i = n] / x[b = k, i = n]
+        int n, k; t_slot(i, BN, n, k);
+        tb[i] = ld1(MODE == 1 ? W_int : x, k0 + k, n0 + n, kend, N, in_f);
       }
     }
   };
@@ -226,100 +253,110 @@ linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, c
     unsigned char* a_lo = a_hi + A_TILE_BYTES;
     unsigned char* b_hi = a_lo + A_TILE_BYTES;
     unsigned char* b_lo = b_hi + B_TILE_BYTES;
+    if constexpr (MODE != 2) {
 #pragma unroll
-    for (int i = 0; i < NA; ++i) {
-      const int e = tid + i * kThreads;
-      float4 v = ra0[i];
-      int off;
-      if (MODE == 0) {
-        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
-        off = kq * (BM * 16) + r * 16;
-      } else if (MODE == 1) {
-        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
-        off = kq * (BM * 16) + r * 16;
-        const int o = k0 + kq * 4;                                       // g = dout * act'(out) * s_row[o]
-        v.x = __fmul_rn(act_bwd(v.x, ra1[i].x, act), o + 0 < kend ? __ldg(s_row + o + 0) : 0.f);
-        v.y = __fmul_rn(act_bwd(v.y, ra1[i].y, act), o + 1 < kend ? __ldg(s_row + o + 1) : 0.f);
-        v.z = __fmul_rn(act_bwd(v.z, ra1[i].z, act), o + 2 < kend ? __ldg(s_row + o + 2) : 0.f);
-        v.w = __fmul_rn(act_bwd(v.w, ra1[i].w, act), o + 3 < kend ? __ldg(s_row + o + 3) : 0.f);
-      } else {
-        const int k = (e & 7) + ((e >> 8) << 3), c = (e >> 3) & 31;
-        off = (k >> 3) * (BM * 32) + c * 128 + (k & 7) * 16;
-        const int o = m0 + c * 4;
-        v.x = __fmul_rn(act_bwd(v.x, ra1[i].x, act), o + 0 < M ? __ldg(s_row + o + 0) : 0.f);
-        v.y = __fmul_rn(act_bwd(v.y, ra1[i].y, act), o + 1 < M ? __ldg(s_row + o + 1) : 0.f);
-        v.z = __fmul_rn(act_bwd(v.z, ra1[i].z, act), o + 2 < M ? __ldg(s_row + o + 2) : 0.f);
-        v.w = __fmul_rn(act_bwd(v.w, ra1[i].w, act), o + 3 < M ? __ldg(s_row + o + 3) : 0.f);
-        if (do_db) {                                                     // column sums of g: this thread's 4 channels
-          db_part.x = __fadd_rn(db_part.x, v.x); db_part.y = __fadd_rn(db_part.y, v.y);
-          db_part.z = __fadd_rn(db_part.z, v.z); db_part.w = __fadd_rn(db_part.w, v.w);
+      for (int i = 0; i < NAV; ++i) {
+        int r, kq; v_slot(tid + i * kThreads, r, kq);
+        float4 v = va0[i];
+        if (MODE == 1) {                                                                 // g = dout * act'(out) * s_row[o]
+          const int o = k0 + kq * 4;
+          v.x = __fmul_rn(act_bwd(v.x, va1[i].x, act), o + 0 < kend ? __ldg(s_row + o + 0) : 0.f);
+          v.y = __fmul_rn(act_bwd(v.y, va1[i].y, act), o + 1 < kend ? __ldg(s_row + o + 1) : 0.f);
+          v.z = __fmul_rn(act_bwd(v.z, va1[i].z, act), o + 2 < kend ? __ldg(s_row + o + 2) : 0.f);
+          v.w = __fmul_rn(act_bwd(v.w, va1[i].w, act), o + 3 < kend ? __ldg(s_row + o + 3) : 0.f);
         }
-      }
-      float4 hi, lo;
-      split4(v, hi, lo);
-      *reinterpret_cast<float4*>(a_hi + off) = hi;
-      *reinterpret_cast<float4*>(a_lo + off) = lo;
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      const int e = tid + i * kThreads;
-      int off;
-      if (MODE == 0) {
-        const int r = (e & 7) + ((e >> 6) << 3), kq = (e >> 3) & 7;
-        off = kq * (BN * 16) + r * 16;
-      } else {
-        const int k = (e & 7) + (e / (2 * BN)) * 8, c = (e >> 3) & (BN / 4 - 1);
-        off = (k >> 3) * (BN * 32) + c * 128 + (k & 7) * 16;
-      }
-      if (MODE == 2) {
         float4 hi, lo;
-        split4(rb[i], hi, lo);
-        *reinterpret_cast<float4*>(b_hi + off) = hi;
-        *reinterpret_cast<float4*>(b_lo + off) = lo;
-      } else {
-        *reinterpret_cast<float4*>(b_hi + off) = rb[i];                  // small integers: exact in TF32 as they are
+        split4(v, hi, lo);
+        const int off = kq * (BM * 16) + r * 16;
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = lo;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NAT; ++i) {
+        int m, k; t_slot(i, BM, m, k);
+        const float g = __fmul_rn(act_bwd(ta0[i], ta1[i], act), m0 + m < M ? __ldg(s_row + m0 + m) : 0.f);
+        if (do_db) db_part[i & 1] = __fadd_rn(db_part[i & 1], g);                        // column sums of g (m alternates with i)
+        const float hi = to_tf32(g), lo = to_tf32(__fsub_rn(g, hi));
+        const int off = (k >> 2) * (BM * 16) + m * 16 + (k & 3) * 4;
+        *reinterpret_cast<float*>(a_hi + off) = hi;
+        *reinterpret_cast<float*>(a_lo + off) = lo;
+      }
+    }
+    if constexpr (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < NBV; ++i) {
+        int r, kq; v_slot(tid + i * kThreads, r, kq);
+        *reinterpret_cast<float4*>(b_hi + kq * (BN * 16) + r * 16) = vb[i];              // small integers: exact in TF32
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NBT; ++i) {
+        int n, k; t_slot(i, BN, n, k);
+        const int off = (k >> 2) * (BN * 16) + n * 16 + (k & 3) * 4;
+        if (MODE == 1) {
+          *reinterpret_cast<float*>(b_hi + off) = tb[i];
+        } else {
+          const float hi = to_tf32(tb[i]);
+          *reinterpret_cast<float*>(b_hi + off) = hi;
+          *reinterpret_cast<float*>(b_lo + off) = to_tf32(__fsub_rn(tb[i], hi));
+        }
       }
     }
   };
 
   // ---- main loop: two stages, the commit of a stage's MMAs frees it ------------------------------------------------
+  // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
+  // accumulations (measured: 6e-5 of the largest output after K = 8192).  So an accumulator only ever collects
+  // kFlush K-chunks (K = 128: <= 48 MMAs); then every thread moves its part of the tile into fp32 REGISTER
+  // accumulators with round-to-nearest adds and the next group starts a fresh TMEM accumulator.
+  constexpr int kFlush = 4;
+  const int q = warp & 3, h = warp >> 2;                                 // TMEM lane quarter, column half
+  const int row = q * 32 + lane;                                         // tile row owned by this thread
+  constexpr int CW = BN / 2;                                             // columns per warp
+  float acc[CW];
+#pragma unroll
+  for (int i = 0; i < CW; ++i) acc[i] = 0.0f;
   if (nchunks) load_chunk(kbeg);
   for (int c = 0; c < nchunks; ++c) {
     const int st = c & 1;
     if (c >= 2) mbar_wait(&bar_stage[st], ((c >> 1) - 1) & 1);           // MMAs of chunk c-2 have read this stage
     store_chunk(st, kbeg + c * BK);
     fence_proxy_async();                                                 // generic-proxy stores -> visible to the MMA
-    __syncthreads();
+    __syncthreads();                                                     // (also: every thread's flush loads are done)
     if (c + 1 < nchunks) load_chunk(kbeg + (c + 1) * BK);                // in flight while the MMAs run
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
       const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
-      // K-major tile of R rows:  LBO (K-chunk stride) = R*16, SBO (8-row group stride) = 128; one K=8 step = 2 chunks
-      // MN-major tile of R cols: SBO (4-element MN-chunk stride) = 128, LBO (8-k group stride) = R*32
-      // either way the next K-step starts R*32 bytes further
-      constexpr uint32_t A_LBO = MODE == 2 ? BM * 32 : BM * 16, B_LBO = MODE == 0 ? BN * 16 : BN * 32;
+      // K-major tile of R rows: LBO (K-chunk stride) = R*16, SBO (8-row group stride) = 128; one K=8 step = 2 chunks,
+      // so the next K-step starts R*32 bytes further
+      constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16;
 #pragma unroll
       for (int j = 0; j < BK / 8; ++j) {
         const uint64_t dah = umma_desc(a_hi + j * BM * 32, A_LBO, 128), dal = umma_desc(a_lo + j * BM * 32, A_LBO, 128);
         const uint64_t dbh = umma_desc(b_hi + j * BN * 32, B_LBO, 128);
-        umma_tf32(tmem_d, dah, dbh, IDESC, (c | j) != 0);
+        umma_tf32(tmem_d, dah, dbh, IDESC, ((c % kFlush) | j) != 0);     // first MMA of a group overwrites
         umma_tf32(tmem_d, dal, dbh, IDESC, 1);
         if (MODE == 2) umma_tf32(tmem_d, dah, umma_desc(b_lo + j * BN * 32, B_LBO, 128), IDESC, 1);
       }
       umma_commit(&bar_stage[st]);
     }
+    if ((c + 1) % kFlush == 0 || c + 1 == nchunks) {                     // CTA-uniform
+      mbar_wait(&bar_stage[st], (c >> 1) & 1);                           // MMAs execute in order: the group is complete
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < CW; cb += 32) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * CW + cb), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[cb + i] = __fadd_rn(acc[cb + i], v[i]);
+      }
+      tc_fence_before();                                                 // ordered before the next group's first MMA by
+    }                                                                    // the __syncthreads of the next iteration
   }
-  if (nchunks) {
-    const int last = nchunks - 1;
-    mbar_wait(&bar_stage[last & 1], (last >> 1) & 1);                    // MMAs execute in order: all are complete
-  }
-  tc_fence_after();
 
   // ---- epilogue ------------------------------------------------------------------------------------------------------
-  const int q = warp & 3, h = warp >> 2;                                 // TMEM lane quarter, column half
-  const int row = q * 32 + lane;                                         // tile row owned by this thread
-  constexpr int CW = BN / 2;                                             // columns per warp
   auto epilogue = [&](int m, int n, float v) {
     if (m >= M || n >= N) return;
     if (MODE == 0) {
@@ -333,31 +370,24 @@ linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, c
       *dst = accumulate ? __fadd_rn(*dst, gq) : gq;
     }
   };
-  if (do_db) db_s[tid & 7][(tid >> 3) * 4 + 0] = db_part.x, db_s[tid & 7][(tid >> 3) * 4 + 1] = db_part.y,
-             db_s[tid & 7][(tid >> 3) * 4 + 2] = db_part.z, db_s[tid & 7][(tid >> 3) * 4 + 3] = db_part.w;
+  if (do_db) {                                                           // thread: rows warp*8+m8 (even i) and +64 (odd i), its k4
+    db_s[lane_k4][warp * 8 + lane_m8] = db_part[0];
+    db_s[lane_k4][(warp + 8) * 8 + lane_m8] = db_part[1];
+  }
   float* red = reinterpret_cast<float*>(smem);                           // [BM][RED_LD] partial tile (split-K only)
+  if (S == 1) {
 #pragma unroll
-  for (int cb = 0; cb < CW; cb += 32) {
-    float v[32];
-    if (nchunks) {
-      tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * CW + cb), v);
-    } else {
+    for (int i = 0; i < CW; ++i) epilogue(m0 + row, n0 + h * CW + i, acc[i]);
+  } else {
+    __syncthreads();                                                     // the stage buffers are free: all MMAs retired
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-    }
-    if (S == 1) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) epilogue(m0 + row, n0 + h * CW + cb + i, v[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) red[row * RED_LD + h * CW + cb + i] = v[i];
-    }
+    for (int i = 0; i < CW; ++i) red[row * RED_LD + h * CW + i] = acc[i];
   }
   __syncthreads();
   if (do_db && tid < BM) {
     float t = db_s[0][tid];
 #pragma unroll
-    for (int j = 1; j < 8; ++j) t = __fadd_rn(t, db_s[j][tid]);
+    for (int j = 1; j < 4; ++j) t = __fadd_rn(t, db_s[j][tid]);
     db_cta[tid] = t;
   }
   if (S == 1) {

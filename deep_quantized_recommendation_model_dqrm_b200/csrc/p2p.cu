@@ -19,8 +19,11 @@
 // order on one stream: a peer's flag for site B(s) is stored after its consumer of site A(s) has retired, and
 // this rank overwrites A only after it has seen B(s) from every peer.
 //
-// A rank that never shows up would spin forever; the wait gives up after ~2 s, sets DQRM_STATUS_P2P_TIMEOUT and
-// lets the step finish with garbage rather than hang the GPU.
+// A rank that never shows up would spin forever; the wait gives up after DQRM_P2P_TIMEOUT_S seconds (default 30;
+// 0 = wait for ever, like NCCL would) and sets DQRM_STATUS_P2P_TIMEOUT.  That bit is FATAL and sticky: the slots may
+// be stale or half written and the single-buffering argument above no longer holds, so the consumers that would
+// apply them to the weights (grad_merge_apply, dense_apply_gathered) turn into no-ops while it is set, and the host
+// raises at its next status poll (EmbeddingTableGroup.check_status / DenseArena.check_status never clear it).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,7 +32,14 @@ namespace dqrm {
 
 constexpr int kP2PThreads = 256;
 constexpr int kP2PMaxWorld = 16;
-constexpr long long kP2PTimeoutCycles = 4000000000ll;      // ~2 s at 1.97 GHz
+static long long p2p_timeout_cycles() {                    // env DQRM_P2P_TIMEOUT_S, default 30 s at ~1.97 GHz; 0 = never
+  static const long long v = [] {
+    const char* e = getenv("DQRM_P2P_TIMEOUT_S");
+    const double sec = e ? atof(e) : 30.0;
+    return sec <= 0.0 ? 0ll : (long long)(sec * 1.965e9);
+  }();
+  return v;
+}
 
 struct PeerPtrs { unsigned char* base[kP2PMaxWorld]; };
 
@@ -45,7 +55,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 // ctl = {counter, arrive, -, -} (local), flags = world x u32 (written by peers), data = world x slot_bytes
 __global__ void __launch_bounds__(kP2PThreads)
 p2p_allgather_kernel(const __grid_constant__ PeerPtrs peers, int world, int rank, size_t ctl_off, size_t flag_off,
-                     size_t data_off, size_t slot_bytes, int* __restrict__ status) {
+                     size_t data_off, size_t slot_bytes, long long timeout_cycles, int* __restrict__ status) {
   unsigned char* local = peers.base[rank];
   unsigned* ctl = reinterpret_cast<unsigned*>(local + ctl_off);
   const unsigned seq = ctl[0] + 1u;          // every CTA reads it before the last CTA (below) bumps it
@@ -75,7 +85,7 @@ p2p_allgather_kernel(const __grid_constant__ PeerPtrs peers, int world, int rank
     const unsigned* f = reinterpret_cast<const unsigned*>(local + flag_off) + threadIdx.x;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(f) - seq) < 0) {
-      if (clock64() - t0 > kP2PTimeoutCycles) { atomicOr(status, DQRM_STATUS_P2P_TIMEOUT); break; }
+      if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) { atomicOr(status, DQRM_STATUS_P2P_TIMEOUT); break; }
       __nanosleep(64);
     }
   }
@@ -109,7 +119,9 @@ __global__ void __launch_bounds__(256)
 dense_apply_gathered_kernel(float* __restrict__ param, const signed char* __restrict__ gathered_codes,
                             size_t code_stride, int world, const long long* __restrict__ chan_begin, int num_chan,
                             const float* __restrict__ scale_mean, float inv_world, float neg_lr,
-                            const float* __restrict__ comp_grad, float* __restrict__ ec_out) {
+                            const float* __restrict__ comp_grad, float* __restrict__ ec_out,
+                            const int* __restrict__ status) {
+  if (status && (*status & DQRM_STATUS_P2P_TIMEOUT)) return;             // an exchange timed out: never apply stale slots
   const int lane = threadIdx.x & 31;
   const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= num_chan) return;
@@ -218,7 +230,7 @@ extern "C" int dqrm_p2p_allgather(void* const* peer_base, int world, int rank, s
   if (grid > 64) grid = 64;
   if (grid < 1) grid = 1;
   p2p_allgather_kernel<<<(unsigned)grid, kP2PThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      pp, world, rank, site_off, site_off + flag_off, site_off + data_off, stride, status);
+      pp, world, rank, site_off, site_off + flag_off, site_off + data_off, stride, p2p_timeout_cycles(), status);
   DQRM_LAUNCH_CHECK("p2p_allgather_kernel");
   return 0;
 }
@@ -238,14 +250,15 @@ extern "C" int dqrm_dense_grad_quant_gathered(const float* grad, const int64_t* 
 
 extern "C" int dqrm_dense_apply_gathered(float* param, const int8_t* gathered_codes, size_t code_stride_bytes, int world,
                                          const int64_t* chan_begin, int num_chan, const float* scale_mean, float lr,
-                                         const float* comp_grad, float* error_comp_out, void* stream) {
+                                         const float* comp_grad, float* error_comp_out, const int32_t* status,
+                                         void* stream) {
   DQRM_REQUIRE(param && gathered_codes && chan_begin && scale_mean && num_chan >= 1 && world >= 1, -EINVAL,
                "dense_apply_gathered: bad argument");
   DQRM_REQUIRE(!error_comp_out || comp_grad, -EINVAL, "dense_apply_gathered: error compensation needs comp_grad");
   dense_apply_gathered_kernel<<<(num_chan + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, reinterpret_cast<const signed char*>(gathered_codes), code_stride_bytes, world,
       reinterpret_cast<const long long*>(chan_begin), num_chan, scale_mean, (float)(1.0 / world), -lr, comp_grad,
-      error_comp_out);
+      error_comp_out, status);
   DQRM_LAUNCH_CHECK("dense_apply_gathered_kernel");
   return 0;
 }

@@ -126,11 +126,15 @@ class DenseArena:
             self._int_views_bound = True
 
     def check_status(self):
-        """Device-side errors of the NVLink exchange (D2H sync)."""
+        """Device-side errors of the NVLink exchange (D2H sync).  A timeout is fatal and sticky: the bit is left set,
+        so the apply kernels stay no-ops and every later poll raises again."""
         s = int(self.status.item())
+        if s & _lib.STATUS_P2P_TIMEOUT:
+            raise _p2p.ExchangeTimeout("a peer never signalled an NVLink exchange site within DQRM_P2P_TIMEOUT_S; the "
+                                       "MLP update was NOT applied and replicas can no longer be trusted -- abort the job")
         if s:
             self.status.zero_()
-            raise RuntimeError(f"dqrm dense exchange status {s}: a peer never signalled an NVLink exchange site (timeout)")
+            raise RuntimeError(f"dqrm dense exchange status {s}")
 
     def join(self):
         """Make the current stream wait for the side-stream weight-gradient kernels of this step."""
@@ -273,7 +277,8 @@ class DenseArena:
         if quantized and getattr(self, "exchanged_gathered", False):
             rc = self.lib.dqrm_dense_apply_gathered(self.flat.data_ptr(), self._code_slots.data_ptr(),
                                                     self._code_slots.stride(0), world, self.chan_begin.data_ptr(),
-                                                    self.num_chan, self.scale_mean.data_ptr(), float(lr), comp, ec, st)
+                                                    self.num_chan, self.scale_mean.data_ptr(), float(lr), comp, ec,
+                                                    self.status.data_ptr(), st)
             _lib.check(rc, "dqrm_dense_apply_gathered")
             return
         _lib.check(self.lib.dqrm_dense_apply(self.flat.data_ptr(), self.codes.data_ptr(), self.chan_begin.data_ptr(),

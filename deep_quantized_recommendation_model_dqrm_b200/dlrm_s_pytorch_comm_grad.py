@@ -221,9 +221,9 @@ class DLRM_Net(nn.Module):
         return g
 
     fuse_mlp = True               # fused QuantLinear+activation kernels over the dense arena (a15)
-    fuse_mlp_max_batch = 2048     # above this the weight-gradient GEMM's K (= batch) outgrows the 8-CTA cluster
-                                  # split and plain cuBLAS SGEMM (library) is faster: measured at batch 8192,
-                                  # Terabyte shape, 6.0 ms fused vs 2.1 ms cuBLAS for the non-scan part of the step
+    fuse_mlp_max_batch = 1 << 30  # no limit: from 256 rows the fused layers contract on the tensor cores
+                                  # (csrc/mlp_tc.cu), so no batch size falls back to cuBLAS any more (round 1:
+                                  # batch > 2048 did, because the FFMA weight-gradient kernel outgrew its cluster split)
 
     def _fused_mlp_arena(self):
         """The dense arena if the fused MLP path applies (all layers quantised per channel on CUDA)."""
@@ -532,11 +532,20 @@ def train(args, rank=0, world_size=1, device=None, log=print):
             it += 1
             if args.print_freq > 0 and it % args.print_freq == 0:
                 losses.append(float(E))                                # the reference syncs here too (:1928)
+                _poll_status(dlrm)                                     # the host is synchronised anyway: poll device errors
                 log("Finished training it {}/{} of epoch {}, loss {:.6f}".format(it, len(train_ld), epoch, losses[-1]))
             if args.num_batches > 0 and it >= args.num_batches * (epoch + 1):
                 break
-    dlrm._ensure_group().check_status()
+    _poll_status(dlrm)
     return losses
+
+
+def _poll_status(dlrm):
+    """Device-side error words of the embedding group and the MLP arena (index range, capacity, exchange timeout)."""
+    dlrm._ensure_group().check_status()
+    arena = getattr(dlrm, "_dense_arena", None)
+    if arena is not None:
+        arena.check_status()
 
 
 def main(argv=None):

@@ -23,6 +23,10 @@ def backend() -> str:
     return b
 
 
+class ExchangeTimeout(RuntimeError):
+    """DQRM_STATUS_P2P_TIMEOUT was raised by an exchange kernel: fatal (see csrc/p2p.cu)."""
+
+
 class P2PUnavailable(RuntimeError):
     """Raised on EVERY rank when any rank could not allocate / export / map a peer arena."""
 

@@ -109,6 +109,9 @@ def grad_update_parallel_comm(model, number_of_gpus, emb_grad_quantized=True, nu
                     g.set_grad_bit(32)
                 g.exchange(world=world, rank=rank)
         arena = _dense_arena(model)
+        groups = _emb_groups(model)
+        if groups and arena.status is not groups[0].status:
+            arena.status = groups[0].status          # ONE status word: a timeout on any site stops every update
         arena.quantize_exchange(world=world, bits=8, quantized=mlp_layer_quantized)
 
 
@@ -145,11 +148,31 @@ def weight_syncc(dlrm, num_gpus):
             dist.all_reduce(table_arena)
             table_arena.mul_(1.0 / num_gpus)
             done |= {id(e.embedding_bag.weight) for e in dlrm.emb_l}
+        # the tables changed behind the scale tracker's back: block maxima, cached scales and a rescan in flight
+        # are stale (incremental / pipelined policies must stay bit-identical to a full rescan)
+        _invalidate_scale_state(dlrm)
         for _, param in dlrm.named_parameters():
             if id(param) in done:
                 continue
             dist.all_reduce(param.data)
             param.data.mul_(1.0 / num_gpus)
+        _invalidate_scale_state(dlrm)
+
+
+def _invalidate_scale_state(model):
+    """Call after mutating embedding tables outside merge_apply / sgd_apply (weight_syncc, checkpoint load)."""
+    groups = []
+    g = getattr(model, "emb_group", None)
+    if g is not None:
+        groups.append(g)
+    for e in getattr(model, "emb_l", []) or []:
+        for cand in (getattr(e, "_group", None), getattr(e, "_solo", None)):
+            if cand is not None and cand not in groups:
+                groups.append(cand)
+    for g in groups:
+        g.invalidate_tracker()
+        g.scale_valid = False
+        g.pipe_pending = False
 
 
 def quantized_gradients_update(model, arg, lr, num_gpus):

@@ -100,6 +100,10 @@ class EmbeddingTableGroup:
     def check_status(self):
         """Device-side data errors (D2H sync). Raises on out-of-range indices etc."""
         s = int(self.status.item())
+        if s & _lib.STATUS_P2P_TIMEOUT:
+            # fatal and sticky: the bit stays set, merge_apply stays a no-op, every later poll raises again
+            raise _p2p.ExchangeTimeout("a peer never signalled an NVLink exchange site within DQRM_P2P_TIMEOUT_S; the "
+                                       "update was NOT applied and replicas can no longer be trusted -- abort the job")
         if s:
             self.status.zero_()
             names = [n for b, n in ((1, "index out of range"), (2, "offsets not monotone"), (4, "capacity exceeded"),

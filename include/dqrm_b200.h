@@ -53,7 +53,9 @@ extern "C" {
 #define DQRM_STATUS_INDEX_RANGE 1    /* an index was <0 or >= rows (clamped) */
 #define DQRM_STATUS_OFFSET_ORDER 2   /* offsets not monotone / outside the index segment */
 #define DQRM_STATUS_CAPACITY 4       /* more unique rows than `capacity` */
-#define DQRM_STATUS_P2P_TIMEOUT 8    /* a peer never signalled an exchange site (dqrm_p2p_allgather gave up after ~2 s) */
+#define DQRM_STATUS_P2P_TIMEOUT 8    /* a peer never signalled an exchange site within DQRM_P2P_TIMEOUT_S (default 30 s, 0 = wait
+                                        for ever).  FATAL and sticky: while set, dqrm_grad_merge_apply and
+                                        dqrm_dense_apply_gathered are no-ops (stale slots are never applied) */
 
 DQRM_API int dqrm_abi_version(void);
 DQRM_API const char* dqrm_last_error(void);
@@ -402,7 +404,8 @@ DQRM_API int dqrm_dense_grad_quant_gathered(const float* grad, const int64_t* ch
  * 957,662-663); rank r's int8 codes at gathered_codes + r * code_stride_bytes. */
 DQRM_API int dqrm_dense_apply_gathered(float* param, const int8_t* gathered_codes, size_t code_stride_bytes, int world,
                                        const int64_t* chan_begin, int num_chan, const float* scale_mean, float lr,
-                                       const float* comp_grad, float* error_comp_out, void* stream);
+                                       const float* comp_grad, float* error_comp_out, const int32_t* status,
+                                       void* stream);
 /* (a1, row-sharded scan) absmax = max over ranks of the gathered per-shard maxima, then scale and 1/scale. */
 DQRM_API int dqrm_scale_from_absmax_gathered(int n_scales, const float* gathered_absmax, size_t stride_elems, int world,
                                              int bits, float* absmax, float* scale, float* inv_scale, void* stream);

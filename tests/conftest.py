@@ -7,6 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# the exchange watchdog (csrc/p2p.cu) defaults to 30 s; the missing-peer test should not take that long.  Read once,
+# when the library first launches an exchange kernel.
+os.environ.setdefault("DQRM_P2P_TIMEOUT_S", "2")
 
 
 def pytest_configure(config):

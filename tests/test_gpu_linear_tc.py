@@ -68,7 +68,7 @@ def test_tensor_core_linear_vs_fp64_and_ffma(shape):
     for name, a, b, w in zip(("out", "dx", "dW", "db"), tc, ff, want):
         e_tc = _close(a, w, 1e-5, f"tensor-core {name} {shape}")
         e_ff = _close(b, w, 1e-5, f"ffma {name} {shape}")
-        assert e_tc <= max(4 * e_ff, 2e-6), f"{name} {shape}: tensor-core error {e_tc:.2e} vs FFMA {e_ff:.2e}"
+        assert e_tc <= max(4 * e_ff, 4e-6), f"{name} {shape}: tensor-core error {e_tc:.2e} vs FFMA {e_ff:.2e}"
     # accumulate = 1 adds to what is there (AccumulateGrad semantics)
     base = (torch.randn_like(Wi), torch.randn_like(bi))
     acc = _run(_lib.LINEAR_TC, x, Wi, bi, s, dout, act, accumulate_into=base)

@@ -46,9 +46,31 @@ def test_allgather_gives_up_when_a_peer_is_missing():
     from deep_quantized_recommendation_model_dqrm_b200 import _lib
     arenas = _arenas({"x": 64, "y": 64}, 2)
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
-    arenas[0].allgather("x", status)                     # rank 1 never calls: ~2 s, then the timeout bit
+    arenas[0].allgather("x", status)                     # rank 1 never calls: DQRM_P2P_TIMEOUT_S, then the timeout bit
     torch.cuda.synchronize()
     assert int(status) == _lib.STATUS_P2P_TIMEOUT
+    # the bit is fatal and sticky: the consumers that would apply the (stale) slots are no-ops while it is set ...
+    lib = _lib.load()
+    param = torch.ones(8, device="cuda")
+    codes = torch.full((2, 16), 5, dtype=torch.int8, device="cuda")
+    chan = torch.tensor([0, 8], dtype=torch.int64, device="cuda")
+    mean = torch.ones(1, device="cuda")
+    _lib.check(lib.dqrm_dense_apply_gathered(param.data_ptr(), codes.data_ptr(), 16, 2, chan.data_ptr(), 1, mean.data_ptr(), 0.1,
+                                             None, None, status.data_ptr(), _lib.stream_ptr()), "apply_g")
+    torch.cuda.synchronize()
+    assert torch.equal(param, torch.ones(8, device="cuda"))
+    # ... and the host-side poll raises without clearing it
+    from deep_quantized_recommendation_model_dqrm_b200 import p2p, tables
+    g = tables.EmbeddingTableGroup([torch.zeros((4, 16), device="cuda")])
+    g.status = status
+    for _ in range(2):
+        with pytest.raises(p2p.ExchangeTimeout):
+            g.check_status()
+    status.zero_()
+    _lib.check(lib.dqrm_dense_apply_gathered(param.data_ptr(), codes.data_ptr(), 16, 2, chan.data_ptr(), 1, mean.data_ptr(), 0.1,
+                                             None, None, status.data_ptr(), _lib.stream_ptr()), "apply_g")
+    torch.cuda.synchronize()
+    assert torch.equal(param, torch.full((8,), 1.0 - 0.1 * 5.0, device="cuda"))
 
 
 @pytest.mark.parametrize("world", [1, 2, 8])
@@ -98,7 +120,7 @@ def test_gathered_dense_consumers_match_allreduce_form(world):
                                                       scales.stride(0), world, 8, codes_i[r].data_ptr(), mean_b.data_ptr(), st), "quant_g")
     pb = param0.clone()
     _lib.check(lib.dqrm_dense_apply_gathered(pb.data_ptr(), codes_i.data_ptr(), stride, world, chan_t.data_ptr(), C,
-                                             mean_b.data_ptr(), 0.1, None, None, st), "apply_g")
+                                             mean_b.data_ptr(), 0.1, None, None, None, st), "apply_g")
     torch.cuda.synchronize()
     assert torch.equal(mean_a, mean_b)
     assert torch.equal(codes_i[:, :total].float(), codes_f)

@@ -1,0 +1,10 @@
+#!/bin/bash
+O=gpurun_out/r2_5; mkdir -p $O
+timeout 300 python -m pytest tests/test_gpu_linear_tc.py -q 2>&1 | tail -15 > $O/tc.log
+timeout 120 python tools/tc_debug.py 2>&1 | grep -v "^ \[\|^\[\[\|got\|want" > $O/dbg_cl.log
+timeout 120 python tools/kernel_times.py --batch 2048 > $O/kt_2048_tc.txt 2>&1
+DQRM_MLP_PATH=ffma timeout 120 python tools/kernel_times.py --batch 2048 > $O/kt_2048_ffma.txt 2>&1
+DQRM_MLP_PATH=tc timeout 120 python tools/kernel_times.py --batch 128 > $O/kt_128_tc.txt 2>&1
+timeout 120 python tools/kernel_times.py --batch 512 > $O/kt_512_tc.txt 2>&1
+timeout 200 python tools/kernel_times.py --workload terabyte --batch 8192 --steps 4 > $O/kt_tb8192.txt 2>&1
+timeout 600 python bench.py --no-cpu-baseline --steps 20 > $O/bench.json 2> $O/bench.err
