@@ -11,7 +11,10 @@
 // dim/4-lane group then folds each row's duplicates left-to-right, reading
 // dy = (g*s)/s straight from dOut (the per-lookup [L,D] value matrix the
 // reference materialises never exists), and the CTA finishes with the table's
-// max|sum| -> 8-bit gradient scale.  Sort, unique, segmented sum and scale are
+// max|sum| -> 8-bit gradient scale.  Rows with more than DQRM_FOLD_BLOCK (64) duplicates -- the 3- and 4-row tables
+// of the Criteo sets collect thousands at batch 8192 -- are folded in blocks of 64 consecutive lookups by different
+// lane groups in parallel and the block sums are folded left to right: still one fixed summation order (the
+// oracle's coalesce_spec defines exactly this shape), but a row's latency is one block, not the whole chain.  Sort, unique, segmented sum and scale are
 // ONE launch for all tables (the reference: index_select, thrust sort,
 // coalesceValuesKernel, 4 reductions and a host sync per table).
 #include "common.cuh"
@@ -20,6 +23,8 @@ namespace dqrm {
 
 constexpr unsigned long long kPadKey = ~0ull;
 constexpr int kBwdPrefetchRows = 8;   // float4 row loads in flight per lane group (divided by COLS)
+constexpr int kFoldBlock = DQRM_FOLD_BLOCK;
+constexpr int kMaxLongRows = DQRM_BWD_CTA_MAX_LOOKUPS / (kFoldBlock + 1) + 4;   // rows with > kFoldBlock duplicates
 
 struct BwdArgs {
   long long rows[DQRM_MAX_TABLES];
@@ -37,11 +42,13 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
                       const float* __restrict__ dout, long long dts, long long dbs,
                       const float* __restrict__ fwd_scale, long long capacity,
                       int* __restrict__ uniq_rows, int* __restrict__ uniq_count, float* __restrict__ grad_sums,
-                      int grad_bits, float* __restrict__ grad_scale_local, int* __restrict__ status) {
+                      int grad_bits, float* __restrict__ grad_scale_local, int* __restrict__ status,
+                      float* __restrict__ partials, long long partial_items) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp_tot[32];
-  __shared__ int s_nvalid, s_unique;
+  __shared__ int s_nvalid, s_unique, s_nlong;
   __shared__ unsigned s_max;
+  __shared__ int s_long_j[kMaxLongRows], s_long_start[kMaxLongRows + 1];
 
   const int t = blockIdx.x;
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -136,16 +143,15 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
   __syncthreads();
   if (U > capacity) U = (int)capacity;
 
-  // 5. segmented left fold of dy over each unique row
+  // 5. segmented fold of dy over each unique row
   const bool quant = fwd_scale != nullptr;
   const float s = quant ? fwd_scale[t] : 1.0f;
   const int lane = tid % group;
   const float* dbase = dout + (long long)t * dts;
   unsigned m = 0u;
-  for (int j = tid / group; j < U; j += nthr / group) {
-    const int p0 = seg_start[j], p1 = seg_start[j + 1];
-    constexpr int kBwdPrefetch = kBwdPrefetchRows / COLS;
-    float4 acc[COLS];
+  constexpr int kBwdPrefetch = kBwdPrefetchRows / COLS;
+  // left fold of the lookups keys[p0..p1) into acc (p1 > p0)
+  auto fold = [&](int p0, int p1, float4 (&acc)[COLS]) {
     for (int p = p0; p < p1; p += kBwdPrefetch) {
       float4 v[kBwdPrefetch][COLS];
 #pragma unroll
@@ -176,6 +182,8 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
         }
       }
     }
+  };
+  auto emit = [&](int j, int p0, const float4 (&acc)[COLS]) {
     if (lane == 0) uniq_rows[(long long)t * capacity + j] = (int)(keys[p0] >> 32);
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
@@ -183,6 +191,71 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
       if (col >= dim4) continue;
       reinterpret_cast<float4*>(grad_sums + ((long long)t * capacity + j) * dim4 * 4)[col] = acc[c];
       m = max(m, abs_bits4(acc[c]));
+    }
+  };
+  if (tid == 0) s_nlong = 0;
+  __syncthreads();
+  // 5a. rows with <= kFoldBlock duplicates: one left fold each; longer rows are queued
+  for (int j = tid / group; j < U; j += nthr / group) {
+    const int p0 = seg_start[j], p1 = seg_start[j + 1];
+    if (p1 - p0 > kFoldBlock && partials != nullptr) {
+      if (lane == 0) s_long_j[atomicAdd(&s_nlong, 1)] = j;               // queue order is irrelevant to the results
+      continue;
+    }
+    float4 acc[COLS];
+    fold(p0, p1, acc);
+    emit(j, p0, acc);
+  }
+  __syncthreads();
+  const int nlong = s_nlong;
+  if (nlong > 0) {                                                       // CTA-uniform
+    // 5b. work items = blocks of kFoldBlock consecutive lookups of the queued rows
+    if (tid == 0) {
+      int it = 0;
+      for (int i = 0; i < nlong; ++i) {
+        s_long_start[i] = it;
+        const int j = s_long_j[i];
+        it += (seg_start[j + 1] - seg_start[j] + kFoldBlock - 1) / kFoldBlock;
+      }
+      s_long_start[nlong] = it;
+    }
+    __syncthreads();
+    const int items = s_long_start[nlong];
+    float* part_t = partials + (long long)t * partial_items * dim4 * 4;
+    for (int it = tid / group; it < items; it += nthr / group) {
+      int lo = 0, hi = nlong;                                            // last i with s_long_start[i] <= it
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_long_start[mid] <= it) lo = mid; else hi = mid; }
+      const int j = s_long_j[lo], blk = it - s_long_start[lo];
+      const int p0 = seg_start[j] + blk * kFoldBlock, p1 = min(seg_start[j + 1], p0 + kFoldBlock);
+      float4 acc[COLS];
+      fold(p0, p1, acc);
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        const int col = lane + c * group;
+        if (col < dim4) reinterpret_cast<float4*>(part_t + (long long)it * dim4 * 4)[col] = acc[c];
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // 5c. block sums of a row folded left to right
+    for (int i = tid / group; i < nlong; i += nthr / group) {
+      const int j = s_long_j[i], it0 = s_long_start[i], it1 = s_long_start[i + 1];
+      float4 acc[COLS];
+      for (int it = it0; it < it1; ++it) {
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+          const int col = lane + c * group;
+          if (col >= dim4) continue;
+          const float4 d = reinterpret_cast<const float4*>(part_t + (long long)it * dim4 * 4)[col];
+          if (it == it0) {
+            acc[c] = d;
+          } else {
+            acc[c].x = __fadd_rn(acc[c].x, d.x); acc[c].y = __fadd_rn(acc[c].y, d.y);
+            acc[c].z = __fadd_rn(acc[c].z, d.z); acc[c].w = __fadd_rn(acc[c].w, d.w);
+          }
+        }
+      }
+      emit(j, seg_start[j], acc);
     }
   }
 
@@ -261,12 +334,15 @@ sgd_rows_kernel(const __grid_constant__ TableSet ts, const __grid_constant__ Mom
 
 using namespace dqrm;
 
-namespace dqrm { size_t bwd_large_workspace_bytes(int64_t lookups); }   // embbag_bwd_large.cu
+namespace dqrm { size_t bwd_large_workspace_bytes(int64_t lookups, int dim); }   // embbag_bwd_large.cu
+
+// blocks of a table's long rows: every one has > DQRM_FOLD_BLOCK lookups, so at most L/64 full + L/65 partial blocks
+static long long partial_items_per_table(int64_t lookups) { return lookups / DQRM_FOLD_BLOCK + lookups / (DQRM_FOLD_BLOCK + 1) + 2; }
 
 extern "C" size_t dqrm_bwd_workspace_bytes(int num_tables, int64_t max_lookups_per_table, int dim) {
-  (void)num_tables; (void)dim;
-  if (max_lookups_per_table <= DQRM_BWD_CTA_MAX_LOOKUPS) return 0;
-  return dqrm::bwd_large_workspace_bytes(max_lookups_per_table);
+  if (max_lookups_per_table <= DQRM_BWD_CTA_MAX_LOOKUPS)          // block sums of the long rows, [T][items][dim] fp32
+    return (size_t)num_tables * (size_t)partial_items_per_table(max_lookups_per_table) * (size_t)dim * sizeof(float);
+  return dqrm::bwd_large_workspace_bytes(max_lookups_per_table, dim);
 }
 
 namespace dqrm {
@@ -320,6 +396,14 @@ extern "C" int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
     return 0;
   }
 
+  // long-row block sums live in the caller's workspace; without one (NULL / too small) every row is a plain left
+  // fold, which is the same arithmetic for rows of <= DQRM_FOLD_BLOCK lookups
+  const long long items = partial_items_per_table(capacity);
+  float* partials = (workspace && workspace_bytes >= (size_t)num_tables * items * dim * sizeof(float) &&
+                     (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0) ? static_cast<float*>(workspace) : nullptr;
+  DQRM_REQUIRE(partials || capacity <= DQRM_FOLD_BLOCK, -ENOMEM,
+               "embbag_bwd: workspace of %zu B needed for the blocked fold (dqrm_bwd_workspace_bytes), got %zu B",
+               (size_t)num_tables * items * dim * sizeof(float), workspace_bytes);
   int n = 2;
   while (n < lmax) n <<= 1;
   int threads = n / 2;
@@ -337,7 +421,8 @@ extern "C" int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
     kern<<<num_tables, threads, smem, st>>>(a, dim / 4, rl.group, reinterpret_cast<const long long*>(indices), \
                                             reinterpret_cast<const long long*>(offsets), bags, dout,           \
                                             dout_table_stride, dout_bag_stride, fwd_scale, capacity, uniq_rows, \
-                                            uniq_count, grad_sums, grad_bits, grad_scale_local, status);       \
+                                            uniq_count, grad_sums, grad_bits, grad_scale_local, status,        \
+                                            partials, items);                                                 \
   } while (0)
   if (rl.cols == 1) DQRM_BWD(1);
   else if (rl.cols == 2) DQRM_BWD(2);

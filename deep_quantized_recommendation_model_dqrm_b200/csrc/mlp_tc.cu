@@ -32,6 +32,12 @@ namespace tc {
 
 constexpr int BM = 128, BK = 32, kThreads = 256;
 constexpr int A_TILE_BYTES = BM * BK * 4;                       // 16 KiB per TF32 term
+// Pipeline shape: NS shared-memory stages, P K-chunks of global loads in flight per thread (register sets).  The
+// kernels are bound by L2 -> SM latency (one chunk per CTA in flight gave 2 us per chunk = 2.4 TB/s over the chip),
+// so P is what sets the throughput; the stage count only has to cover the MMAs that still read older stages.
+__host__ __device__ constexpr int stage_bytes(int mode, int bn) { return 2 * A_TILE_BYTES + (mode == 2 ? 2 : 1) * bn * BK * 4; }
+__host__ __device__ constexpr int num_stages(int mode, int bn) { return (196 * 1024) / stage_bytes(mode, bn) >= 4 ? 4 : 3; }
+__host__ __device__ constexpr int prefetch_depth(int mode, int bn) { return mode == 2 ? 2 : 3; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -105,17 +111,37 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
                    to_tf32(__fsub_rn(v.w, hi.w)));
 }
 
+// Global loads as PREDICATED instructions with the zero default written before them (inline asm, volatile): no
+// branch and no merge of two code paths follows a load, so nothing consumes a loaded register until the chunk is
+// stored -- the loads of P chunks really are in flight together -- and the compiler cannot sink them towards their
+// use.  (A C++ "in range ? load : 0" was compiled into branches with register moves right behind each load: every
+// load's latency was exposed, measured as 50 % long-scoreboard stalls.)
+__device__ __forceinline__ float ldg_pred(const float* p, bool ok) {
+  float v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+               : "=f"(v) : "l"(p), "r"((int)ok));
+  return v;
+}
+__device__ __forceinline__ float4 ldg4_pred(const float* p, bool ok) {
+  float4 v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+               "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "r"((int)ok));
+  return v;
+}
 // 4 consecutive elements of row `row` starting at column `col` (col % 4 == 0) of a row-major [nrows, ncols] matrix;
-// out-of-range elements read as 0.  `vec`: the matrix allows 16-byte loads (ld % 4 == 0, base 16-byte aligned).
-__device__ __forceinline__ float4 ld4(const float* __restrict__ p, int row, int col, int nrows, int ncols, int ld, bool vec) {
-  if (row >= nrows || col >= ncols) return make_float4(0.f, 0.f, 0.f, 0.f);
+// out-of-range elements read as 0.  VEC: the matrix allows 16-byte loads (ld % 4 == 0, base 16-byte aligned; then
+// ncols -- K or a K-slice end, multiples of 4 -- never cuts a vector).
+template <bool VEC>
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p, int row, int col, int nrows, int ncols, int ld) {
   const float* q = p + (long long)row * ld + col;
-  if (vec && col + 3 < ncols) return __ldg(reinterpret_cast<const float4*>(q));
-  float4 r = make_float4(__ldg(q), 0.f, 0.f, 0.f);
-  if (col + 1 < ncols) r.y = __ldg(q + 1);
-  if (col + 2 < ncols) r.z = __ldg(q + 2);
-  if (col + 3 < ncols) r.w = __ldg(q + 3);
-  return r;
+  const bool in = row < nrows;
+  if constexpr (VEC) {
+    return ldg4_pred(q, in && col < ncols);
+  } else {
+    return make_float4(ldg_pred(q, in && col < ncols), ldg_pred(q + 1, in && col + 1 < ncols),
+                       ldg_pred(q + 2, in && col + 2 < ncols), ldg_pred(q + 3, in && col + 3 < ncols));
+  }
 }
 
 __device__ __forceinline__ float act_bwd(float dout, float out, int act) {
@@ -133,22 +159,24 @@ __device__ __forceinline__ float act_fwd(float z, int act) {
 // MODE 1 (dx) : C[b, i]  = sum_o g[b,o] W[o,i],  g = dout * act'(out) * s    M = batch, N = in,  K = out
 // MODE 2 (dW) : C[o, i] (+)= (sum_b g[b,o] x[b,i]) / s[o] ; db[o] (+)= (sum_b g[b,o]) / s[o]
 //                                                                            M = out,   N = in,  K = batch
-template <int MODE, int BN, bool CL>
+template <int MODE, int BN, bool CL, bool VEC>
 __global__ void __launch_bounds__(kThreads)
 linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, const float* __restrict__ b_int,
                  const float* __restrict__ s_row, const float* __restrict__ dout, const float* __restrict__ out,
                  float* __restrict__ C, float* __restrict__ db, int batch, int out_f, int in_f, int act, int kc,
-                 int accumulate, int vec_x, int vec_w, int vec_g) {
+                 int accumulate) {
   namespace cg = cooperative_groups;
   constexpr int B_TILE_BYTES = BN * BK * 4;
   constexpr int B_TERMS = MODE == 2 ? 2 : 1;
-  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + B_TERMS * B_TILE_BYTES;
+  constexpr int STAGE_BYTES = stage_bytes(MODE, BN);
+  constexpr int NS = num_stages(MODE, BN), P = prefetch_depth(MODE, BN);
+  static_assert(STAGE_BYTES == 2 * A_TILE_BYTES + B_TERMS * B_TILE_BYTES, "stage layout");
   constexpr int RED_LD = BN + 1;                                       // padded partial-tile row (bank-conflict free)
-  static_assert(BM * RED_LD * 4 <= 2 * STAGE_BYTES, "partial tile must fit in the stage buffers");
+  static_assert(BM * RED_LD * 4 <= 2 * stage_bytes(MODE, BN), "partial tile must fit in the stage buffers");
   constexpr uint32_t IDESC = umma_idesc(BM, BN, 0, 0);                 // both operands K-major
 
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_stage[2];
+  __shared__ __align__(8) uint64_t bar_stage[NS];
   __shared__ uint32_t s_tmem;
   __shared__ float db_s[4][BM];
   __shared__ float db_cta[BM];
@@ -168,8 +196,7 @@ linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, c
   const int nchunks = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
 
   if (tid == 0) {
-    mbar_init(&bar_stage[0], 1);
-    mbar_init(&bar_stage[1], 1);
+    for (int i = 0; i < NS; ++i) mbar_init(&bar_stage[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -187,125 +214,185 @@ linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, c
   // 4 consecutive k.
   //  * operand already K-contiguous in global memory (x and W_int in fwd, g in dx): "V" staging -- 16-byte slots,
   //    8 consecutive lanes = 8 rows of one K-chunk: a warp reads 8 global rows x 64 B and writes 4 whole core
-  //    matrices with conflict-free 16-byte stores.
+  //    matrices with conflict-free 16-byte stores.  Slot i of a thread: row r0 + 32 i, K-chunk kq.
   //  * operand contiguous along M/N in global memory (W_int in dx, g and x in dW, whose K is the batch): "T" staging
   //    -- scalar slots, a warp covers 8 consecutive m x 4 consecutive k: 4 fully used 32-byte sectors per load
-  //    instruction, and the transposing 4-byte shared stores hit 32 distinct banks.
+  //    instruction, and the transposing 4-byte shared stores hit 32 distinct banks.  Slot i of a thread in a tile
+  //    of R rows: m = mt + 64 (i & 1), k = 4 (i >> 1) + k4 for R = 128;  m = mt, k = 4 i + k4 for R = 64.
+  // The kernels are instruction-issue bound in this staging code (first version: 2000 instructions per warp and
+  // chunk), so everything that does not depend on the chunk -- row / column predicates, base pointers, shared-memory
+  // offsets (compile-time multiples of the slot index), s_row factors -- is computed once, before the K loop.
   constexpr int NAV = BM * (BK / 4) / kThreads;                        // V slots per thread: A (4)
   constexpr int NBV = BN * (BK / 4) / kThreads;                        //                     B (BN / 32)
   constexpr int NAT = BM * BK / kThreads;                              // T slots per thread: A (16)
   constexpr int NBT = BN * BK / kThreads;                              //                     B (BN / 8)
-  float4 va0[MODE == 2 ? 1 : NAV], va1[MODE == 1 ? NAV : 1], vb[MODE == 0 ? NBV : 1];
-  float ta0[MODE == 2 ? NAT : 1], ta1[MODE == 2 ? NAT : 1], tb[MODE == 0 ? 1 : NBT];
+  struct RegSet {                                                      // one K-chunk of this thread's global loads
+    float4 va0[MODE == 2 ? 1 : NAV], va1[MODE == 1 ? NAV : 1], vb[MODE == 0 ? NBV : 1];
+    float ta0[MODE == 2 ? NAT : 1], ta1[MODE == 2 ? NAT : 1], tb[MODE == 0 ? 1 : NBT];
+  };
+  RegSet rs[P];
   const bool do_db = MODE == 2 && db != nullptr && blockIdx.x == 0;
   float db_part[2] = {0.f, 0.f};
   const int lane_m8 = lane & 7, lane_k4 = lane >> 3;
+  const int v_r0 = (tid & 7) + ((tid >> 6) << 3), v_kq = (tid >> 3) & 7;  // V: row of slot 0, K-chunk of every slot
+  const int t_m = warp * 8 + lane_m8;                                    // T: row (m or n) of slot 0
+  const int ldx = in_f, ldg = out_f;
+  // A operand
+  const float* gA0 = nullptr; const float* gA1 = nullptr;               // chunk-0 addresses of slot 0
+  unsigned a_ok = 0;                                                     // bit i: slot row i (V) / column half i (T) in range
+  float a_s[2] = {0.f, 0.f};                                             // MODE 2: s_row of this thread's two channels
+  if (MODE == 0) {
+    gA0 = x + (long long)(m0 + v_r0) * ldx + kbeg + v_kq * 4;
+#pragma unroll
+    for (int i = 0; i < NAV; ++i) a_ok |= (unsigned)(m0 + v_r0 + 32 * i < M) << i;
+  } else if (MODE == 1) {
+    gA0 = dout + (long long)(m0 + v_r0) * ldg + kbeg + v_kq * 4;
+    gA1 = out + (long long)(m0 + v_r0) * ldg + kbeg + v_kq * 4;
+#pragma unroll
+    for (int i = 0; i < NAV; ++i) a_ok |= (unsigned)(m0 + v_r0 + 32 * i < M) << i;
+  } else {
+    gA0 = dout + (long long)(kbeg + lane_k4) * ldg + m0 + t_m;
+    gA1 = out + (long long)(kbeg + lane_k4) * ldg + m0 + t_m;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const bool ok = m0 + t_m + 64 * hh < M;
+      a_ok |= (unsigned)ok << hh;
+      a_s[hh] = ok ? __ldg(s_row + m0 + t_m + 64 * hh) : 0.f;
+    }
+  }
+  // B operand
+  const float* gB0 = nullptr;
+  unsigned b_ok = 0;
+  if (MODE == 0) {
+    gB0 = W_int + (long long)(n0 + v_r0) * ldx + kbeg + v_kq * 4;
+#pragma unroll
+    for (int i = 0; i < NBV; ++i) b_ok |= (unsigned)(n0 + v_r0 + 32 * i < N) << i;
+  } else {
+    gB0 = (MODE == 1 ? W_int : x) + (long long)(kbeg + lane_k4) * ldx + n0 + t_m;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) b_ok |= (unsigned)(n0 + t_m + 64 * hh < N) << hh;
+  }
+  // T slot i of a tile of R rows: column half and K-quad
+  auto t_half = [](int i, int R) { return R == 128 ? (i & 1) : 0; };
+  auto t_quad = [](int i, int R) { return R == 128 ? (i >> 1) : i; };
 
-  // V slot e of an [R x BK] tile: row, K-chunk
-  auto v_slot = [](int e, int& r, int& kq) { r = (e & 7) + ((e >> 6) << 3); kq = (e >> 3) & 7; };
-  // T slot i of this thread in an [R x BK] tile: m (0..R), k (0..BK)
-  auto t_slot = [&](int i, int R, int& m, int& k) {
-    const int w = warp + (kThreads / 32) * i, groups = R / 8;
-    m = (w % groups) * 8 + lane_m8;
-    k = (w / groups) * 4 + lane_k4;
-  };
-  auto ld1 = [](const float* __restrict__ p, int row, int col, int nrows, int ncols, int ld) -> float {
-    return (row < nrows && col < ncols) ? __ldg(p + (long long)row * ld + col) : 0.0f;
-  };
-
-  auto load_chunk = [&](int k0) {
+  // loads of the chunk that starts `kofs` elements after kbeg (kofs + kbeg = k0)
+  auto load_chunk = [&](RegSet& R, int kofs) {
+    const int k0 = kbeg + kofs;
     if constexpr (MODE != 2) {
+      const bool kok = k0 + v_kq * 4 < kend;                            // (VEC: K and the slices are multiples of 4)
 #pragma unroll
       for (int i = 0; i < NAV; ++i) {
-        int r, kq; v_slot(tid + i * kThreads, r, kq);
-        if (MODE == 0) {
-          va0[i] = ld4(x, m0 + r, k0 + kq * 4, M, kend, in_f, vec_x);                    // x[m, k]
+        const bool ok = ((a_ok >> i) & 1u) && kok;
+        const long long o = (long long)(32 * i) * (MODE == 0 ? ldx : ldg) + kofs;
+        if constexpr (VEC) {
+          R.va0[i] = ldg4_pred(gA0 + o, ok);
+          if (MODE == 1) R.va1[i] = ldg4_pred(gA1 + o, ok);
         } else {
-          va0[i] = ld4(dout, m0 + r, k0 + kq * 4, M, kend, out_f, vec_g);                // g[b = m, o = k]
-          va1[i] = ld4(out, m0 + r, k0 + kq * 4, M, kend, out_f, vec_g);
+          const int kk = k0 + v_kq * 4;
+          R.va0[i] = make_float4(ldg_pred(gA0 + o, ok), ldg_pred(gA0 + o + 1, ok && kk + 1 < kend),
+                                 ldg_pred(gA0 + o + 2, ok && kk + 2 < kend), ldg_pred(gA0 + o + 3, ok && kk + 3 < kend));
+          if (MODE == 1)
+            R.va1[i] = make_float4(ldg_pred(gA1 + o, ok), ldg_pred(gA1 + o + 1, ok && kk + 1 < kend),
+                                   ldg_pred(gA1 + o + 2, ok && kk + 2 < kend), ldg_pred(gA1 + o + 3, ok && kk + 3 < kend));
         }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < NAT; ++i) {                                                    // g[b = k, o = m]
-        int m, k; t_slot(i, BM, m, k);
-        ta0[i] = ld1(dout, k0 + k, m0 + m, kend, M, out_f);
-        ta1[i] = ld1(out, k0 + k, m0 + m, kend, M, out_f);
+      for (int i = 0; i < NAT; ++i) {                                    // g[b = k, o = m]
+        const int hh = t_half(i, BM), qd = t_quad(i, BM);
+        const bool ok = ((a_ok >> hh) & 1u) && (k0 + qd * 4 + lane_k4 < kend);
+        const long long o = (long long)(kofs + qd * 4) * ldg + 64 * hh;
+        R.ta0[i] = ldg_pred(gA0 + o, ok);
+        R.ta1[i] = ldg_pred(gA1 + o, ok);
       }
     }
     if constexpr (MODE == 0) {
+      const bool kok = k0 + v_kq * 4 < kend;
 #pragma unroll
       for (int i = 0; i < NBV; ++i) {
-        int r, kq; v_slot(tid + i * kThreads, r, kq);
-        vb[i] = ld4(W_int, n0 + r, k0 + kq * 4, N, kend, in_f, vec_w);                   // W_int[n, k]
+        const bool ok = ((b_ok >> i) & 1u) && kok;
+        const long long o = (long long)(32 * i) * ldx + kofs;
+        if constexpr (VEC) {
+          R.vb[i] = ldg4_pred(gB0 + o, ok);
+        } else {
+          const int kk = k0 + v_kq * 4;
+          R.vb[i] = make_float4(ldg_pred(gB0 + o, ok), ldg_pred(gB0 + o + 1, ok && kk + 1 < kend),
+                                ldg_pred(gB0 + o + 2, ok && kk + 2 < kend), ldg_pred(gB0 + o + 3, ok && kk + 3 < kend));
+        }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < NBT; ++i) {                                                    // W_int[o = k, i = n] / x[b = k, i = n]
-        int n, k; t_slot(i, BN, n, k);
-        tb[i] = ld1(MODE == 1 ? W_int : x, k0 + k, n0 + n, kend, N, in_f);
+      for (int i = 0; i < NBT; ++i) {                                    // W_int[o = k, i = n] / x[b = k, i = n]
+        const int hh = t_half(i, BN), qd = t_quad(i, BN);
+        const bool ok = ((b_ok >> hh) & 1u) && (k0 + qd * 4 + lane_k4 < kend);
+        R.tb[i] = ldg_pred(gB0 + (long long)(kofs + qd * 4) * ldx + 64 * hh, ok);
       }
     }
   };
 
-  auto store_chunk = [&](int stage, int k0) {
+  // TF32 terms by masking (the tensor core reads the top 19 bits): hi = v & ~0x1fff, lo = (v - hi) & ~0x1fff.
+  // Truncation instead of cvt.rna: 3 full-rate instructions per element; the dropped remainder is < 2^-21 |v|.
+  auto tf32_hi = [](float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); };
+  const uint32_t sA_v = (uint32_t)(v_kq * (BM * 16) + v_r0 * 16);        // V slot 0 offsets inside a tile (slot i: + 512 i)
+  const uint32_t sB_v = (uint32_t)(v_kq * (BN * 16) + v_r0 * 16);
+  const uint32_t sT = (uint32_t)(t_m * 16 + lane_k4 * 4);                // T slot 0 (slot i: + quad * R*16 + half * 1024)
+
+  auto store_chunk = [&](const RegSet& R, int stage, int kofs) {
     unsigned char* a_hi = smem + stage * STAGE_BYTES;
     unsigned char* a_lo = a_hi + A_TILE_BYTES;
     unsigned char* b_hi = a_lo + A_TILE_BYTES;
     unsigned char* b_lo = b_hi + B_TILE_BYTES;
     if constexpr (MODE != 2) {
+      float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (MODE == 1) {                                                   // s_row[o] of this thread's K-chunk (0 beyond K)
+        const int o = kbeg + kofs + v_kq * 4;
+        sv.x = o + 0 < kend ? __ldg(s_row + o + 0) : 0.f; sv.y = o + 1 < kend ? __ldg(s_row + o + 1) : 0.f;
+        sv.z = o + 2 < kend ? __ldg(s_row + o + 2) : 0.f; sv.w = o + 3 < kend ? __ldg(s_row + o + 3) : 0.f;
+      }
 #pragma unroll
       for (int i = 0; i < NAV; ++i) {
-        int r, kq; v_slot(tid + i * kThreads, r, kq);
-        float4 v = va0[i];
-        if (MODE == 1) {                                                                 // g = dout * act'(out) * s_row[o]
-          const int o = k0 + kq * 4;
-          v.x = __fmul_rn(act_bwd(v.x, va1[i].x, act), o + 0 < kend ? __ldg(s_row + o + 0) : 0.f);
-          v.y = __fmul_rn(act_bwd(v.y, va1[i].y, act), o + 1 < kend ? __ldg(s_row + o + 1) : 0.f);
-          v.z = __fmul_rn(act_bwd(v.z, va1[i].z, act), o + 2 < kend ? __ldg(s_row + o + 2) : 0.f);
-          v.w = __fmul_rn(act_bwd(v.w, va1[i].w, act), o + 3 < kend ? __ldg(s_row + o + 3) : 0.f);
+        float4 v = R.va0[i];
+        if (MODE == 1) {                                                 // g = dout * act'(out) * s_row[o]
+          v.x = __fmul_rn(act_bwd(v.x, R.va1[i].x, act), sv.x); v.y = __fmul_rn(act_bwd(v.y, R.va1[i].y, act), sv.y);
+          v.z = __fmul_rn(act_bwd(v.z, R.va1[i].z, act), sv.z); v.w = __fmul_rn(act_bwd(v.w, R.va1[i].w, act), sv.w);
         }
-        float4 hi, lo;
-        split4(v, hi, lo);
-        const int off = kq * (BM * 16) + r * 16;
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        *reinterpret_cast<float4*>(a_lo + off) = lo;
+        const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        const float4 lo = make_float4(__fsub_rn(v.x, hi.x), __fsub_rn(v.y, hi.y), __fsub_rn(v.z, hi.z), __fsub_rn(v.w, hi.w));
+        *reinterpret_cast<float4*>(a_hi + sA_v + 512 * i) = hi;
+        *reinterpret_cast<float4*>(a_lo + sA_v + 512 * i) = lo;          // (the MMA ignores lo's low 13 bits itself)
       }
     } else {
 #pragma unroll
       for (int i = 0; i < NAT; ++i) {
-        int m, k; t_slot(i, BM, m, k);
-        const float g = __fmul_rn(act_bwd(ta0[i], ta1[i], act), m0 + m < M ? __ldg(s_row + m0 + m) : 0.f);
-        if (do_db) db_part[i & 1] = __fadd_rn(db_part[i & 1], g);                        // column sums of g (m alternates with i)
-        const float hi = to_tf32(g), lo = to_tf32(__fsub_rn(g, hi));
-        const int off = (k >> 2) * (BM * 16) + m * 16 + (k & 3) * 4;
-        *reinterpret_cast<float*>(a_hi + off) = hi;
-        *reinterpret_cast<float*>(a_lo + off) = lo;
+        const int hh = t_half(i, BM), qd = t_quad(i, BM);
+        const float g = __fmul_rn(act_bwd(R.ta0[i], R.ta1[i], act), a_s[hh]);
+        if (do_db) db_part[hh] = __fadd_rn(db_part[hh], g);              // column sums of g
+        const float hi = tf32_hi(g);
+        *reinterpret_cast<float*>(a_hi + sT + qd * (BM * 16) + hh * 1024) = hi;
+        *reinterpret_cast<float*>(a_lo + sT + qd * (BM * 16) + hh * 1024) = __fsub_rn(g, hi);
       }
     }
     if constexpr (MODE == 0) {
 #pragma unroll
-      for (int i = 0; i < NBV; ++i) {
-        int r, kq; v_slot(tid + i * kThreads, r, kq);
-        *reinterpret_cast<float4*>(b_hi + kq * (BN * 16) + r * 16) = vb[i];              // small integers: exact in TF32
-      }
+      for (int i = 0; i < NBV; ++i) *reinterpret_cast<float4*>(b_hi + sB_v + 512 * i) = R.vb[i];   // small integers: exact
     } else {
 #pragma unroll
       for (int i = 0; i < NBT; ++i) {
-        int n, k; t_slot(i, BN, n, k);
-        const int off = (k >> 2) * (BN * 16) + n * 16 + (k & 3) * 4;
+        const int hh = t_half(i, BN), qd = t_quad(i, BN);
+        const uint32_t off = sT + qd * (BN * 16) + hh * 1024;
         if (MODE == 1) {
-          *reinterpret_cast<float*>(b_hi + off) = tb[i];
+          *reinterpret_cast<float*>(b_hi + off) = R.tb[i];
         } else {
-          const float hi = to_tf32(tb[i]);
+          const float hi = tf32_hi(R.tb[i]);
           *reinterpret_cast<float*>(b_hi + off) = hi;
-          *reinterpret_cast<float*>(b_lo + off) = to_tf32(__fsub_rn(tb[i], hi));
+          *reinterpret_cast<float*>(b_lo + off) = __fsub_rn(R.tb[i], hi);
         }
       }
     }
   };
 
-  // ---- main loop: two stages, the commit of a stage's MMAs frees it ------------------------------------------------
+  // ---- main loop: NS stages, the commit of a stage's MMAs frees it ------------------------------------------------
   // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
   // accumulations (measured: 6e-5 of the largest output after K = 8192).  So an accumulator only ever collects
   // kFlush K-chunks (K = 128: <= 48 MMAs); then every thread moves its part of the tile into fp32 REGISTER
@@ -317,43 +404,51 @@ linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, c
   float acc[CW];
 #pragma unroll
   for (int i = 0; i < CW; ++i) acc[i] = 0.0f;
-  if (nchunks) load_chunk(kbeg);
-  for (int c = 0; c < nchunks; ++c) {
-    const int st = c & 1;
-    if (c >= 2) mbar_wait(&bar_stage[st], ((c >> 1) - 1) & 1);           // MMAs of chunk c-2 have read this stage
-    store_chunk(st, kbeg + c * BK);
-    fence_proxy_async();                                                 // generic-proxy stores -> visible to the MMA
-    __syncthreads();                                                     // (also: every thread's flush loads are done)
-    if (c + 1 < nchunks) load_chunk(kbeg + (c + 1) * BK);                // in flight while the MMAs run
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
-      const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
-      // K-major tile of R rows: LBO (K-chunk stride) = R*16, SBO (8-row group stride) = 128; one K=8 step = 2 chunks,
-      // so the next K-step starts R*32 bytes further
-      constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16;
 #pragma unroll
-      for (int j = 0; j < BK / 8; ++j) {
-        const uint64_t dah = umma_desc(a_hi + j * BM * 32, A_LBO, 128), dal = umma_desc(a_lo + j * BM * 32, A_LBO, 128);
-        const uint64_t dbh = umma_desc(b_hi + j * BN * 32, B_LBO, 128);
-        umma_tf32(tmem_d, dah, dbh, IDESC, ((c % kFlush) | j) != 0);     // first MMA of a group overwrites
-        umma_tf32(tmem_d, dal, dbh, IDESC, 1);
-        if (MODE == 2) umma_tf32(tmem_d, dah, umma_desc(b_lo + j * BN * 32, B_LBO, 128), IDESC, 1);
+  for (int p = 0; p < P; ++p)
+    if (p < nchunks) load_chunk(rs[p], p * BK);
+  for (int c0 = 0; c0 < nchunks; c0 += P) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {                                        // register set p <-> chunks c0 + p (static index)
+      const int c = c0 + p;
+      if (c < nchunks) {                                                 // CTA-uniform
+        const int st = c % NS, use = c / NS;
+        if (use > 0) mbar_wait(&bar_stage[st], (use - 1) & 1);           // MMAs of chunk c-NS have read this stage
+        store_chunk(rs[p], st, c * BK);
+        fence_proxy_async();                                             // generic-proxy stores -> visible to the MMA
+        __syncthreads();                                                 // (also: every thread's flush loads are done)
+        if (c + P < nchunks) load_chunk(rs[p], (c + P) * BK);     // P chunks in flight while the MMAs run
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+          // K-major tile of R rows: LBO (K-chunk stride) = R*16, SBO (8-row group stride) = 128; one K=8 step = 2
+          // chunks, so the next K-step starts R*32 bytes further
+          constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t dah = umma_desc(a_hi + j * BM * 32, A_LBO, 128), dal = umma_desc(a_lo + j * BM * 32, A_LBO, 128);
+            const uint64_t dbh = umma_desc(b_hi + j * BN * 32, B_LBO, 128);
+            umma_tf32(tmem_d, dah, dbh, IDESC, ((c % kFlush) | j) != 0); // first MMA of a group overwrites
+            umma_tf32(tmem_d, dal, dbh, IDESC, 1);
+            if (MODE == 2) umma_tf32(tmem_d, dah, umma_desc(b_lo + j * BN * 32, B_LBO, 128), IDESC, 1);
+          }
+          umma_commit(&bar_stage[st]);
+        }
+        if ((c + 1) % kFlush == 0 || c + 1 == nchunks) {                 // CTA-uniform
+          mbar_wait(&bar_stage[st], use & 1);                            // MMAs execute in order: the group is complete
+          tc_fence_after();
+#pragma unroll
+          for (int cb = 0; cb < CW; cb += 32) {
+            float v[32];
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * CW + cb), v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[cb + i] = __fadd_rn(acc[cb + i], v[i]);
+          }
+          tc_fence_before();                                             // ordered before the next group's first MMA by
+        }                                                                // the __syncthreads of the next iteration
       }
-      umma_commit(&bar_stage[st]);
     }
-    if ((c + 1) % kFlush == 0 || c + 1 == nchunks) {                     // CTA-uniform
-      mbar_wait(&bar_stage[st], (c >> 1) & 1);                           // MMAs execute in order: the group is complete
-      tc_fence_after();
-#pragma unroll
-      for (int cb = 0; cb < CW; cb += 32) {
-        float v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * CW + cb), v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[cb + i] = __fadd_rn(acc[cb + i], v[i]);
-      }
-      tc_fence_before();                                                 // ordered before the next group's first MMA by
-    }                                                                    // the __syncthreads of the next iteration
   }
 
   // ---- epilogue ------------------------------------------------------------------------------------------------------
@@ -370,14 +465,47 @@ linear_tc_kernel(const float* __restrict__ x, const float* __restrict__ W_int, c
       *dst = accumulate ? __fadd_rn(*dst, gq) : gq;
     }
   };
-  if (do_db) {                                                           // thread: rows warp*8+m8 (even i) and +64 (odd i), its k4
-    db_s[lane_k4][warp * 8 + lane_m8] = db_part[0];
-    db_s[lane_k4][(warp + 8) * 8 + lane_m8] = db_part[1];
+  if (do_db) {                                                           // thread: channels t_m and t_m + 64, its k4
+    db_s[lane_k4][t_m] = db_part[0];
+    db_s[lane_k4][t_m + 64] = db_part[1];
   }
   float* red = reinterpret_cast<float*>(smem);                           // [BM][RED_LD] partial tile (split-K only)
   if (S == 1) {
+    // thread = tile row: its CW consecutive outputs go out as 16-byte stores when the row pitch allows
+    const int ldc = MODE == 0 ? out_f : in_f, m = m0 + row;
+    const bool vec_c = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15u) == 0;
+    if (m < M) {
+      float sm = 0.0f;
+      if (MODE == 2) sm = __ldg(s_row + m);
 #pragma unroll
-    for (int i = 0; i < CW; ++i) epilogue(m0 + row, n0 + h * CW + i, acc[i]);
+      for (int i = 0; i < CW; i += 4) {
+        const int n = n0 + h * CW + i;
+        if (vec_c && n + 3 < N) {
+          float4 r;
+          if (MODE == 0) {
+            const float4 bb = b_int ? __ldg(reinterpret_cast<const float4*>(b_int + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 ss = __ldg(reinterpret_cast<const float4*>(s_row + n));
+            r.x = act_fwd(__fmul_rn(__fadd_rn(acc[i + 0], bb.x), ss.x), act);
+            r.y = act_fwd(__fmul_rn(__fadd_rn(acc[i + 1], bb.y), ss.y), act);
+            r.z = act_fwd(__fmul_rn(__fadd_rn(acc[i + 2], bb.z), ss.z), act);
+            r.w = act_fwd(__fmul_rn(__fadd_rn(acc[i + 3], bb.w), ss.w), act);
+          } else if (MODE == 1) {
+            r = make_float4(acc[i + 0], acc[i + 1], acc[i + 2], acc[i + 3]);
+          } else {
+            r = make_float4(__fdiv_rn(acc[i + 0], sm), __fdiv_rn(acc[i + 1], sm), __fdiv_rn(acc[i + 2], sm),
+                            __fdiv_rn(acc[i + 3], sm));
+            if (accumulate) {
+              const float4 o4 = *reinterpret_cast<const float4*>(C + (long long)m * ldc + n);
+              r.x = __fadd_rn(o4.x, r.x); r.y = __fadd_rn(o4.y, r.y); r.z = __fadd_rn(o4.z, r.z); r.w = __fadd_rn(o4.w, r.w);
+            }
+          }
+          *reinterpret_cast<float4*>(C + (long long)m * ldc + n) = r;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) epilogue(m, n + u, acc[i + u]);
+        }
+      }
+    }
   } else {
     __syncthreads();                                                     // the stage buffers are free: all MMAs retired
 #pragma unroll
@@ -442,11 +570,12 @@ static int launch(const float* x, const float* W_int, const float* b_int, const 
   const int S = pick_split(gx * gy, K);
   int kc = (K + S - 1) / S;
   kc = ((kc + BK - 1) / BK) * BK;
-  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + (MODE == 2 ? 2 : 1) * BN * BK * 4;
-  const size_t smem = 2 * (size_t)STAGE_BYTES;
-  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const int vec_x = (in_f % 4 == 0) && al16(x), vec_w = (in_f % 4 == 0) && al16(W_int);
-  const int vec_g = (out_f % 4 == 0) && (!dout || al16(dout)) && (!out || al16(out));
+  const size_t smem = (size_t)num_stages(MODE, BN) * stage_bytes(MODE, BN);
+  auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  // 16-byte loads need every operand the mode reads along its contiguous dimension to be aligned (the Criteo layer
+  // widths 13 / 367 / 415 are not multiples of 4: those layers take the scalar-load instantiation)
+  const bool vec = MODE == 0 ? (in_f % 4 == 0 && al16(x) && al16(W_int))
+                             : (MODE == 1 ? (out_f % 4 == 0 && al16(dout) && al16(out)) : false);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, gy, S);
   cfg.blockDim = dim3(kThreads);
@@ -458,19 +587,17 @@ static int launch(const float* x, const float* W_int, const float* b_int, const 
   cfg.attrs = attr;
   cfg.numAttrs = S > 1 ? 1 : 0;
   cudaError_t e;
-  if (S > 1) {
-    auto kern = linear_tc_kernel<MODE, BN, true>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      e = cudaLaunchKernelEx(&cfg, kern, x, W_int, b_int, s_row, dout, out, C, db, batch, out_f, in_f, act, kc, accumulate,
-                             vec_x, vec_w, vec_g);
-  } else {
-    auto kern = linear_tc_kernel<MODE, BN, false>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      e = cudaLaunchKernelEx(&cfg, kern, x, W_int, b_int, s_row, dout, out, C, db, batch, out_f, in_f, act, kc, accumulate,
-                             vec_x, vec_w, vec_g);
-  }
+#define DQRM_TC_LAUNCH(CLV, VECV)                                                                                     \
+  do {                                                                                                                \
+    auto kern = linear_tc_kernel<MODE, BN, CLV, VECV>;                                                                \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+    if (e == cudaSuccess)                                                                                             \
+      e = cudaLaunchKernelEx(&cfg, kern, x, W_int, b_int, s_row, dout, out, C, db, batch, out_f, in_f, act, kc,       \
+                             accumulate);                                                                             \
+  } while (0)
+  if (S > 1) { if (vec) DQRM_TC_LAUNCH(true, true); else DQRM_TC_LAUNCH(true, false); }
+  else       { if (vec) DQRM_TC_LAUNCH(false, true); else DQRM_TC_LAUNCH(false, false); }
+#undef DQRM_TC_LAUNCH
   if (e != cudaSuccess) { set_error("linear_tc_kernel<%d,%d>: %s", MODE, BN, cudaGetErrorString(e)); return -EIO; }
   return 0;
 }

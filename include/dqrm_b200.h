@@ -49,6 +49,8 @@ extern "C" {
 #define DQRM_ABI_VERSION 3
 #define DQRM_MAX_TABLES 64           /* tables per call (kernel-parameter descriptor size) */
 #define DQRM_BWD_CTA_MAX_LOOKUPS 16384 /* per-table lookups handled by the single-CTA sort path */
+#define DQRM_FOLD_BLOCK 64            /* duplicate-row gradients: left fold in lookup order; rows with more duplicates
+                                         are folded in blocks of this many lookups, then the block sums left to right */
 
 #define DQRM_STATUS_INDEX_RANGE 1    /* an index was <0 or >= rows (clamped) */
 #define DQRM_STATUS_OFFSET_ORDER 2   /* offsets not monotone / outside the index segment */
@@ -176,7 +178,10 @@ DQRM_API int dqrm_embbag_fwd_int4(int num_tables, const uint8_t* const* packed, 
  * mask), one value row per lookup (ATen sparse EmbeddingBag backward,
  * triggered at dlrm_s_pytorch_comm_grad.py:1938), then Tensor.coalesce
  * (sgd_quantized_gradients_parallel_comm.py:859): rows sorted ascending and
- * unique, duplicates summed as a left fold in original lookup order.
+ * unique, duplicates summed as a left fold in original lookup order (rows with more than DQRM_FOLD_BLOCK
+ * duplicates: blocks of DQRM_FOLD_BLOCK consecutive lookups folded left to right, then the block sums left to
+ * right -- one fixed order, defined by the oracle's coalesce_spec; the reference's own fold order is
+ * implementation-defined).
  * Optionally also the per-table gradient scale of quantize_emb_grad step 2
  * (sgd...parallel_comm.py:861): s_local = max(max|sums|,1e-8)/(2^(grad_bits-1)-1).
  *   dout       dev fp32, element (k,b,d) at dout[k*dout_table_stride + b*dout_bag_stride + d]
@@ -186,8 +191,9 @@ DQRM_API int dqrm_embbag_fwd_int4(int num_tables, const uint8_t* const* packed, 
  *   grad_sums  dev fp32 [num_tables, capacity, dim]
  *   grad_scale_local dev [num_tables] or NULL (then grad_bits is ignored)
  * One CTA per table sorts (row, bag) keys in shared memory; tables with more
- * than DQRM_BWD_CTA_MAX_LOOKUPS lookups take the multi-block radix-sort path,
- * which needs `workspace` (dqrm_bwd_workspace_bytes, 0 when not needed).
+ * than DQRM_BWD_CTA_MAX_LOOKUPS lookups take the multi-block radix-sort path.
+ * `workspace` (16-byte aligned, dqrm_bwd_workspace_bytes(num_tables, capacity, dim) bytes) holds the block sums
+ * of the long rows, or the sort buffers of the radix path.
  */
 DQRM_API size_t dqrm_bwd_workspace_bytes(int num_tables, int64_t max_lookups_per_table, int dim);
 DQRM_API int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,

@@ -248,7 +248,10 @@ def embbag_forward_int4_spec(packed: np.ndarray, idx, offsets, scale) -> np.ndar
 # (a7 step 1) coalesce                                              sgd:859
 # --------------------------------------------------------------------------
 
-def coalesce_spec(rows: np.ndarray, values: np.ndarray, order: np.ndarray | None = None):
+FOLD_BLOCK = 64      # include/dqrm_b200.h DQRM_FOLD_BLOCK
+
+
+def coalesce_spec(rows: np.ndarray, values: np.ndarray, order: np.ndarray | None = None, block: int | None = FOLD_BLOCK):
     """``Tensor.coalesce``: sorted-ascending unique rows; duplicates of a row
     summed as a left fold.  Returns (uniq_rows[U] int64, sums[U, D] fp32).
 
@@ -259,7 +262,14 @@ def coalesce_spec(rows: np.ndarray, values: np.ndarray, order: np.ndarray | None
     reference contract.  The spec fixes ORIGINAL-OCCURRENCE order (stable sort),
     which is what the CUDA kernel implements; ``order`` lets a test pass
     torch's permutation to reproduce the reference's bits.  Row sets are exact
-    either way; sums agree to fp32 rounding (north_star: 1e-5 relative)."""
+    either way; sums agree to fp32 rounding (north_star: 1e-5 relative).
+
+    ``block``: a row with more than ``block`` duplicates is folded in blocks of
+    ``block`` consecutive occurrences (each a left fold), then the block sums are
+    folded left to right -- the shape the CUDA kernel uses so that thousands of
+    duplicates of one row (3-row tables at batch 8192) do not form one serial
+    chain.  Identical to the plain left fold for rows of <= ``block`` duplicates;
+    ``block=None`` is the plain left fold for any length."""
     rows = np.asarray(rows, dtype=np.int64)
     values = np.asarray(values, dtype=F32)
     if order is None:
@@ -272,9 +282,19 @@ def coalesce_spec(rows: np.ndarray, values: np.ndarray, order: np.ndarray | None
     seg_len = seg_end - seg_start
     uniq = srows[seg_start]
     sums = values[order[seg_start]].copy()
-    for r in range(1, int(seg_len.max()) if seg_len.size else 0):
-        live = np.nonzero(seg_len > r)[0]
+    short = np.ones(seg_len.shape[0], dtype=bool) if block is None else seg_len <= block
+    for r in range(1, int(seg_len[short].max()) if short.any() else 0):
+        live = np.nonzero(short & (seg_len > r))[0]
         sums[live] = (sums[live] + values[order[seg_start[live] + r]]).astype(F32)
+    for j in np.nonzero(~short)[0]:                                 # long rows: blocked fold
+        occ = values[order[seg_start[j]:seg_end[j]]]
+        total = None
+        for b0 in range(0, occ.shape[0], block):
+            part = occ[b0].copy()
+            for v in occ[b0 + 1:b0 + block]:
+                part = (part + v).astype(F32)
+            total = part if total is None else (total + part).astype(F32)
+        sums[j] = total
     return uniq, sums
 
 

@@ -232,6 +232,46 @@ def test_large_table_path_matches_oracle():
     assert bits_equal(cpu(g.grad_scale_local[0]), O.grad_scale_spec(sums, 8))
 
 
+@pytest.mark.parametrize("case", ["zipf_onehot", "three_rows", "ragged_multihot", "dim64"])
+def test_large_path_one_kernel_sort(case):
+    """> DQRM_BWD_CTA_MAX_LOOKUPS lookups on one table: the persistent radix-sort kernel (csrc/embbag_bwd_large.cu)
+    against the oracle -- ascending unique rows, blocked left fold of heavy duplicates, gradient scale: bit-exact."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    rng = np.random.RandomState(11)
+    dim = 64 if case == "dim64" else 16
+    if case == "zipf_onehot":
+        rows, B = 300, 40000
+        idx = torch.from_numpy(np.minimum(rng.zipf(1.1, size=B) - 1, rows - 1).astype(np.int64))
+        off = torch.arange(B, dtype=torch.int64)
+    elif case == "three_rows":
+        rows, B = 3, 50000
+        idx = torch.from_numpy(rng.randint(0, 3, size=B).astype(np.int64))
+        off = torch.arange(B, dtype=torch.int64)
+    elif case == "ragged_multihot":
+        rows, B = 100000, 9000
+        idx, off = synthetic.random_bags(rows, B, 7, rng)
+        off[1000:1100] = off[1000]                       # a run of empty bags
+    else:
+        rows, B = 1 << 20, 20000
+        idx, off = synthetic.random_bags(rows, B, 2, rng, fixed=True)
+    assert idx.numel() > _lib.BWD_CTA_MAX_LOOKUPS
+    W = synthetic.table_weights_numpy(rows, dim, rng)
+    g = tables.EmbeddingTableGroup([torch.tensor(W, device="cuda")], embedding_bit=4)
+    i2, o2, ib, bags = tables.EmbeddingTableGroup.pack_inputs([idx], [off], "cuda")
+    g.scan_scales()
+    g.forward(i2, o2, ib, bags)
+    dout = rng.randn(1, bags, dim).astype(np.float32)
+    for rep in range(2):                                 # the second call reuses the workspace (barrier state reset)
+        g.backward(torch.tensor(dout, device="cuda"), world=1)
+        g.check_status()
+        sp = g.sparse_grad(0)
+        r0, v0 = O.embbag_backward_spec(dout[0], idx.numpy(), off.numpy(), O.table_scale_spec(W, 4))
+        urows, sums = O.coalesce_spec(r0, v0)
+        assert np.array_equal(cpu(sp._indices()[0]), urows)
+        assert bits_equal(cpu(sp._values()), sums)
+        assert bits_equal(cpu(g.grad_scale_local[0]), O.grad_scale_spec(sums, 8))
+
+
 def test_max_cta_lookups_boundary():
     """Exactly DQRM_BWD_CTA_MAX_LOOKUPS lookups (largest single-CTA sort) with heavy duplication."""
     _lib, synthetic, tables, qm, qu = _mods()

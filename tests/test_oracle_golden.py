@@ -40,7 +40,7 @@ def test_emb_backward_and_coalesce_spec(name):
     np.testing.assert_allclose(sums, g["co_vals"], rtol=RTOL, atol=1e-5 * np.abs(vals).max())
     # ... and bit-exact once the fold follows torch.sort's own permutation
     perm = torch.from_numpy(rows).sort(0)[1].numpy()
-    urows2, sums2 = O.coalesce_spec(rows, vals, order=perm)
+    urows2, sums2 = O.coalesce_spec(rows, vals, order=perm, block=None)
     assert np.array_equal(urows2, g["co_rows"]) and np.array_equal(sums2, g["co_vals"])
 
 
@@ -50,11 +50,20 @@ def test_coalesce_fold_order_heavy_duplicates():
     vals = rng.randn(20000, 16).astype(np.float32)
     sp = torch.sparse_coo_tensor(torch.from_numpy(rows)[None], torch.from_numpy(vals), size=(37, 16)).coalesce()
     perm = torch.from_numpy(rows).sort(0)[1].numpy()
-    urows, sums = O.coalesce_spec(rows, vals, order=perm)
+    urows, sums = O.coalesce_spec(rows, vals, order=perm, block=None)   # torch: one left fold in its sort's order
     assert np.array_equal(urows, sp.indices()[0].numpy())
     assert np.array_equal(sums, sp.values().numpy())
-    _, sums_stable = O.coalesce_spec(rows, vals)
+    _, sums_stable = O.coalesce_spec(rows, vals, block=None)
     np.testing.assert_allclose(sums_stable, sums, rtol=1e-4, atol=1e-3)
+    # the spec's blocked fold (rows with > FOLD_BLOCK duplicates; here ~540 each): same rows, fp32-rounding agreement,
+    # and identical to the plain fold when no row exceeds the block
+    urows_b, sums_b = O.coalesce_spec(rows, vals)
+    assert np.array_equal(urows_b, urows)
+    np.testing.assert_allclose(sums_b, sums, rtol=1e-4, atol=1e-3)
+    few = rng.randint(0, 5000, size=300)
+    a = O.coalesce_spec(few, vals[:300])
+    b = O.coalesce_spec(few, vals[:300], block=None)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
 @pytest.mark.parametrize("name", ["linear_13_64", "linear_367_32", "linear_64_1"])

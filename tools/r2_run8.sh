@@ -1,0 +1,6 @@
+#!/bin/bash
+O=gpurun_out/r2_8; mkdir -p $O
+timeout 300 python -m pytest tests/test_gpu_linear_tc.py -q 2>&1 | tail -15 > $O/tc.log
+timeout 300 python tools/tc_bench.py > $O/tc_bench.txt 2>&1
+timeout 200 python tools/kernel_times.py --workload terabyte --batch 8192 --steps 4 > $O/kt_tb8192.txt 2>&1
+timeout 120 python tools/kernel_times.py --batch 2048 > $O/kt_2048.txt 2>&1
