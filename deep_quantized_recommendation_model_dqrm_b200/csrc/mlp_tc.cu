@@ -36,7 +36,7 @@ constexpr int A_TILE_BYTES = BM * BK * 4;                       // 16 KiB per TF
 // kernels are bound by L2 -> SM latency (one chunk per CTA in flight gave 2 us per chunk = 2.4 TB/s over the chip),
 // so P is what sets the throughput; the stage count only has to cover the MMAs that still read older stages.
 __host__ __device__ constexpr int stage_bytes(int mode, int bn) { return 2 * A_TILE_BYTES + (mode == 2 ? 2 : 1) * bn * BK * 4; }
-__host__ __device__ constexpr int num_stages(int mode, int bn) { return (196 * 1024) / stage_bytes(mode, bn) >= 4 ? 4 : 3; }
+__host__ __device__ constexpr int num_stages(int mode, int bn) { return 3; }
 __host__ __device__ constexpr int prefetch_depth(int mode, int bn) { return mode == 2 ? 2 : 3; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,17 +115,20 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 // branch and no merge of two code paths follows a load, so nothing consumes a loaded register until the chunk is
 // stored -- the loads of P chunks really are in flight together -- and the compiler cannot sink them towards their
 // use.  (A C++ "in range ? load : 0" was compiled into branches with register moves right behind each load: every
-// load's latency was exposed, measured as 50 % long-scoreboard stalls.)
+// load's latency was exposed, measured as 50 % long-scoreboard stalls.)  L1::no_allocate: with ~150-190 KB of the
+// SM's 256 KB configured as shared memory the L1 is a few tens of KB, and allocating loads can only be in flight
+// for as many lines as it has (measured: 1.45 TB/s over the chip, 12 long-scoreboard stalls per issue); every
+// sector is consumed by the one instruction that loads it, so there is nothing to cache.
 __device__ __forceinline__ float ldg_pred(const float* p, bool ok) {
   float v;
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.L1::no_allocate.f32 %0, [%1];\n\t}"
                : "=f"(v) : "l"(p), "r"((int)ok));
   return v;
 }
 __device__ __forceinline__ float4 ldg4_pred(const float* p, bool ok) {
   float4 v;
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
-               "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+               "@q ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "r"((int)ok));
   return v;
 }

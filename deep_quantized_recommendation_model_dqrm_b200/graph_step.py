@@ -55,6 +55,9 @@ class GraphedTrainStep:
         self.group = dlrm._ensure_group()
         self.group.dp_world, self.group.dp_rank = world_size, rank
         self.pipelined = self.group.scale_policy == "pipelined"
+        # row-sharded scan: the absmax exchange + scale are issued right before the embedding forward (inside the
+        # graph, after the bottom MLP) instead of right behind the scan -- its round trip is off the critical path
+        self.group.defer_scan_reduce = world_size > 1 and self.group.scale_policy == "full"
         # multi-rank: launch the embedding exchange from inside the backward (side stream), overlapping the two
         # all-gathers + pack with the bottom-MLP backward; grad_update_parallel_comm then only joins
         self.group.eager_exchange = (world_size > 1 and self.group.grad_bit == grad_bits and not self.pipelined and

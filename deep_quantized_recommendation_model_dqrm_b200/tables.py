@@ -86,6 +86,8 @@ class EmbeddingTableGroup:
         self.dp_world, self.dp_rank = 1, 0
         self.fixed_capacity = None  # rows per table in the exchange slots (default: this step's largest table)
         self.keep_debug = False   # also emit updated_rows / qbar in merge (parity tests, .grad materialisation)
+        self.defer_scan_reduce = False     # sharded scan: leave the MAX over ranks to finish_scan() (called by forward)
+        self._scan_reduce_pending = None
 
     # ---- helpers --------------------------------------------------------
     def _wptrs(self):
@@ -277,11 +279,23 @@ class EmbeddingTableGroup:
             events[1].record()
         _lib.check(rc, "dqrm_table_absmax_scale")
         if sharded:
-            self._allreduce_absmax_to_scale(process_group)
+            if self.defer_scan_reduce:
+                # the cross-rank MAX + scale only has to be done before the embedding forward: the bottom MLP runs in
+                # between (dlrm_s_pytorch_comm_grad.py:855-857), which hides this exchange's round trip and rank skew
+                self._scan_reduce_pending = (process_group,)
+            else:
+                self._allreduce_absmax_to_scale(process_group)
         self.scale_valid = True
+
+    def finish_scan(self):
+        """Complete a row-sharded scan whose cross-rank reduction was deferred (defer_scan_reduce)."""
+        if self._scan_reduce_pending is not None:
+            (pg,), self._scan_reduce_pending = self._scan_reduce_pending, None
+            self._allreduce_absmax_to_scale(pg)
 
     # ---- (a3) -----------------------------------------------------------
     def forward(self, indices, offsets, idx_begin, bags, full_precision=False, want_codes=True, out=None):
+        self.finish_scan()
         lib, st = self.lib, _lib.stream_ptr()
         dev = self.device
         if out is None:
