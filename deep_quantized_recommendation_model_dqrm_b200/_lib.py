@@ -37,6 +37,9 @@ SIGNATURES = {
     "dqrm_embbag_fwd": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _p, _p, _i32, _p, _i64, _i64, _p, _p, _p]),
     "dqrm_table_pack_int4": (_i32, [_i32, _p, _p, _i32, _p, _p, _p]),
     "dqrm_embbag_fwd_int4": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _p, _p, _i64, _i64, _p, _p]),
+    "dqrm_shadow_refresh": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "dqrm_shadow_update_rows": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i32, _i64, _i32, _p, _p, _p]),
+    "dqrm_embbag_fwd_shadow": (_i32, [_i32, _p, _p, _p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _i64, _i64, _p, _p, _p]),
     "dqrm_bwd_workspace_bytes": (_sz, [_i32, _i64, _i32]),
     "dqrm_embbag_bwd": (_i32, [_i32, _p, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p, _i32, _p,
                                _p, _p, _sz, _p]),
@@ -83,6 +86,7 @@ LAUNCHING = ("dqrm_table_absmax_scale", "dqrm_scale_from_absmax", "dqrm_embbag_f
              "dqrm_mlp_fakequant_all", "dqrm_linear_fwd", "dqrm_linear_bwd",
              "dqrm_blockmax_build", "dqrm_blockmax_update", "dqrm_blockmax_scan", "dqrm_blockmax_update_shard",
              "dqrm_blockmax_reduce", "dqrm_table_pack_int4", "dqrm_embbag_fwd_int4",
+             "dqrm_shadow_refresh", "dqrm_shadow_update_rows", "dqrm_embbag_fwd_shadow",
              "dqrm_dense_grad_scale", "dqrm_dense_grad_quant", "dqrm_dense_apply",
              "dqrm_bce_loss_grad", "dqrm_p2p_allgather", "dqrm_dense_grad_quant_gathered", "dqrm_dense_apply_gathered",
              "dqrm_scale_from_absmax_gathered")

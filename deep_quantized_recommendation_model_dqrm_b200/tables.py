@@ -86,6 +86,9 @@ class EmbeddingTableGroup:
         self.dp_world, self.dp_rank = 1, 0
         self.fixed_capacity = None  # rows per table in the exchange slots (default: this step's largest table)
         self.keep_debug = False   # also emit updated_rows / qbar in merge (parity tests, .grad materialisation)
+        # packed-INT4 shadow rows for the training forward (csrc/shadow.cu): None = off (fp32 rows only)
+        self.shadow = None
+        self.shadow_scale = self._shadow_flags = self._shadow_ptrs = self._shadow_buf = None
         self.defer_scan_reduce = False     # sharded scan: leave the MAX over ranks to finish_scan() (called by forward)
         self._scan_reduce_pending = None
 
@@ -151,6 +154,7 @@ class EmbeddingTableGroup:
     def invalidate_tracker(self):
         """Call after mutating a table outside merge_apply / sgd_apply (e.g. loading a checkpoint)."""
         self._bm_valid = False
+        self.invalidate_shadow()
 
     def _tracker_scan(self, events=None):
         lib, st = self.lib, _lib.stream_ptr()
@@ -293,6 +297,48 @@ class EmbeddingTableGroup:
             (pg,), self._scan_reduce_pending = self._scan_reduce_pending, None
             self._allreduce_absmax_to_scale(pg)
 
+    # ---- packed-INT4 shadow rows in the training forward (north-star kernel 2) ------------------------------
+    def enable_shadow(self):
+        """Keep a bit-packed INT4 copy of every table (rows_k x D/2 bytes, 1/8 of the fp32 arena) that the forward
+        reads instead of the fp32 rows whenever that gives the same bits: bags of one index (all Criteo lookups)
+        of a table whose scale is bit-identical to the one its shadow was encoded with.  fp32 rows stay the master
+        copy; stale tables are re-encoded after the scan, updated rows after the update (csrc/shadow.cu)."""
+        if self.embedding_bit != 4 or self.dim % 16:
+            raise ValueError("the INT4 shadow needs embedding_bit == 4 and dim % 16 == 0")
+        half, offs, off = self.dim // 2, [], 0
+        for n in self.rows:
+            offs.append(off)
+            off += (n * half + 15) // 16 * 16                     # every table 16-byte aligned (128-bit staging loads)
+        self._shadow_buf = torch.zeros(off + 16, dtype=torch.uint8, device=self.device)
+        self.shadow = [self._shadow_buf[o:o + n * half].view(n, half) for o, n in zip(offs, self.rows)]
+        self._shadow_ptrs = _lib.ptr_array(self.shadow)
+        self.shadow_scale = torch.zeros(self.T, dtype=torch.float32, device=self.device)   # 0 != any scale: all stale
+        self._shadow_flags = torch.zeros(self.T, dtype=torch.int32, device=self.device)
+
+    def invalidate_shadow(self):
+        """Tables were changed outside merge_apply / sgd_apply: every shadow is stale."""
+        if self.shadow is not None:
+            self.shadow_scale.zero_()
+
+    def _shadow_refresh(self):
+        rc = self.lib.dqrm_shadow_refresh(self.T, self._wptrs(), self._rows_arr, self.dim, self.scale.data_ptr(),
+                                          self.inv_scale.data_ptr(), self._shadow_ptrs, self.shadow_scale.data_ptr(),
+                                          self._shadow_flags.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "dqrm_shadow_refresh")
+
+    def _shadow_update_rows(self, from_slots):
+        if self.shadow is None:
+            return
+        if from_slots:
+            rc = self.lib.dqrm_shadow_update_rows(self.T, self._wptrs(), self._rows_arr, self.dim, self.inv_scale.data_ptr(),
+                                                  self._shadow_ptrs, self.gathered.data_ptr(), self.world, self.capacity,
+                                                  self.grad_bit, None, None, _lib.stream_ptr())
+        else:
+            rc = self.lib.dqrm_shadow_update_rows(self.T, self._wptrs(), self._rows_arr, self.dim, self.inv_scale.data_ptr(),
+                                                  self._shadow_ptrs, None, 0, self.capacity, self.grad_bit,
+                                                  self.uniq_rows.data_ptr(), self.uniq_count.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "dqrm_shadow_update_rows")
+
     # ---- (a3) -----------------------------------------------------------
     def forward(self, indices, offsets, idx_begin, bags, full_precision=False, want_codes=True, out=None):
         self.finish_scan()
@@ -305,6 +351,16 @@ class EmbeddingTableGroup:
             codes = torch.empty((self.T, bags, self.dim), dtype=torch.int8 if self.embedding_bit <= 8 else torch.int16,
                                 device=dev)
         ib = _lib.i64_array(idx_begin)
+        if self.shadow is not None and not full_precision:
+            self._shadow_refresh()                   # re-encode the tables whose scale changed since their shadow was made
+            rc = lib.dqrm_embbag_fwd_shadow(self.T, self._wptrs(), self._shadow_ptrs, self._rows_arr, self.dim,
+                                            indices.data_ptr(), offsets.data_ptr(), ib, bags, self.scale.data_ptr(),
+                                            self.inv_scale.data_ptr(), self.shadow_scale.data_ptr(), out.data_ptr(),
+                                            out.stride(0), out.stride(1), _lib.ptr(codes), self.status.data_ptr(), st)
+            _lib.check(rc, "dqrm_embbag_fwd_shadow")
+            self.last = (indices, offsets, idx_begin, ib, bags, full_precision)
+            self.codes = codes
+            return out
         rc = lib.dqrm_embbag_fwd(self.T, self._wptrs(), self._rows_arr, self.dim, indices.data_ptr(),
                                  offsets.data_ptr(), ib, bags,
                                  None if full_precision else self.scale.data_ptr(),
@@ -574,6 +630,7 @@ class EmbeddingTableGroup:
                                        _lib.ptr(self.updated_count) if dbg else None,
                                        _lib.ptr(self.qbar) if dbg else None, self.status.data_ptr(), st)
         _lib.check(rc, "dqrm_grad_merge_apply")
+        self._shadow_update_rows(from_slots=True)
         self._tracker_update(from_slots=True)
 
     def sgd_apply(self, lr, inv_world=1.0, momentum=None, eps=1e-10):
@@ -584,6 +641,7 @@ class EmbeddingTableGroup:
                                     self.uniq_count.data_ptr(), self.grad_sums.data_ptr(), self.capacity, float(lr),
                                     float(inv_world), mom, float(eps), st)
         _lib.check(rc, "dqrm_sgd_rows")
+        self._shadow_update_rows(from_slots=False)
         self._tracker_update(from_slots=False)
 
     # ---- views for tests / API compatibility (these synchronise) ----------

@@ -297,6 +297,35 @@ DQRM_API int dqrm_interact_bwd(const float* x, const float* ly, int64_t ly_table
                       float* dx, float* dly, int64_t dly_table_stride, int64_t dly_bag_stride,
                       const float* ste_scale, void* stream);
 
+/* --------------------------------------------------- (a3, north-star kernel 2) --
+ * Packed-INT4 shadow rows in the TRAINING forward.  The reference quantises the POOLED vector
+ * (quant_modules_not_quantize_grad.py:367,378,393); for a bag of one index Q(pooled) == Q(row), so the forward may read
+ * the row's 4-bit codes (D/2 bytes) instead of its fp32 values (4D bytes) and return the same bits, as long as the
+ * codes were made with the scale this forward uses.  shadow[k] is dev uint8 [rows_k, dim/2] (element d in byte d/2,
+ * low nibble for even d; 16-byte aligned), shadow_scale dev fp32 [num_tables] = the scale each shadow was encoded
+ * with (0 = never).  fp32 rows stay authoritative.
+ *   dqrm_shadow_refresh     : tables whose scale differs BIT-WISE from shadow_scale are re-encoded from the fp32 rows
+ *                             (flags: dev int32 [num_tables] scratch), shadow_scale <- scale.  Call after the scan.
+ *   dqrm_shadow_update_rows : re-encode the rows a step updated (same row lists as dqrm_blockmax_update: the gathered
+ *                             exchange slots, or uniq_rows/uniq_count) with the step's inv_scale.  Call after the update.
+ *   dqrm_embbag_fwd_shadow  : dqrm_embbag_fwd (4-bit, int8 codes) that takes a bag's codes from the shadow when the bag
+ *                             has one index and shadow_scale[k] == scale[k] bit-wise, and pools the fp32 rows otherwise
+ *                             -- bit-identical outputs and codes either way.  Packed tables of <= 32 KiB are staged in
+ *                             shared memory with 128-bit loads first.
+ */
+DQRM_API int dqrm_shadow_refresh(int num_tables, const float* const* weight, const int64_t* rows, int dim,
+                                 const float* scale, const float* inv_scale, uint8_t* const* shadow,
+                                 float* shadow_scale, int32_t* flags, void* stream);
+DQRM_API int dqrm_shadow_update_rows(int num_tables, const float* const* weight, const int64_t* rows, int dim,
+                                     const float* inv_scale, uint8_t* const* shadow, const void* gathered, int world,
+                                     int64_t capacity, int bits, const int32_t* uniq_rows, const int32_t* uniq_count,
+                                     void* stream);
+DQRM_API int dqrm_embbag_fwd_shadow(int num_tables, const float* const* weight, uint8_t* const* shadow,
+                                    const int64_t* rows, int dim, const int64_t* indices, const int64_t* offsets,
+                                    const int64_t* idx_begin, int64_t bags, const float* scale, const float* inv_scale,
+                                    const float* shadow_scale, float* out, int64_t out_table_stride,
+                                    int64_t out_bag_stride, void* codes, int32_t* status, void* stream);
+
 /* ----------------------------------------------------------------- (a15) --
  * QuantLinear weight/bias fake-quantisation, per output channel:
  *   s_row = max(max|W_row|,1e-8)/(2^(bits-1)-1); W_int = clamp(rint((1/s_row) W));
