@@ -44,12 +44,12 @@ SIGNATURES = {
     "dqrm_embbag_bwd": (_i32, [_i32, _p, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p, _i32, _p,
                                _p, _p, _sz, _p]),
     "dqrm_grad_absmax_scale": (_i32, [_i32, _i32, _p, _p, _i64, _i32, _p, _p]),
-    "dqrm_sgd_rows": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _f32, _f32, _p, _f32, _p]),
+    "dqrm_sgd_rows": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _f32, _p, _f32, _p, _f32, _p]),
     "dqrm_slot_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "dqrm_slot_layout": (_i32, [_i32, _i64, _i32, _i32, C.POINTER(_sz), C.POINTER(_sz)]),
     "dqrm_grad_pack": (_i32, [_i32, _i32, _p, _p, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p]),
     "dqrm_grad_topk": (_i32, [_i32, _i32, _p, _p, _p, _i64, _i64, _p]),
-    "dqrm_grad_merge_apply": (_i32, [_i32, _p, _p, _i32, _p, _i32, _i64, _i32, _p, _f32, _p, _p, _p, _p, _p]),
+    "dqrm_grad_merge_apply": (_i32, [_i32, _p, _p, _i32, _p, _i32, _i64, _i32, _p, _f32, _p, _p, _p, _p, _p, _p]),
     "dqrm_interact_fwd": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p]),
     "dqrm_interact_bwd": (_i32, [_p, _p, _i64, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _i64, _i64, _p, _p]),
     "dqrm_linear_fakequant": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
@@ -59,7 +59,7 @@ SIGNATURES = {
     "dqrm_fake_quant": (_i32, [_p, _i64, _i64, _p, _i32, _i32, _p, _p, _p]),
     "dqrm_dense_grad_scale": (_i32, [_p, _p, _p, _i32, _i32, _p, _p]),
     "dqrm_dense_grad_quant": (_i32, [_p, _p, _i32, _p, _f32, _i32, _p, _p, _p]),
-    "dqrm_dense_apply": (_i32, [_p, _p, _p, _i32, _p, _f32, _f32, _p, _p, _p]),
+    "dqrm_dense_apply": (_i32, [_p, _p, _p, _i32, _p, _f32, _f32, _p, _p, _p, _p]),
     "dqrm_bce_loss_grad": (_i32, [_p, _p, _i64, _p, _p, _p]),
     "dqrm_p2p_alloc": (_i32, [_sz, C.POINTER(_vp), _p]),
     "dqrm_p2p_open": (_i32, [_p, C.POINTER(_vp)]),
@@ -69,7 +69,7 @@ SIGNATURES = {
     "dqrm_p2p_site_layout": (_i32, [_i32, _sz, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "dqrm_p2p_allgather": (_i32, [_p, _i32, _i32, _sz, _sz, _p, _p]),
     "dqrm_dense_grad_quant_gathered": (_i32, [_p, _p, _i32, _p, _sz, _i32, _i32, _p, _p, _p]),
-    "dqrm_dense_apply_gathered": (_i32, [_p, _p, _sz, _i32, _p, _i32, _p, _f32, _p, _p, _p, _p]),
+    "dqrm_dense_apply_gathered": (_i32, [_p, _p, _sz, _i32, _p, _i32, _p, _f32, _p, _p, _p, _p, _p]),
     "dqrm_scale_from_absmax_gathered": (_i32, [_i32, _p, _sz, _i32, _i32, _p, _p, _p, _p]),
 }
 

@@ -286,7 +286,9 @@ template <int COLS, bool USE_MOM>
 __global__ void __launch_bounds__(256)
 sgd_rows_kernel(const __grid_constant__ TableSet ts, const __grid_constant__ MomPtrs mom, int dim4, int group,
                 const int* __restrict__ uniq_rows, const int* __restrict__ uniq_count,
-                const float* __restrict__ grad_sums, long long capacity, float neg_lr, float inv_world, float eps) {
+                const float* __restrict__ grad_sums, long long capacity, float neg_lr_arg, const float* __restrict__ lr_dev,
+                float inv_world, float eps) {
+  const float neg_lr = lr_dev ? -(*lr_dev) : neg_lr_arg;
   const int t = blockIdx.y;
   const int U = uniq_count[t];
   const int lane = threadIdx.x % group;
@@ -444,7 +446,7 @@ extern "C" int dqrm_grad_absmax_scale(int num_tables, int dim, const float* grad
 
 extern "C" int dqrm_sgd_rows(int num_tables, float* const* weight, const int64_t* rows, int dim,
                              const int32_t* uniq_rows, const int32_t* uniq_count, const float* grad_sums,
-                             int64_t capacity, float lr, float inv_world, float* const* momentum, float eps,
+                             int64_t capacity, float lr, const float* lr_dev, float inv_world, float* const* momentum, float eps,
                              void* stream) {
   DQRM_REQUIRE(weight && rows && uniq_rows && uniq_count && grad_sums, -EINVAL, "sgd_rows: null argument");
   DQRM_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= 512, -EINVAL, "sgd_rows: dim=%d", dim);
@@ -462,9 +464,9 @@ extern "C" int dqrm_sgd_rows(int num_tables, float* const* weight, const int64_t
 #define DQRM_SGD(COLS)                                                                                              \
   do {                                                                                                              \
     if (momentum) sgd_rows_kernel<COLS, true><<<grid, 256, 0, st>>>(ts, mom, dim / 4, rl.group, uniq_rows, uniq_count, \
-                                                                    grad_sums, capacity, neg_lr, inv_world, eps);   \
+                                                                    grad_sums, capacity, neg_lr, lr_dev, inv_world, eps); \
     else sgd_rows_kernel<COLS, false><<<grid, 256, 0, st>>>(ts, mom, dim / 4, rl.group, uniq_rows, uniq_count,      \
-                                                            grad_sums, capacity, neg_lr, inv_world, eps);           \
+                                                            grad_sums, capacity, neg_lr, lr_dev, inv_world, eps);   \
   } while (0)
   if (rl.cols == 1) DQRM_SGD(1);
   else if (rl.cols == 2) DQRM_SGD(2);

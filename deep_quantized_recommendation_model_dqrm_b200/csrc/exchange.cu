@@ -94,11 +94,13 @@ template <int COLS, typename CodeT>
 __global__ void __launch_bounds__(256)
 grad_merge_apply_kernel(const __grid_constant__ TableSet ts, int dim4, int group,
                         const unsigned char* __restrict__ gathered, SlotLayout lay, int world, long long capacity,
-                        const float* __restrict__ scale_mean, float neg_lr, float inv_world,
+                        const float* __restrict__ scale_mean, float neg_lr_arg, const float* __restrict__ lr_dev,
+                        float inv_world,
                         int* __restrict__ updated_rows, int* __restrict__ updated_count, float* __restrict__ qbar,
                         int* __restrict__ status) {
   using C4 = typename Code4<CodeT>::type;
   if (*status & DQRM_STATUS_P2P_TIMEOUT) return;                         // an exchange timed out: never apply stale slots
+  const float neg_lr = lr_dev ? -(*lr_dev) : neg_lr_arg;                 // lr from device memory: graph replays follow a schedule
   const int t = blockIdx.z, r = blockIdx.y;
   const unsigned char* my = gathered + (size_t)r * lay.bytes;
   const int U = reinterpret_cast<const int*>(my)[t];
@@ -226,7 +228,7 @@ extern "C" int dqrm_grad_pack(int num_tables, int dim, const float* grad_sums, c
 
 extern "C" int dqrm_grad_merge_apply(int num_tables, float* const* weight, const int64_t* rows, int dim,
                                      const void* gathered, int world, int64_t capacity, int bits,
-                                     const float* scale_mean, float lr,
+                                     const float* scale_mean, float lr, const float* lr_dev,
                                      int32_t* updated_rows, int32_t* updated_count, float* qbar,
                                      int32_t* status, void* stream) {
   DQRM_REQUIRE(weight && rows && gathered && scale_mean && status, -EINVAL, "grad_merge_apply: null argument");
@@ -251,7 +253,7 @@ extern "C" int dqrm_grad_merge_apply(int num_tables, float* const* weight, const
   const float neg_lr = -lr;
 #define DQRM_MERGE(COLS, CT)                                                                                         \
   grad_merge_apply_kernel<COLS, CT><<<grid, 256, 0, st>>>(ts, dim / 4, rl.group, static_cast<const unsigned char*>(gathered), \
-                                                          lay, world, capacity, scale_mean, neg_lr, inv_world,        \
+                                                          lay, world, capacity, scale_mean, neg_lr, lr_dev, inv_world, \
                                                           updated_rows, updated_count, qbar, status)
   if (bits == 32) { if (rl.cols == 1) DQRM_MERGE(1, float); else if (rl.cols == 2) DQRM_MERGE(2, float); else DQRM_MERGE(4, float); }
   else if (bits <= 8) { if (rl.cols == 1) DQRM_MERGE(1, int8_t); else if (rl.cols == 2) DQRM_MERGE(2, int8_t); else DQRM_MERGE(4, int8_t); }

@@ -68,8 +68,9 @@ dense_grad_quant_kernel(const float* __restrict__ grad, const long long* __restr
 
 __global__ void __launch_bounds__(256)
 dense_apply_kernel(float* __restrict__ param, const float* __restrict__ code_sum, const long long* __restrict__ chan_begin,
-                   int num_chan, const float* __restrict__ scale_mean, float inv_world, float neg_lr,
-                   const float* __restrict__ comp_grad, float* __restrict__ ec_out) {
+                   int num_chan, const float* __restrict__ scale_mean, float inv_world, float neg_lr_arg,
+                   const float* __restrict__ lr_dev, const float* __restrict__ comp_grad, float* __restrict__ ec_out) {
+  const float neg_lr = lr_dev ? -(*lr_dev) : neg_lr_arg;
   const int lane = threadIdx.x & 31;
   const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= num_chan) return;
@@ -148,13 +149,13 @@ extern "C" int dqrm_dense_grad_quant(const float* grad, const int64_t* chan_begi
 }
 
 extern "C" int dqrm_dense_apply(float* param, const float* code_sum, const int64_t* chan_begin, int num_chan,
-                                const float* scale_mean, float inv_world, float lr, const float* comp_grad,
+                                const float* scale_mean, float inv_world, float lr, const float* lr_dev, const float* comp_grad,
                                 float* error_comp_out, void* stream) {
   DQRM_REQUIRE(param && code_sum && chan_begin && num_chan >= 1, -EINVAL, "dense_apply: bad argument");
   DQRM_REQUIRE(!error_comp_out || (comp_grad && scale_mean), -EINVAL, "dense_apply: error compensation needs comp_grad and scale_mean");
   dense_apply_kernel<<<(num_chan + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, code_sum, reinterpret_cast<const long long*>(chan_begin), num_chan, scale_mean, inv_world, -lr, comp_grad,
-      error_comp_out);
+      param, code_sum, reinterpret_cast<const long long*>(chan_begin), num_chan, scale_mean, inv_world, -lr, lr_dev,
+      comp_grad, error_comp_out);
   DQRM_LAUNCH_CHECK("dense_apply_kernel");
   return 0;
 }

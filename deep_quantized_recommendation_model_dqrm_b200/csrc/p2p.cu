@@ -118,10 +118,11 @@ dense_grad_quant_gathered_kernel(const float* __restrict__ grad, const long long
 __global__ void __launch_bounds__(256)
 dense_apply_gathered_kernel(float* __restrict__ param, const signed char* __restrict__ gathered_codes,
                             size_t code_stride, int world, const long long* __restrict__ chan_begin, int num_chan,
-                            const float* __restrict__ scale_mean, float inv_world, float neg_lr,
-                            const float* __restrict__ comp_grad, float* __restrict__ ec_out,
-                            const int* __restrict__ status) {
+                            const float* __restrict__ scale_mean, float inv_world, float neg_lr_arg,
+                            const float* __restrict__ lr_dev, const float* __restrict__ comp_grad,
+                            float* __restrict__ ec_out, const int* __restrict__ status) {
   if (status && (*status & DQRM_STATUS_P2P_TIMEOUT)) return;             // an exchange timed out: never apply stale slots
+  const float neg_lr = lr_dev ? -(*lr_dev) : neg_lr_arg;
   const int lane = threadIdx.x & 31;
   const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= num_chan) return;
@@ -250,14 +251,14 @@ extern "C" int dqrm_dense_grad_quant_gathered(const float* grad, const int64_t* 
 
 extern "C" int dqrm_dense_apply_gathered(float* param, const int8_t* gathered_codes, size_t code_stride_bytes, int world,
                                          const int64_t* chan_begin, int num_chan, const float* scale_mean, float lr,
-                                         const float* comp_grad, float* error_comp_out, const int32_t* status,
+                                         const float* lr_dev, const float* comp_grad, float* error_comp_out, const int32_t* status,
                                          void* stream) {
   DQRM_REQUIRE(param && gathered_codes && chan_begin && scale_mean && num_chan >= 1 && world >= 1, -EINVAL,
                "dense_apply_gathered: bad argument");
   DQRM_REQUIRE(!error_comp_out || comp_grad, -EINVAL, "dense_apply_gathered: error compensation needs comp_grad");
   dense_apply_gathered_kernel<<<(num_chan + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, reinterpret_cast<const signed char*>(gathered_codes), code_stride_bytes, world,
-      reinterpret_cast<const long long*>(chan_begin), num_chan, scale_mean, (float)(1.0 / world), -lr, comp_grad,
+      reinterpret_cast<const long long*>(chan_begin), num_chan, scale_mean, (float)(1.0 / world), -lr, lr_dev, comp_grad,
       error_comp_out, status);
   DQRM_LAUNCH_CHECK("dense_apply_gathered_kernel");
   return 0;

@@ -90,6 +90,7 @@ class DenseArena:
         # call site of the reference (:341,350); allocated on first use.
         self.error_compensation = False
         self.ec = None
+        self.lr_dev = None                 # device fp32 [1]: when set, apply() reads the learning rate from it
         self._bind_scale_views()
 
     def _bind_scale_views(self):
@@ -277,10 +278,11 @@ class DenseArena:
         if quantized and getattr(self, "exchanged_gathered", False):
             rc = self.lib.dqrm_dense_apply_gathered(self.flat.data_ptr(), self._code_slots.data_ptr(),
                                                     self._code_slots.stride(0), world, self.chan_begin.data_ptr(),
-                                                    self.num_chan, self.scale_mean.data_ptr(), float(lr), comp, ec,
-                                                    self.status.data_ptr(), st)
+                                                    self.num_chan, self.scale_mean.data_ptr(), float(lr),
+                                                    _lib.ptr(self.lr_dev), comp, ec, self.status.data_ptr(), st)
             _lib.check(rc, "dqrm_dense_apply_gathered")
             return
         _lib.check(self.lib.dqrm_dense_apply(self.flat.data_ptr(), self.codes.data_ptr(), self.chan_begin.data_ptr(),
                                              self.num_chan, self.scale_mean.data_ptr() if quantized else None,
-                                             float(1.0 / world), float(lr), comp, ec, st), "dqrm_dense_apply")
+                                             float(1.0 / world), float(lr), _lib.ptr(self.lr_dev), comp, ec, st),
+                   "dqrm_dense_apply")

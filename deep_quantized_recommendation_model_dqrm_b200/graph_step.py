@@ -51,9 +51,16 @@ class GraphedTrainStep:
         for v, src in zip(views, (X, lS_o, lS_i, T)):
             v.copy_(src)
         self.loss = torch.zeros((), device=dev)
+        # the learning rate lives in device memory: the update kernels read it at run time, so set_lr() takes effect on
+        # the next replay of the captured graph (LRPolicyScheduler warm-up / decay without re-capture)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.fused_loss = dlrm.loss_function == "bce" and not (0.0 < dlrm.loss_threshold < 1.0)
         self.group = dlrm._ensure_group()
         self.group.dp_world, self.group.dp_rank = world_size, rank
+        self.group.lr_dev = self.lr_dev
+        from .sgd_quantized_gradients_parallel_comm import _dense_arena as _arena_of
+        _arena_of(dlrm).lr_dev = self.lr_dev
         self.pipelined = self.group.scale_policy == "pipelined"
         # row-sharded scan: the absmax exchange + scale are issued right before the embedding forward (inside the
         # graph, after the bottom MLP) instead of right behind the scan -- its round trip is off the critical path
@@ -172,6 +179,13 @@ class GraphedTrainStep:
         self.scan(events)
         self.replay()
         return self.loss
+
+    def set_lr(self, lr):
+        """New learning rate for the following steps (asynchronous; ordered on the current stream before the next
+        run()).  Works for graph replays and the eager body alike."""
+        self.lr = float(lr)
+        self._lr_host[0] = self.lr
+        self.lr_dev.copy_(self._lr_host, non_blocking=True)
 
     def input_bytes(self):
         return int(self._stage.numel())

@@ -89,6 +89,7 @@ class EmbeddingTableGroup:
         # packed-INT4 shadow rows for the training forward (csrc/shadow.cu): None = off (fp32 rows only)
         self.shadow = None
         self.shadow_scale = self._shadow_flags = self._shadow_ptrs = self._shadow_buf = None
+        self.lr_dev = None                 # device fp32 [1]: when set, the update kernels read the learning rate from it
         self.defer_scan_reduce = False     # sharded scan: leave the MAX over ranks to finish_scan() (called by forward)
         self._scan_reduce_pending = None
 
@@ -626,7 +627,7 @@ class EmbeddingTableGroup:
         dbg = self.keep_debug
         rc = lib.dqrm_grad_merge_apply(self.T, self._wptrs(), self._rows_arr, self.dim, self.gathered.data_ptr(),
                                        self.world, self.capacity, self.grad_bit, self.grad_scale_mean.data_ptr(),
-                                       float(lr), _lib.ptr(self.updated_rows) if dbg else None,
+                                       float(lr), _lib.ptr(self.lr_dev), _lib.ptr(self.updated_rows) if dbg else None,
                                        _lib.ptr(self.updated_count) if dbg else None,
                                        _lib.ptr(self.qbar) if dbg else None, self.status.data_ptr(), st)
         _lib.check(rc, "dqrm_grad_merge_apply")
@@ -639,7 +640,7 @@ class EmbeddingTableGroup:
         mom = _lib.ptr_array(momentum) if momentum is not None else None
         rc = self.lib.dqrm_sgd_rows(self.T, self._wptrs(), self._rows_arr, self.dim, self.uniq_rows.data_ptr(),
                                     self.uniq_count.data_ptr(), self.grad_sums.data_ptr(), self.capacity, float(lr),
-                                    float(inv_world), mom, float(eps), st)
+                                    _lib.ptr(self.lr_dev), float(inv_world), mom, float(eps), st)
         _lib.check(rc, "dqrm_sgd_rows")
         self._shadow_update_rows(from_slots=False)
         self._tracker_update(from_slots=False)

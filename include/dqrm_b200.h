@@ -46,6 +46,9 @@ extern "C" {
 #define DQRM_API
 #endif
 
+/* `lr_dev` (dqrm_sgd_rows, dqrm_grad_merge_apply, dqrm_dense_apply, dqrm_dense_apply_gathered): when not NULL the
+ * learning rate is read from this device fp32 scalar at kernel run time instead of the by-value `lr`, so a captured
+ * CUDA graph follows an LR schedule (LRPolicyScheduler, dlrm_s_pytorch_comm_grad.py:221-255) without re-capture. */
 #define DQRM_ABI_VERSION 3
 #define DQRM_MAX_TABLES 64           /* tables per call (kernel-parameter descriptor size) */
 #define DQRM_BWD_CTA_MAX_LOOKUPS 16384 /* per-table lookups handled by the single-CTA sort path */
@@ -218,7 +221,7 @@ DQRM_API int dqrm_grad_absmax_scale(int num_tables, int dim, const float* grad_s
  */
 DQRM_API int dqrm_sgd_rows(int num_tables, float* const* weight, const int64_t* rows, int dim,
                   const int32_t* uniq_rows, const int32_t* uniq_count, const float* grad_sums, int64_t capacity,
-                  float lr, float inv_world, float* const* momentum, float eps, void* stream);
+                  float lr, const float* lr_dev, float inv_world, float* const* momentum, float eps, void* stream);
 
 /* ----------------------------------------------------------- (a7 steps 3-4) --
  * Quantise this rank's de-duplicated row gradients into its exchange slot.
@@ -276,7 +279,7 @@ DQRM_API int dqrm_grad_topk(int num_tables, int dim, float* grad_sums, int32_t* 
  */
 DQRM_API int dqrm_grad_merge_apply(int num_tables, float* const* weight, const int64_t* rows, int dim,
                           const void* gathered, int world, int64_t capacity, int bits,
-                          const float* scale_mean, float lr,
+                          const float* scale_mean, float lr, const float* lr_dev,
                           int32_t* updated_rows, int32_t* updated_count, float* qbar,
                           int32_t* status, void* stream);
 
@@ -396,7 +399,7 @@ DQRM_API int dqrm_dense_grad_quant(const float* grad, const int64_t* chan_begin,
                           const float* scale_sum, float inv_world, int bits,
                           float* codes, float* scale_mean, void* stream);
 DQRM_API int dqrm_dense_apply(float* param, const float* code_sum, const int64_t* chan_begin, int num_chan,
-                     const float* scale_mean, float inv_world, float lr, const float* comp_grad,
+                     const float* scale_mean, float inv_world, float lr, const float* lr_dev, const float* comp_grad,
                      float* error_comp_out, void* stream);
 
 /* BCE loss (mean reduction) and its gradient in one launch: torch.nn.BCELoss()(Z, T) + E.backward() of the
@@ -439,6 +442,7 @@ DQRM_API int dqrm_dense_grad_quant_gathered(const float* grad, const int64_t* ch
  * 957,662-663); rank r's int8 codes at gathered_codes + r * code_stride_bytes. */
 DQRM_API int dqrm_dense_apply_gathered(float* param, const int8_t* gathered_codes, size_t code_stride_bytes, int world,
                                        const int64_t* chan_begin, int num_chan, const float* scale_mean, float lr,
+                                       const float* lr_dev,
                                        const float* comp_grad, float* error_comp_out, const int32_t* status,
                                        void* stream);
 /* (a1, row-sharded scan) absmax = max over ranks of the gathered per-shard maxima, then scale and 1/scale. */

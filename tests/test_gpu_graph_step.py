@@ -65,3 +65,38 @@ def test_graph_step_matches_eager_iteration(use_graph):
         assert torch.equal(a, b)                                 # identical gradients -> identical tables
     for (na, pa), (nb, pb) in zip(ref.named_parameters(), m.named_parameters()):
         assert torch.equal(pa, pb), na
+
+
+def test_graph_replay_follows_an_lr_schedule():
+    """The learning rate is read from device memory by the update kernels: GraphedTrainStep.set_lr() between replays
+    of ONE captured graph must give the same model as the eager iteration called with each step's lr
+    (LRPolicyScheduler warm-up + decay, dlrm_s_pytorch_comm_grad.py:221-255)."""
+    import numpy as np
+    from helpers import C_SMALL, build_cuda_model
+    from deep_quantized_recommendation_model_dqrm_b200 import synthetic
+    from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
+    from deep_quantized_recommendation_model_dqrm_b200.graph_step import GraphedTrainStep
+    ma, mb = build_cuda_model(C_SMALL, seed=31), build_cuda_model(C_SMALL, seed=31)
+    sched = drv.LRPolicyScheduler(0.4, num_warmup_steps=3, decay_start_step=4, num_decay_steps=4)
+    b0 = [t.cuda() for t in synthetic.criteo_batch(C_SMALL["rows"], 32, seed=900)]
+    lrs = []
+    for _ in range(8):
+        lrs.append(sched.get_lr()[-1])
+        sched.step()
+    assert len(set(lrs)) > 3
+    snapshot = {k: v.detach().clone() for k, v in mb.named_parameters()}
+    step = GraphedTrainStep(mb, *b0, lr=lrs[0], warmup=1, use_graph=True)     # warm-up iterations train: rewind
+    with torch.no_grad():
+        for k, v in mb.named_parameters():
+            v.copy_(snapshot[k])
+    mb.emb_group.scale_valid = False
+    for i, lr in enumerate(lrs):
+        bt = synthetic.criteo_batch(C_SMALL["rows"], 32, seed=901 + i, zipf=1.2)
+        la = drv.train_iteration(ma, *bt, lr=lr)
+        with torch.cuda.stream(step.stream):
+            step.set_lr(lr)
+            step.load(*[t.cuda() for t in bt])
+            step.run()
+        torch.cuda.synchronize()
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            assert torch.equal(pa, pb), i

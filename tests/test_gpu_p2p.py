@@ -56,7 +56,7 @@ def test_allgather_gives_up_when_a_peer_is_missing():
     chan = torch.tensor([0, 8], dtype=torch.int64, device="cuda")
     mean = torch.ones(1, device="cuda")
     _lib.check(lib.dqrm_dense_apply_gathered(param.data_ptr(), codes.data_ptr(), 16, 2, chan.data_ptr(), 1, mean.data_ptr(), 0.1,
-                                             None, None, status.data_ptr(), _lib.stream_ptr()), "apply_g")
+                                             None, None, None, status.data_ptr(), _lib.stream_ptr()), "apply_g")
     torch.cuda.synchronize()
     assert torch.equal(param, torch.ones(8, device="cuda"))
     # ... and the host-side poll raises without clearing it
@@ -68,7 +68,7 @@ def test_allgather_gives_up_when_a_peer_is_missing():
             g.check_status()
     status.zero_()
     _lib.check(lib.dqrm_dense_apply_gathered(param.data_ptr(), codes.data_ptr(), 16, 2, chan.data_ptr(), 1, mean.data_ptr(), 0.1,
-                                             None, None, status.data_ptr(), _lib.stream_ptr()), "apply_g")
+                                             None, None, None, status.data_ptr(), _lib.stream_ptr()), "apply_g")
     torch.cuda.synchronize()
     assert torch.equal(param, torch.full((8,), 1.0 - 0.1 * 5.0, device="cuda"))
 
@@ -110,7 +110,7 @@ def test_gathered_dense_consumers_match_allreduce_form(world):
     for r in range(1, world):
         csum = csum + codes_f[r]
     pa = param0.clone()
-    _lib.check(lib.dqrm_dense_apply(pa.data_ptr(), csum.data_ptr(), chan_t.data_ptr(), C, mean_a.data_ptr(), 1.0 / world, 0.1, None, None, st), "apply")
+    _lib.check(lib.dqrm_dense_apply(pa.data_ptr(), csum.data_ptr(), chan_t.data_ptr(), C, mean_a.data_ptr(), 1.0 / world, 0.1, None, None, None, st), "apply")
     # gathered form
     stride = (total + 15) // 16 * 16 + 16
     codes_i = torch.zeros((world, stride), dtype=torch.int8, device="cuda")
@@ -120,7 +120,7 @@ def test_gathered_dense_consumers_match_allreduce_form(world):
                                                       scales.stride(0), world, 8, codes_i[r].data_ptr(), mean_b.data_ptr(), st), "quant_g")
     pb = param0.clone()
     _lib.check(lib.dqrm_dense_apply_gathered(pb.data_ptr(), codes_i.data_ptr(), stride, world, chan_t.data_ptr(), C,
-                                             mean_b.data_ptr(), 0.1, None, None, None, st), "apply_g")
+                                             mean_b.data_ptr(), 0.1, None, None, None, None, st), "apply_g")
     torch.cuda.synchronize()
     assert torch.equal(mean_a, mean_b)
     assert torch.equal(codes_i[:, :total].float(), codes_f)
