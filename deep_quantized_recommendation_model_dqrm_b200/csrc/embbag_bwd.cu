@@ -195,13 +195,69 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
   };
   if (tid == 0) s_nlong = 0;
   __syncthreads();
-  // 5a. rows with <= kFoldBlock duplicates: one left fold each; longer rows are queued
-  for (int j = tid / group; j < U; j += nthr / group) {
-    const int p0 = seg_start[j], p1 = seg_start[j + 1];
-    if (p1 - p0 > kFoldBlock && partials != nullptr) {
-      if (lane == 0) s_long_j[atomicAdd(&s_nlong, 1)] = j;               // queue order is irrelevant to the results
-      continue;
+  // 5a. rows with <= kFoldBlock duplicates: left fold each; longer rows are queued.  A lane group folds
+  // kRowsInFlight rows at once (step s of all of them together): several independent gathers in flight per group
+  // instead of one dependent load per unique row.
+  constexpr int kRowsInFlight = 4, kShortRow = 4;
+  const int gstride = nthr / group;
+  for (int jb = tid / group; jb < U; jb += gstride * kRowsInFlight) {
+    int p0[kRowsInFlight], len[kRowsInFlight], maxlen = 0;
+#pragma unroll
+    for (int r = 0; r < kRowsInFlight; ++r) {
+      const int j = jb + r * gstride;
+      p0[r] = 0; len[r] = 0;
+      if (j < U) {
+        p0[r] = seg_start[j];
+        len[r] = seg_start[j + 1] - p0[r];
+        if (len[r] > kFoldBlock && partials != nullptr) {
+          if (lane == 0) s_long_j[atomicAdd(&s_nlong, 1)] = j;             // queue order is irrelevant to the results
+          len[r] = 0;
+        }
+      }
+      if (len[r] <= kShortRow) maxlen = max(maxlen, len[r]);
     }
+    float4 acc[kRowsInFlight][COLS];
+    for (int st = 0; st < maxlen; ++st) {
+      float4 v[kRowsInFlight][1][COLS];   // (64 registers per thread at 1024 threads)
+#pragma unroll
+      for (int r = 0; r < kRowsInFlight; ++r)
+#pragma unroll
+        for (int u = 0; u < 1; ++u) {
+          const bool live = st + u < len[r] && len[r] <= kShortRow;
+          const long long bag = live ? (long long)(unsigned)keys[p0[r] + st + u] : 0;
+#pragma unroll
+          for (int c = 0; c < COLS; ++c) {
+            const int col = lane + c * group;
+            v[r][u][c] = (live && col < dim4) ? __ldg(reinterpret_cast<const float4*>(dbase + bag * dbs) + col)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+      for (int r = 0; r < kRowsInFlight; ++r)
+#pragma unroll
+        for (int u = 0; u < 1; ++u) {
+          if (st + u >= len[r] || len[r] > kShortRow) continue;
+#pragma unroll
+          for (int c = 0; c < COLS; ++c) {
+            const float4 d = make_float4(ste_dy(v[r][u][c].x, s, quant), ste_dy(v[r][u][c].y, s, quant),
+                                         ste_dy(v[r][u][c].z, s, quant), ste_dy(v[r][u][c].w, s, quant));
+            if (st + u == 0) acc[r][c] = d;
+            else {
+              acc[r][c].x = __fadd_rn(acc[r][c].x, d.x); acc[r][c].y = __fadd_rn(acc[r][c].y, d.y);
+              acc[r][c].z = __fadd_rn(acc[r][c].z, d.z); acc[r][c].w = __fadd_rn(acc[r][c].w, d.w);
+            }
+          }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsInFlight; ++r)
+      if (len[r] > 0 && len[r] <= kShortRow) emit(jb + r * gstride, p0[r], acc[r]);
+  }
+  // rows with 5..kFoldBlock duplicates: one row at a time, 8 gathers in flight (a separate loop keeps the two
+  // register working sets apart: 64 registers per thread at 1024 threads)
+  for (int j = tid / group; j < U; j += gstride) {
+    const int p0 = seg_start[j], p1 = seg_start[j + 1];
+    if (p1 - p0 <= kShortRow || (p1 - p0 > kFoldBlock && partials != nullptr)) continue;
     float4 acc[COLS];
     fold(p0, p1, acc);
     emit(j, p0, acc);

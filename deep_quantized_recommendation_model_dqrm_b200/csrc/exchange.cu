@@ -210,7 +210,8 @@ extern "C" int dqrm_grad_pack(int num_tables, int dim, const float* grad_sums, c
   const SlotLayout lay = slot_layout(num_tables, capacity, dim, bits);
   const RowLanes rl = row_lanes(dim);
   long long blocks = ceil_div(capacity, 256 / rl.group);
-  if (blocks > 2 * kSMs) blocks = 2 * kSMs;
+  const long long cap_blocks = ceil_div(16ll * kSMs, num_tables);        // ~16 CTAs per SM over all tables: the rows of one
+  if (blocks > cap_blocks) blocks = cap_blocks;                          // big table need many loads in flight
   dim3 grid((unsigned)blocks, num_tables);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float inv_world = (float)(1.0 / world);
@@ -247,7 +248,8 @@ extern "C" int dqrm_grad_merge_apply(int num_tables, float* const* weight, const
     DQRM_REQUIRE(e == cudaSuccess, -EIO, "grad_merge_apply: memset failed: %s", cudaGetErrorString(e));
   }
   long long blocks = ceil_div(capacity, 256 / rl.group);
-  if (blocks > kSMs) blocks = kSMs;
+  const long long cap_blocks = ceil_div(16ll * kSMs, (long long)num_tables * world);   // random-row RMW: latency-bound,
+  if (blocks > cap_blocks) blocks = cap_blocks;                                        // so fill the SMs
   dim3 grid((unsigned)blocks, world, num_tables);
   const float inv_world = (float)(1.0 / world);
   const float neg_lr = -lr;
