@@ -114,6 +114,14 @@ class QuantEmbeddingBagTwo(Module):
     def unfix(self):
         self.fix_flag = False
 
+    def set_iteration_bound(self):
+        """Periodic-rescan schedule of the reference (quant_modules_not_quantize_grad.py:303-315). Its only caller
+        there is commented out (:348-361), so the counters never move and every training forward rescans; kept
+        for API parity."""
+        if self.iteration_nt == 1 and self.iteration_bound == 0:
+            self.iteration_bound += 1000
+            print("bound increasing to {}".format(self.iteration_bound.item()))
+
     # -- group plumbing -----------------------------------------------------
     def _own_group(self):
         w = self.embedding_bag.weight

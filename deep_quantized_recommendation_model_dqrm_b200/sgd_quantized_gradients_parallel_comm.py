@@ -20,7 +20,8 @@ from .quantization_supp.quant_modules import QuantEmbeddingBagTwo, QuantLinear
 from .quantization_supp.quant_utils import *  # noqa: F401,F403  (star-import kept from the reference, :19)
 
 __all__ = ["clear_gradients", "grad_update_parallel_comm", "weight_update_parallel_comm", "weight_syncc",
-           "quantized_gradients_update", "quantize_emb_grad", "quantize_linear_grad", "quantize_bias_grad"]
+           "quantized_gradients_update", "quantize_emb_grad", "quantize_linear_grad", "quantize_bias_grad",
+           "grad_precision_and_scale"]
 
 
 def _rank_world(number_of_gpus):
@@ -80,6 +81,15 @@ def clear_gradients(model):
             else:
                 param.grad.requires_grad_(False)
             param.grad.zero_()
+
+
+def grad_precision_and_scale(model, number_of_gpus, rank_for_debug, output_flag=False):
+    """Per-table gradient bit width from the gradient range (sgd_quantized_gradients_parallel_comm.py:158-255):
+    an experiment (``ranking_range=True``) whose only call sites are commented out in the reference drivers
+    (dlrm_s_pytorch_comm_grad.py:1946-1951); it also samples the ranking with numpy on rank 0 for exactly 26
+    tables. Out of scope for the hot path: fails loudly instead of silently doing something else."""
+    raise NotImplementedError("grad_precision_and_scale / ranking_range: commented out in the reference drivers "
+                              "(dlrm_s_pytorch_comm_grad.py:1946-1951); not part of the data-parallel hot path")
 
 
 def grad_update_parallel_comm(model, number_of_gpus, emb_grad_quantized=True, num_bits=16, ranking_range=False,

@@ -242,3 +242,18 @@ def test_lr_policy_scheduler_vs_reference_sequence():
         assert got == g["lrs"], name
     with pytest.raises(SystemExit):
         drv.LRPolicyScheduler(0.1, 5, 2, 3)
+
+
+def test_reference_api_leftovers(capsys):
+    """Names the reference modules export that its drivers never reach: present, documented, loud."""
+    import pytest
+    from deep_quantized_recommendation_model_dqrm_b200 import sgd_quantized_gradients_parallel_comm as sgd
+    from deep_quantized_recommendation_model_dqrm_b200.quantization_supp.quant_modules import QuantEmbeddingBagTwo
+    with pytest.raises(NotImplementedError):
+        sgd.grad_precision_and_scale(None, 2, 0)
+    e = QuantEmbeddingBagTwo(10, 16)
+    e.set_iteration_bound()
+    assert e.iteration_bound.item() == 0                     # (counters never move in the reference: qmngq:348-361)
+    e.iteration_nt += 1
+    e.set_iteration_bound()
+    assert e.iteration_bound.item() == 1000 and "bound increasing to 1000" in capsys.readouterr().out
