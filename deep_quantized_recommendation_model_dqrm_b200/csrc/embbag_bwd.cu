@@ -17,6 +17,8 @@
 // oracle's coalesce_spec defines exactly this shape), but a row's latency is one block, not the whole chain.  Sort, unique, segmented sum and scale are
 // ONE launch for all tables (the reference: index_select, thrust sort,
 // coalesceValuesKernel, 4 reductions and a host sync per table).
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace dqrm {
@@ -398,9 +400,28 @@ namespace dqrm { size_t bwd_large_workspace_bytes(int64_t lookups, int dim); }  
 static long long partial_items_per_table(int64_t lookups) { return lookups / DQRM_FOLD_BLOCK + lookups / (DQRM_FOLD_BLOCK + 1) + 2; }
 
 extern "C" size_t dqrm_bwd_workspace_bytes(int num_tables, int64_t max_lookups_per_table, int dim) {
-  if (max_lookups_per_table <= DQRM_BWD_CTA_MAX_LOOKUPS)          // block sums of the long rows, [T][items][dim] fp32
-    return (size_t)num_tables * (size_t)partial_items_per_table(max_lookups_per_table) * (size_t)dim * sizeof(float);
-  return dqrm::bwd_large_workspace_bytes(max_lookups_per_table, dim);
+  // either path may be chosen per call (pick_sort_path below): room for both
+  const size_t sort_bytes = dqrm::bwd_large_workspace_bytes(max_lookups_per_table, dim);
+  if (max_lookups_per_table > DQRM_BWD_CTA_MAX_LOOKUPS) return sort_bytes;
+  const size_t cta_bytes =                                        // block sums of the long rows, [T][items][dim] fp32
+      (size_t)num_tables * (size_t)partial_items_per_table(max_lookups_per_table) * (size_t)dim * sizeof(float);
+  return cta_bytes > sort_bytes ? cta_bytes : sort_bytes;
+}
+
+// One CTA per table (all tables in ONE launch, time ~ the longest table) against one cooperative whole-chip sort
+// launch per table (time ~ a fixed ~60 us of grid barriers each, then ~0.15 us per 1k lookups).  Measured on B200
+// (profiles/r02_sweep.jsonl): the CTA path costs ~(12 + dim/4) us per 1k lookups of the longest table.  26 tables of
+// 8192 lookups stay on the CTA path (0.2 ms vs 26 x 60 us); ONE table of >= 4k lookups goes to the sort kernel.
+// DQRM_BWD_PATH=cta|sort pins the choice (tests).  Both paths produce the same bits (blocked left fold, same order).
+static bool pick_sort_path(int num_tables, const long long* lookups, long long lmax, int dim) {
+  if (lmax > DQRM_BWD_CTA_MAX_LOOKUPS) return true;
+  const char* e = getenv("DQRM_BWD_PATH");                       // read per call: tests switch it
+  if (e && !strcmp(e, "cta")) return false;
+  if (e && !strcmp(e, "sort")) return true;
+  const double cta_us = (double)lmax * (12.0 + 0.25 * dim) / 1024.0;
+  double sort_us = 0.0;
+  for (int k = 0; k < num_tables; ++k) sort_us += lookups[k] ? 60.0 + (double)lookups[k] * (0.08 + 0.001 * dim) / 1024.0 : 2.0;
+  return sort_us < cta_us;
 }
 
 namespace dqrm {
@@ -429,7 +450,7 @@ extern "C" int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
                -EINVAL, "embbag_bwd: dout must be 16-byte aligned with strides multiple of 4");
   DQRM_REQUIRE((reinterpret_cast<uintptr_t>(grad_sums) & 15u) == 0, -EINVAL, "embbag_bwd: grad_sums not 16-byte aligned");
   BwdArgs a;
-  long long lmax = 0;
+  long long lmax = 0, lookups[DQRM_MAX_TABLES];
   for (int k = 0; k < num_tables; ++k) {
     DQRM_REQUIRE(rows[k] >= 1 && rows[k] < (1ll << 31), -EINVAL, "embbag_bwd: rows[%d]=%lld", k, (long long)rows[k]);
     DQRM_REQUIRE(idx_begin[k + 1] >= idx_begin[k], -EINVAL, "embbag_bwd: idx_begin not monotone at %d", k);
@@ -438,13 +459,15 @@ extern "C" int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
     const long long L = idx_begin[k + 1] - idx_begin[k];
     DQRM_REQUIRE(L <= capacity, -EINVAL, "embbag_bwd: table %d has %lld lookups > capacity %lld", k, L, (long long)capacity);
     if (L > lmax) lmax = L;
+    lookups[k] = L;
   }
   a.idx_begin[num_tables] = idx_begin[num_tables];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const RowLanes rl = row_lanes(dim);
 
-  if (lmax > DQRM_BWD_CTA_MAX_LOOKUPS) {
-    // large tables: one multi-block radix-sort pipeline per table
+  if (pick_sort_path(num_tables, lookups, lmax, dim) &&
+      (lmax > DQRM_BWD_CTA_MAX_LOOKUPS || workspace_bytes >= dqrm::bwd_large_workspace_bytes(lmax, dim))) {
+    // one persistent whole-chip radix-sort + fold launch per table
     for (int k = 0; k < num_tables; ++k) {
       int rc = embbag_bwd_large(k, rows[k], idx_begin[k], idx_begin[k + 1], dim, indices, offsets, bags, dout,
                                 dout_table_stride, dout_bag_stride, fwd_scale, capacity, uniq_rows, uniq_count,

@@ -42,10 +42,25 @@ dense_grad_scale_kernel(float* __restrict__ grad, const float* __restrict__ ec, 
   if (ch >= num_chan) return;
   const long long a = chan_begin[ch], e = chan_begin[ch + 1];
   unsigned m = 0u;
-  for (long long i = a + lane; i < e; i += 32) {
-    float w = grad[i];
-    if (ec) { w = __fadd_rn(w, ec[i]); grad[i] = w; }                     // weight = grad + error_compensation  (:899-900,938-939)
-    m = max(m, abs_bits(w));
+  for (long long i0 = a + lane; i0 < e; i0 += 128) {                      // four elements in flight per lane
+    long long idx[4];
+    bool ok[4];
+    float w[4], c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { idx[j] = i0 + 32 * j; ok[j] = idx[j] < e; idx[j] = ok[j] ? idx[j] : e - 1; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = grad[idx[j]];
+    if (ec) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = ec[idx[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!ok[j]) continue;
+      float v = w[j];
+      if (ec) { v = __fadd_rn(v, c[j]); grad[idx[j]] = v; }                // weight = grad + error_compensation  (:899-900,938-939)
+      m = max(m, abs_bits(v));
+    }
   }
   m = warp_max_u32(m);
   if (lane == 0) scale_local[ch] = scale_of(__uint_as_float(m), bits);
@@ -62,6 +77,7 @@ dense_grad_quant_kernel(const float* __restrict__ grad, const long long* __restr
   const float s_bar = __fmul_rn(scale_sum[ch], inv_world);
   const float inv = __fdiv_rn(1.0f, s_bar);
   const float hi = qmax_of(bits), lo = -hi - 1.0f;
+#pragma unroll 4
   for (long long i = a + lane; i < e; i += 32) codes[i] = quant_code(grad[i], inv, lo, hi);
   if (lane == 0) scale_mean[ch] = s_bar;
 }
@@ -76,12 +92,27 @@ dense_apply_kernel(float* __restrict__ param, const float* __restrict__ code_sum
   if (ch >= num_chan) return;
   const long long a = chan_begin[ch], e = chan_begin[ch + 1];
   const float s = scale_mean ? scale_mean[ch] : 1.0f;
-  for (long long i = a + lane; i < e; i += 32) {
-    const float g = __fmul_rn(code_sum[i], inv_world);                    // all_reduce(SUM) * (1/N)
-    float u = __fmul_rn(neg_lr, g);                                       // (-lr * grad) ...
-    if (scale_mean) u = __fmul_rn(u, s);                                  // ... * s          (:642-643)
-    param[i] = __fadd_rn(param[i], u);
-    if (ec_out) ec_out[i] = __fsub_rn(comp_grad[i], __fmul_rn(g, s));     // weight - grad_up * s   (:926-927,958-959)
+  for (long long i0 = a + lane; i0 < e; i0 += 128) {                      // four elements in flight per lane (see p2p.cu)
+    long long idx[4];
+    bool ok[4];
+    float cs[4], p[4], c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { idx[j] = i0 + 32 * j; ok[j] = idx[j] < e; idx[j] = ok[j] ? idx[j] : e - 1; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cs[j] = code_sum[idx[j]]; p[j] = param[idx[j]]; }
+    if (ec_out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = comp_grad[idx[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!ok[j]) continue;
+      const float g = __fmul_rn(cs[j], inv_world);                        // all_reduce(SUM) * (1/N)
+      float u = __fmul_rn(neg_lr, g);                                     // (-lr * grad) ...
+      if (scale_mean) u = __fmul_rn(u, s);                                // ... * s          (:642-643)
+      param[idx[j]] = __fadd_rn(p[j], u);
+      if (ec_out) ec_out[idx[j]] = __fsub_rn(c[j], __fmul_rn(g, s));      // weight - grad_up * s   (:926-927,958-959)
+    }
   }
 }
 

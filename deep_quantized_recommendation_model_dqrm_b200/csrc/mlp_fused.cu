@@ -117,21 +117,41 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
   const int tx = tid & 15, ty = tid >> 4;                               // thread tile rows ty*4.., cols tx*4..
   const int kbeg = rank * kc, kend = min(K, kbeg + kc);
 
-  auto g_at = [&](int bi, int oi) -> float {                            // g = dout * act'(out) * s_row
-    const long long e = (long long)bi * out_f + oi;
-    return __fmul_rn(act_bwd(__ldg(dout + e), __ldg(out + e), act), __ldg(s_row + oi));
+  // Staging loads are BRANCH-FREE: out-of-range elements read a clamped (valid) address and are zeroed by a select
+  // afterwards, and the activation derivative is a select too.  With `if (m >= M) return 0` / `out > 0 ? dout : 0`
+  // written as control flow, ptxas emitted one reconvergence region per element -- load dout+out, wait, branch, load
+  // s_row, wait -- i.e. 8 serialised load latencies per K-tile (ncu source page, profiles/r02_linear_gemm_ncu.txt);
+  // now every load of a K-tile is in flight before the first use.  Same arithmetic, same bits.
+  struct Raw { float d, o, s; bool ok; };
+  auto A_issue = [&](int m, int k) -> Raw {
+    Raw r;
+    r.ok = m < M && k < kend;
+    const int mc = min(m, M - 1), kk = min(k, kend - 1);
+    if (MODE == 0) {
+      r.d = __ldg(x + (long long)mc * in_f + kk);
+      r.o = 0.0f; r.s = 0.0f;
+    } else {
+      const int bi = MODE == 1 ? mc : kk, oi = MODE == 1 ? kk : mc;      // g(batch bi, out oi) = dout * act'(out) * s_row
+      const long long e = (long long)bi * out_f + oi;
+      r.d = __ldg(dout + e);
+      r.o = __ldg(out + e);
+      r.s = __ldg(s_row + oi);
+    }
+    return r;
   };
-  auto A_at = [&](int m, int k) -> float {
-    if (m >= M || k >= kend) return 0.0f;
-    if (MODE == 0) return __ldg(x + (long long)m * in_f + k);
-    if (MODE == 1) return g_at(m, k);
-    return g_at(k, m);
+  auto A_finish = [&](const Raw& r) -> float {
+    if (MODE == 0) return r.ok ? r.d : 0.0f;
+    const float relu = r.o > 0.0f ? r.d : 0.0f;                           // threshold_backward
+    const float sigm = __fmul_rn(r.d, __fmul_rn(__fsub_rn(1.0f, r.o), r.o));   // sigmoid_backward
+    const float g = act == kActRelu ? relu : (act == kActSigmoid ? sigm : r.d);
+    return r.ok ? __fmul_rn(g, r.s) : 0.0f;
   };
-  auto B_at = [&](int k, int n) -> float {
-    if (k >= kend || n >= N) return 0.0f;
-    if (MODE == 0) return __ldg(W_int + (long long)n * in_f + k);
-    if (MODE == 1) return __ldg(W_int + (long long)k * in_f + n);
-    return __ldg(x + (long long)k * in_f + n);
+  auto B_issue = [&](int k, int n, bool& ok) -> float {
+    ok = k < kend && n < N;
+    const int kk = min(k, kend - 1), nc = min(n, N - 1);
+    if (MODE == 0) return __ldg(W_int + (long long)nc * in_f + kk);
+    if (MODE == 1) return __ldg(W_int + (long long)kk * in_f + nc);
+    return __ldg(x + (long long)kk * in_f + nc);
   };
   // element -> (row, k) mappings chosen so that consecutive threads read consecutive addresses
   auto a_coord = [&](int e, int& am, int& ak) {
@@ -149,10 +169,16 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
   float db_part = 0.0f;
   float a_reg[A_PER_THR], b_reg[B_PER_THR];
   auto fetch = [&](int k0) {
+    Raw ar[A_PER_THR];
+    bool bok[B_PER_THR];
 #pragma unroll
-    for (int i = 0; i < A_PER_THR; ++i) { int am, ak; a_coord(tid + i * kGemmThreads, am, ak); a_reg[i] = A_at(m0 + am, k0 + ak); }
+    for (int i = 0; i < A_PER_THR; ++i) { int am, ak; a_coord(tid + i * kGemmThreads, am, ak); ar[i] = A_issue(m0 + am, k0 + ak); }
 #pragma unroll
-    for (int i = 0; i < B_PER_THR; ++i) { int bk, bn; b_coord(tid + i * kGemmThreads, bk, bn); b_reg[i] = B_at(k0 + bk, n0 + bn); }
+    for (int i = 0; i < B_PER_THR; ++i) { int bk, bn; b_coord(tid + i * kGemmThreads, bk, bn); b_reg[i] = B_issue(k0 + bk, n0 + bn, bok[i]); }
+#pragma unroll
+    for (int i = 0; i < A_PER_THR; ++i) a_reg[i] = A_finish(ar[i]);
+#pragma unroll
+    for (int i = 0; i < B_PER_THR; ++i) b_reg[i] = bok[i] ? b_reg[i] : 0.0f;
   };
   auto stash = [&](int buf) {
 #pragma unroll
@@ -176,9 +202,13 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
 #pragma unroll
       for (int t = 0; t < NT; ++t) {                                    // every load of the slice in flight
 #pragma unroll
-        for (int i = 0; i < A_PER_THR; ++i) { int am, ak; a_coord(tid + i * kGemmThreads, am, ak); a_all[t][i] = A_at(m0 + am, kbeg + t * BK + ak); }
+        for (int i = 0; i < A_PER_THR; ++i) { int am, ak; a_coord(tid + i * kGemmThreads, am, ak); a_all[t][i] = A_finish(A_issue(m0 + am, kbeg + t * BK + ak)); }
 #pragma unroll
-        for (int i = 0; i < B_PER_THR; ++i) { int bk, bn; b_coord(tid + i * kGemmThreads, bk, bn); b_all[t][i] = B_at(kbeg + t * BK + bk, n0 + bn); }
+        for (int i = 0; i < B_PER_THR; ++i) {
+          int bk, bn; bool ok; b_coord(tid + i * kGemmThreads, bk, bn);
+          const float v = B_issue(kbeg + t * BK + bk, n0 + bn, ok);
+          b_all[t][i] = ok ? v : 0.0f;
+        }
       }
 #pragma unroll
       for (int t = 0; t < NT; ++t) {

@@ -110,6 +110,7 @@ dense_grad_quant_gathered_kernel(const float* __restrict__ grad, const long long
   const float s_bar = __fmul_rn(acc, inv_world);
   const float inv = __fdiv_rn(1.0f, s_bar);
   const float hi = qmax_of(bits), lo = -hi - 1.0f;
+#pragma unroll 4
   for (long long i = a + lane; i < e; i += 32) codes[i] = (signed char)quant_code(grad[i], inv, lo, hi);
   if (lane == 0) scale_mean[ch] = s_bar;
 }
@@ -128,13 +129,35 @@ dense_apply_gathered_kernel(float* __restrict__ param, const signed char* __rest
   if (ch >= num_chan) return;
   const long long a = chan_begin[ch], e = chan_begin[ch + 1];
   const float s = scale_mean[ch];
-  for (long long i = a + lane; i < e; i += 32) {
-    int q = 0;
-    for (int r = 0; r < world; ++r) q += gathered_codes[(size_t)r * code_stride + i];
-    const float g = __fmul_rn((float)q, inv_world);                       // all_reduce(SUM) * (1/N)
-    const float u = __fmul_rn(__fmul_rn(neg_lr, g), s);                   // (-lr * grad) * s     (:642-643)
-    param[i] = __fadd_rn(param[i], u);
-    if (ec_out) ec_out[i] = __fsub_rn(comp_grad[i], __fmul_rn(g, s));     // weight - grad_up * s   (:926-927,958-959)
+  // four strided elements per lane and trip, every load (world codes + the parameter + comp_grad) issued before the
+  // first store: with one element per trip the row cost one dependent load round trip per 32 elements (14 us at
+  // world 2 for the 0.47 M MLP parameters of the Kaggle shape).  Out-of-range lanes read a clamped address.
+  for (long long i0 = a + lane; i0 < e; i0 += 128) {
+    long long idx[4];
+    bool ok[4];
+    int q[4] = {0, 0, 0, 0};
+    float p[4], c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { idx[j] = i0 + 32 * j; ok[j] = idx[j] < e; idx[j] = ok[j] ? idx[j] : e - 1; }
+#pragma unroll 2
+    for (int r = 0; r < world; ++r) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[j] += gathered_codes[(size_t)r * code_stride + idx[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = param[idx[j]];
+    if (ec_out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = comp_grad[idx[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!ok[j]) continue;
+      const float g = __fmul_rn((float)q[j], inv_world);                  // all_reduce(SUM) * (1/N)
+      const float u = __fmul_rn(__fmul_rn(neg_lr, g), s);                 // (-lr * grad) * s     (:642-643)
+      param[idx[j]] = __fadd_rn(p[j], u);
+      if (ec_out) ec_out[idx[j]] = __fsub_rn(c[j], __fmul_rn(g, s));      // weight - grad_up * s   (:926-927,958-959)
+    }
   }
 }
 

@@ -272,10 +272,15 @@ def test_large_path_one_kernel_sort(case):
         assert bits_equal(cpu(g.grad_scale_local[0]), O.grad_scale_spec(sums, 8))
 
 
-def test_max_cta_lookups_boundary():
-    """Exactly DQRM_BWD_CTA_MAX_LOOKUPS lookups (largest single-CTA sort) with heavy duplication."""
+@pytest.mark.parametrize("path,lookups", [("cta", None), ("sort", None), ("auto", None), ("cta", 6000), ("auto", 6000)])
+def test_max_cta_lookups_boundary(path, lookups, monkeypatch):
+    """Exactly DQRM_BWD_CTA_MAX_LOOKUPS lookups (largest single-CTA sort) with heavy duplication, on the single-CTA
+    path, on the whole-chip sort kernel, and on whichever the cost model picks (one table of >= 4k lookups: the sort
+    kernel): the same bits either way."""
     _lib, synthetic, tables, qm, qu = _mods()
-    rows, dim, B = 300, 16, _lib.BWD_CTA_MAX_LOOKUPS
+    if path != "auto":
+        monkeypatch.setenv("DQRM_BWD_PATH", path)
+    rows, dim, B = 300, 16, lookups or _lib.BWD_CTA_MAX_LOOKUPS
     rng = np.random.RandomState(4)
     W = synthetic.table_weights_numpy(rows, dim, rng)
     idx = torch.from_numpy(np.minimum(rng.zipf(1.1, size=B) - 1, rows - 1).astype(np.int64))

@@ -33,7 +33,9 @@ def test_argument_validation_without_a_device():
     assert lib.dqrm_scan_workspace_bytes(26) == 27 * 4
     assert lib.dqrm_slot_bytes(26, 128, 16, 8) == 112 + 26 * 128 * 4 + 26 * 128 * 16
     assert lib.dqrm_slot_bytes(26, 128, 16, 16) == 112 + 26 * 128 * 4 + 26 * 128 * 16 * 2
-    assert lib.dqrm_bwd_workspace_bytes(26, 128, 16) == 26 * (128 // 64 + 128 // 65 + 2) * 16 * 4      # block sums of long rows
+    # room for either backward path (CTA: block sums of long rows; sort kernel: keys, histograms, partial sums)
+    assert lib.dqrm_bwd_workspace_bytes(26, 128, 16) >= 26 * (128 // 64 + 128 // 65 + 2) * 16 * 4
+    assert lib.dqrm_bwd_workspace_bytes(26, 8192, 64) >= 26 * (8192 // 64 + 8192 // 65 + 2) * 64 * 4
     assert lib.dqrm_bwd_workspace_bytes(1, 1 << 20, 16) > 4 * (1 << 20) * 4
     # errors are returned, not thrown, and carry a message (no kernel is launched on these paths)
     rc = lib.dqrm_table_absmax_scale(0, None, None, 16, 4, 0, 1, None, None, None, None, None)
