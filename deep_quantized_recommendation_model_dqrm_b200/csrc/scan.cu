@@ -9,6 +9,7 @@
 // touched.  The last CTA to finish turns the per-table maxima into
 // (absmax, scale, 1/scale) and re-zeros the workspace, so the scale never
 // visits the host (the reference pays a D2H sync per table, quant_utils.py:191).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dqrm {
@@ -128,7 +129,14 @@ extern "C" int dqrm_table_absmax_scale(int num_tables, const float* const* weigh
   a.tile_begin[num_tables] = (int)tiles;
   unsigned* acc = static_cast<unsigned*>(workspace);
   unsigned* counter = acc + num_tables;
-  long long grid = tiles < (long long)kSMs * kScanCtasPerSm ? tiles : (long long)kSMs * kScanCtasPerSm;
+  // resident CTAs per SM: 8 fills every thread slot; fewer leave room for kernels of other streams to run beside the
+  // pass (the bottom MLP does not depend on it) -- 46 KiB in flight per SM already covers HBM latency x bandwidth
+  static const int ctas_per_sm = [] {
+    const char* e = getenv("DQRM_SCAN_CTAS_PER_SM");
+    const int v = e ? atoi(e) : kScanCtasPerSm;
+    return v < 1 ? 1 : (v > kScanCtasPerSm ? kScanCtasPerSm : v);
+  }();
+  long long grid = tiles < (long long)kSMs * ctas_per_sm ? tiles : (long long)kSMs * ctas_per_sm;
   if (grid < 1) grid = 1;
   table_absmax_kernel<<<(unsigned)grid, kScanThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       a, acc, counter, absmax, scale, inv_scale, bits, (int)tiles);
