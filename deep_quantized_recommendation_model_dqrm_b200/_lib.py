@@ -60,6 +60,7 @@ SIGNATURES = {
     "dqrm_dense_grad_scale": (_i32, [_p, _p, _p, _i32, _i32, _p, _p]),
     "dqrm_dense_grad_quant": (_i32, [_p, _p, _i32, _p, _f32, _i32, _p, _p, _p]),
     "dqrm_dense_apply": (_i32, [_p, _p, _p, _i32, _p, _f32, _f32, _p, _p, _p, _p]),
+    "dqrm_dense_quant_apply_local": (_i32, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _f32, _p, _p]),
     "dqrm_bce_loss_grad": (_i32, [_p, _p, _i64, _p, _p, _p]),
     "dqrm_p2p_alloc": (_i32, [_sz, C.POINTER(_vp), _p]),
     "dqrm_p2p_open": (_i32, [_p, C.POINTER(_vp)]),
@@ -73,7 +74,7 @@ SIGNATURES = {
     "dqrm_scale_from_absmax_gathered": (_i32, [_i32, _p, _sz, _i32, _i32, _p, _p, _p, _p]),
 }
 
-LINEAR_AUTO, LINEAR_FFMA, LINEAR_TC = 0, 1, 2
+LINEAR_AUTO, LINEAR_FFMA, LINEAR_TC, LINEAR_FFMA_SERIAL = 0, 1, 2, 3
 # contraction engine of the fused QuantLinear kernels (include/dqrm_b200.h DQRM_LINEAR_*); env DQRM_MLP_PATH=ffma|tc|auto
 linear_path = {"auto": LINEAR_AUTO, "ffma": LINEAR_FFMA, "tc": LINEAR_TC}[os.environ.get("DQRM_MLP_PATH", "auto").lower()]
 
@@ -87,7 +88,7 @@ LAUNCHING = ("dqrm_table_absmax_scale", "dqrm_scale_from_absmax", "dqrm_embbag_f
              "dqrm_blockmax_build", "dqrm_blockmax_update", "dqrm_blockmax_scan", "dqrm_blockmax_update_shard",
              "dqrm_blockmax_reduce", "dqrm_table_pack_int4", "dqrm_embbag_fwd_int4",
              "dqrm_shadow_refresh", "dqrm_shadow_update_rows", "dqrm_embbag_fwd_shadow",
-             "dqrm_dense_grad_scale", "dqrm_dense_grad_quant", "dqrm_dense_apply",
+             "dqrm_dense_grad_scale", "dqrm_dense_grad_quant", "dqrm_dense_apply", "dqrm_dense_quant_apply_local",
              "dqrm_bce_loss_grad", "dqrm_p2p_allgather", "dqrm_dense_grad_quant_gathered", "dqrm_dense_apply_gathered",
              "dqrm_scale_from_absmax_gathered")
 launch_counts = {}

@@ -116,6 +116,69 @@ dense_apply_kernel(float* __restrict__ param, const float* __restrict__ code_sum
   }
 }
 
+// Single rank: dense_grad_scale + dense_grad_quant + dense_apply in ONE launch (a warp owns a channel from its
+// max-abs to its updated parameters; the channel's second read hits L1/L2).  The same operations in the same order
+// as the three kernels with inv_world = 1, and the same buffers written (scale_local, scale_mean, codes, grad when
+// error compensation is on), so every observable result is bit-identical -- it only removes two launches from the
+// tail of the step.  error_comp and error_comp_out may alias (the reference's buffer is read, then overwritten).
+__global__ void __launch_bounds__(256)
+dense_local_quant_apply_kernel(float* __restrict__ param, float* __restrict__ grad, const float* error_comp,
+                               const long long* __restrict__ chan_begin, int num_chan, int bits,
+                               float* __restrict__ scale_local, float* __restrict__ codes, float* __restrict__ scale_mean,
+                               float neg_lr_arg, const float* __restrict__ lr_dev, float* error_comp_out) {
+  const float neg_lr = lr_dev ? -(*lr_dev) : neg_lr_arg;
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ch >= num_chan) return;
+  const long long a = chan_begin[ch], e = chan_begin[ch + 1];
+  unsigned m = 0u;
+  for (long long i0 = a + lane; i0 < e; i0 += 128) {
+    long long idx[4];
+    bool ok[4];
+    float w[4], c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { idx[j] = i0 + 32 * j; ok[j] = idx[j] < e; idx[j] = ok[j] ? idx[j] : e - 1; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = grad[idx[j]];
+    if (error_comp) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = error_comp[idx[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!ok[j]) continue;
+      float v = w[j];
+      if (error_comp) { v = __fadd_rn(v, c[j]); grad[idx[j]] = v; }
+      m = max(m, abs_bits(v));
+    }
+  }
+  m = warp_max_u32(m);
+  const float s_local = scale_of(__uint_as_float(m), bits);
+  const float s_bar = __fmul_rn(s_local, 1.0f);                           // scale_sum * inv_world
+  const float inv = __fdiv_rn(1.0f, s_bar);
+  const float hi = qmax_of(bits), lo = -hi - 1.0f;
+  if (lane == 0) { scale_local[ch] = s_local; scale_mean[ch] = s_bar; }
+  for (long long i0 = a + lane; i0 < e; i0 += 128) {                      // each lane re-reads what it wrote above
+    long long idx[4];
+    bool ok[4];
+    float w[4], p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { idx[j] = i0 + 32 * j; ok[j] = idx[j] < e; idx[j] = ok[j] ? idx[j] : e - 1; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { w[j] = grad[idx[j]]; p[j] = param[idx[j]]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!ok[j]) continue;
+      const float q = quant_code(w[j], inv, lo, hi);
+      codes[idx[j]] = q;
+      const float g = __fmul_rn(q, 1.0f);                                 // code_sum * inv_world
+      const float u = __fmul_rn(__fmul_rn(neg_lr, g), s_bar);
+      param[idx[j]] = __fadd_rn(p[j], u);
+      if (error_comp_out) error_comp_out[idx[j]] = __fsub_rn(w[j], __fmul_rn(g, s_bar));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 fake_quant_kernel(const float* __restrict__ x, long long rows, long long cols, const float* __restrict__ scale,
                   int per_row, int bits, float* __restrict__ q, float* __restrict__ dq) {
@@ -188,6 +251,19 @@ extern "C" int dqrm_dense_apply(float* param, const float* code_sum, const int64
       param, code_sum, reinterpret_cast<const long long*>(chan_begin), num_chan, scale_mean, inv_world, -lr, lr_dev,
       comp_grad, error_comp_out);
   DQRM_LAUNCH_CHECK("dense_apply_kernel");
+  return 0;
+}
+
+extern "C" int dqrm_dense_quant_apply_local(float* param, float* grad, float* error_comp, const int64_t* chan_begin,
+                                            int num_chan, int bits, float* scale_local, float* codes, float* scale_mean,
+                                            float lr, const float* lr_dev, void* stream) {
+  DQRM_REQUIRE(param && grad && chan_begin && scale_local && codes && scale_mean && num_chan >= 1, -EINVAL,
+               "dense_quant_apply_local: bad argument");
+  DQRM_REQUIRE(bits >= 2 && bits <= 16, -EINVAL, "dense_quant_apply_local: bits=%d outside [2,16]", bits);
+  dense_local_quant_apply_kernel<<<(num_chan + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, error_comp, reinterpret_cast<const long long*>(chan_begin), num_chan, bits, scale_local, codes,
+      scale_mean, -lr, lr_dev, error_comp);
+  DQRM_LAUNCH_CHECK("dense_local_quant_apply_kernel");
   return 0;
 }
 

@@ -82,23 +82,21 @@ __device__ __forceinline__ float act_bwd(float dout, float out, int act) {
 // one row-slice of the tile over ranks 0..S-1 through distributed shared memory -- a fixed order, so the
 // result is deterministic (no atomics, no workspace; replicas stay bit-identical) -- and applies the
 // epilogue for that slice.  Inside a CTA the K loop is a register-prefetch double buffer.
-constexpr int BM = 32, BN = 64, BK = 16, TM = 4, TN = 4, kGemmThreads = 128;
-constexpr int A_PER_THR = BM * BK / kGemmThreads, B_PER_THR = BK * BN / kGemmThreads;    // 4, 8
+constexpr int BM = 32, BN = 64, TM = 4, TN = 4, kGemmThreads = 128;
+constexpr int kSliceMin = 64;                                 // a cluster rank's K-slice is at least this long
 constexpr int APAD = BM + 4, BPAD = BN + 4;
 
 // CL = false: the same kernel with no cluster instruction at all (S = 1).  A grid that uses clusters was
 // measured not to become co-resident with a long-running non-cluster grid (the pipelined table rescan,
 // tracker.cu): the step's GEMMs waited for the whole pass.  See DESIGN.md "pipelined rescan".
-// NT > 0 (experimental, DQRM_GEMM_PREFETCH=1, not yet validated on hardware): the CTA's whole K-slice is at most NT
-// tiles; ALL of its global loads are issued before the first FMA, so the kernel pays one load latency instead of one
-// per K-tile (these GEMMs are latency-bound: ~4 dependent 0.7 us round trips per launch at Kaggle shape).  Same tile
-// order, same FMA order: bit-identical results.  NT = 0 (default): the register double-buffered loop, unchanged.
-template <int MODE, bool CL = true, int NT = 0>
+// BK: K-tile depth (16 or 32).  A "prefetch the whole K-slice into registers before the first FMA" variant
+// (DQRM_GEMM_PREFETCH of round 1) was measured SLOWER on B200 (dW 11.0 vs 7.8 us) and is gone.
+template <int MODE, bool CL, int BK>
 __global__ void __launch_bounds__(kGemmThreads)
 linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int, const float* __restrict__ b_int,
                    const float* __restrict__ s_row, const float* __restrict__ dout, const float* __restrict__ out,
                    float* __restrict__ C, float* __restrict__ db, int batch, int out_f, int in_f, int act, int kc,
-                   int accumulate) {
+                   int accumulate, int serial) {
   namespace cg = cooperative_groups;
   int S = 1, rank = 0;
   if constexpr (CL) {
@@ -106,6 +104,7 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
     S = (int)cluster.num_blocks();
     rank = (int)cluster.block_rank();
   }
+  constexpr int A_PER_THR = BM * BK / kGemmThreads, B_PER_THR = BK * BN / kGemmThreads;    // BK 16: 4, 8
   __shared__ __align__(16) float As[2][BK][APAD];
   __shared__ __align__(16) float Bs[2][BK][BPAD];                       // also the partial tile red[BM][BN]
   static_assert(2 * BK * BPAD >= BM * BN, "partial tile must fit in Bs");
@@ -115,7 +114,7 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;                               // thread tile rows ty*4.., cols tx*4..
-  const int kbeg = rank * kc, kend = min(K, kbeg + kc);
+  int kbeg = rank * kc, kend = min(K, kbeg + kc);
 
   // Staging loads are BRANCH-FREE: out-of-range elements read a clamped (valid) address and are zeroed by a select
   // afterwards, and the activation derivative is a select too.  With `if (m >= M) return 0` / `out > 0 ? dout : 0`
@@ -196,32 +195,23 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
-  if constexpr (NT > 0) {
-    if (kbeg < kend) {                                                  // host guarantees kend - kbeg <= NT * BK
-      float a_all[NT][A_PER_THR], b_all[NT][B_PER_THR];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {                                    // every load of the slice in flight
-#pragma unroll
-        for (int i = 0; i < A_PER_THR; ++i) { int am, ak; a_coord(tid + i * kGemmThreads, am, ak); a_all[t][i] = A_finish(A_issue(m0 + am, kbeg + t * BK + ak)); }
-#pragma unroll
-        for (int i = 0; i < B_PER_THR; ++i) {
-          int bk, bn; bool ok; b_coord(tid + i * kGemmThreads, bk, bn);
-          const float v = B_issue(kbeg + t * BK + bk, n0 + bn, ok);
-          b_all[t][i] = ok ? v : 0.0f;
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        if (kbeg + t * BK < kend) {                                     // CTA-uniform
-          const int buf = t & 1;                                        // last read by tile t-2: every thread passed
-#pragma unroll                                                          // that before the barrier of tile t-1
-          for (int i = 0; i < A_PER_THR; ++i) {
-            int am, ak; a_coord(tid + i * kGemmThreads, am, ak); As[buf][ak][am] = a_all[t][i];
-            if (MODE == 2) db_part = __fadd_rn(db_part, a_all[t][i]);
-          }
-#pragma unroll
-          for (int i = 0; i < B_PER_THR; ++i) { int bk, bn; b_coord(tid + i * kGemmThreads, bk, bn); Bs[buf][bk][bn] = b_all[t][i]; }
-          __syncthreads();
+  {
+    // serial > 1 (CL = false, forward only): ONE CTA walks the `serial` K-slices that a cluster of that size would
+    // have split between its CTAs, one after the other, and adds the slice sums in rank order -- the same bits as the
+    // cluster launch, without a cluster launch (which does not become co-resident beside a long-running grid: the
+    // bottom MLP that runs next to the table scan uses this, DQRM_LINEAR_FFMA_SERIAL)
+    const int slices = (!CL && serial > 1) ? serial : 1;
+    float tot[TM][TN];
+    for (int sl = 0; sl < slices; ++sl) {
+      if (slices > 1) { kbeg = sl * kc; kend = min(K, kbeg + kc); }
+      if (kbeg < kend) {
+        fetch(kbeg);
+        stash(0);
+        __syncthreads();
+        int buf = 0;
+        for (int k0 = kbeg; k0 < kend; k0 += BK) {
+          const bool more = k0 + BK < kend;
+          if (more) fetch(k0 + BK);                                     // loads in flight during the FMAs below
 #pragma unroll
           for (int k = 0; k < BK; ++k) {
             const float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
@@ -232,31 +222,20 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
 #pragma unroll
               for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
           }
+          if (more) stash(buf ^ 1);
+          __syncthreads();
+          buf ^= 1;
         }
       }
-      __syncthreads();                                                  // Bs is reused for the partial tile below
-    }
-  } else if (kbeg < kend) {
-    fetch(kbeg);
-    stash(0);
-    __syncthreads();
-    int buf = 0;
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-      const bool more = k0 + BK < kend;
-      if (more) fetch(k0 + BK);                                         // loads in flight during the FMAs below
-#pragma unroll
-      for (int k = 0; k < BK; ++k) {
-        const float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
-        const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
-        const float a[TM] = {av.x, av.y, av.z, av.w}, b[TN] = {bv.x, bv.y, bv.z, bv.w};
+      if (slices > 1) {
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < TN; ++j) {
+            tot[i][j] = sl == 0 ? acc[i][j] : __fadd_rn(tot[i][j], acc[i][j]);
+            acc[i][j] = sl + 1 == slices ? tot[i][j] : 0.0f;
+          }
       }
-      if (more) stash(buf ^ 1);
-      __syncthreads();
-      buf ^= 1;
     }
   }
 
@@ -326,26 +305,28 @@ linear_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W_int,
   }
 }
 
-// cluster size: enough K-slices to put >= ~128 CTAs on the chip, each slice >= 2 K-tiles
+// cluster size: enough K-slices to put >= ~128 CTAs on the chip, each slice >= kSliceMin long
 // (DQRM_MLP_MAX_CLUSTER caps it -- a diagnostic knob: 1 = no cluster launch at all)
 static int pick_split(int tiles, int K) {
   static const int max_s = [] { const char* e = getenv("DQRM_MLP_MAX_CLUSTER"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   int S = 1;
-  while (S < max_s && tiles * S < 128 && K / (S * 2) >= 2 * BK) S *= 2;
+  while (S < max_s && tiles * S < 128 && K / (S * 2) >= kSliceMin / 2) S *= 2;
   return S;
 }
 
 template <int MODE>
 static int launch_gemm(const float* x, const float* W_int, const float* b_int, const float* s_row, const float* dout,
                        const float* out, float* C, float* db, int batch, int out_f, int in_f, int act, int accumulate,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool serial_slices = false) {
   const int M = MODE == 2 ? out_f : batch;
   const int N = MODE == 0 ? out_f : in_f;
   const int K = MODE == 0 ? in_f : (MODE == 1 ? out_f : batch);
   const int gx = (N + BN - 1) / BN, gy = (M + BM - 1) / BM;
-  const int S = pick_split(gx * gy, K);
+  int S = pick_split(gx * gy, K);
   int kc = (K + S - 1) / S;
-  kc = ((kc + BK - 1) / BK) * BK;
+  kc = ((kc + 31) / 32) * 32;                                            // a multiple of either K-tile depth: same slices, same bits
+  const int serial = (serial_slices && MODE == 0) ? S : 1;              // the same slices, walked by one CTA
+  if (serial > 1) S = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, gy, S);
   cfg.blockDim = dim3(kGemmThreads);
@@ -356,29 +337,23 @@ static int launch_gemm(const float* x, const float* W_int, const float* b_int, c
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
   cfg.attrs = attr;
   cfg.numAttrs = S > 1 ? 1 : 0;
-  // experimental: prefetch the whole K-slice when it is at most 4 tiles (see the kernel comment); off by default
-  static const bool prefetch = [] { const char* e = getenv("DQRM_GEMM_PREFETCH"); return e && atoi(e) != 0; }();
-  const int nt = (prefetch && kc <= 4 * BK) ? kc / BK : 0;
+  // K-tile depth: 32 halves the number of dependent load round trips of a slice (DQRM_GEMM_BK=16 for comparison)
+  static const int bk = [] { const char* e = getenv("DQRM_GEMM_BK"); return (e && atoi(e) == 16) ? 16 : 32; }();
   cudaError_t e;
-#define DQRM_GEMM_LAUNCH(NTV)                                                                                        \
+#define DQRM_GEMM_LAUNCH(BKV)                                                                                        \
   do {                                                                                                               \
     if (S > 1) {                                                                                                     \
-      e = cudaLaunchKernelEx(&cfg, linear_gemm_kernel<MODE, true, NTV>, x, W_int, b_int, s_row, dout, out, C, db,    \
-                             batch, out_f, in_f, act, kc, accumulate);                                               \
+      e = cudaLaunchKernelEx(&cfg, linear_gemm_kernel<MODE, true, BKV>, x, W_int, b_int, s_row, dout, out, C, db,    \
+                             batch, out_f, in_f, act, kc, accumulate, 1);                                            \
     } else {                                                                                                         \
-      linear_gemm_kernel<MODE, false, NTV><<<cfg.gridDim, cfg.blockDim, 0, st>>>(x, W_int, b_int, s_row, dout, out,  \
+      linear_gemm_kernel<MODE, false, BKV><<<cfg.gridDim, cfg.blockDim, 0, st>>>(x, W_int, b_int, s_row, dout, out,  \
                                                                                  C, db, batch, out_f, in_f, act, kc, \
-                                                                                 accumulate);                        \
+                                                                                 accumulate, serial);                \
       e = cudaGetLastError();                                                                                        \
     }                                                                                                                \
   } while (0)
-  switch (nt) {
-    case 1: DQRM_GEMM_LAUNCH(1); break;
-    case 2: DQRM_GEMM_LAUNCH(2); break;
-    case 3: DQRM_GEMM_LAUNCH(3); break;
-    case 4: DQRM_GEMM_LAUNCH(4); break;
-    default: DQRM_GEMM_LAUNCH(0); break;
-  }
+  if (bk == 16) DQRM_GEMM_LAUNCH(16);
+  else DQRM_GEMM_LAUNCH(32);
 #undef DQRM_GEMM_LAUNCH
   if (e != cudaSuccess) { set_error("linear_gemm_kernel<%d>: %s", MODE, cudaGetErrorString(e)); return -EIO; }
   return 0;
@@ -393,7 +368,7 @@ int launch_gemm_tc(int mode, const float* x, const float* W_int, const float* b_
 // that a layer is a handful of tiles and the cluster split-K FFMA kernel's shorter prologue wins.
 static bool use_tc(int path, int batch) {
   static const int min_batch = [] { const char* e = getenv("DQRM_MLP_TC_MIN_BATCH"); return e ? atoi(e) : 256; }();
-  if (path == DQRM_LINEAR_FFMA) return false;
+  if (path == DQRM_LINEAR_FFMA || path == DQRM_LINEAR_FFMA_SERIAL) return false;
   if (path == DQRM_LINEAR_TC) return true;
   return batch >= min_batch;
 }
@@ -430,12 +405,12 @@ extern "C" int dqrm_linear_fwd(const float* x, const float* W_int, const float* 
                                int batch, int out_features, int in_features, int act, float* out, int path, void* stream) {
   DQRM_REQUIRE(x && W_int && scale_row && out, -EINVAL, "linear_fwd: null argument");
   DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_fwd: bad shape/act");
-  DQRM_REQUIRE(path >= 0 && path <= 2, -EINVAL, "linear_fwd: path=%d", path);
+  DQRM_REQUIRE(path >= 0 && path <= 3, -EINVAL, "linear_fwd: path=%d", path);
   if (use_tc(path, batch))
     return launch_gemm_tc(0, x, W_int, b_int, scale_row, nullptr, nullptr, out, nullptr, batch, out_features, in_features,
                           act, 0, static_cast<cudaStream_t>(stream));
   return launch_gemm<0>(x, W_int, b_int, scale_row, nullptr, nullptr, out, nullptr, batch, out_features, in_features, act,
-                        0, static_cast<cudaStream_t>(stream));
+                        0, static_cast<cudaStream_t>(stream), path == DQRM_LINEAR_FFMA_SERIAL);
 }
 
 extern "C" int dqrm_linear_bwd(const float* x, const float* W_int, const float* scale_row, const float* dout,
@@ -443,7 +418,7 @@ extern "C" int dqrm_linear_bwd(const float* x, const float* W_int, const float* 
                                float* dx, float* dW, float* db, int accumulate, int path, void* stream) {
   DQRM_REQUIRE(x && W_int && scale_row && dout && out && (dW || dx), -EINVAL, "linear_bwd: null argument");
   DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_bwd: bad shape/act");
-  DQRM_REQUIRE(path >= 0 && path <= 2, -EINVAL, "linear_bwd: path=%d", path);
+  DQRM_REQUIRE(path >= 0 && path <= 3, -EINVAL, "linear_bwd: path=%d", path);     // (_SERIAL: same as _FFMA here)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tcp = use_tc(path, batch);
   if (dx) {

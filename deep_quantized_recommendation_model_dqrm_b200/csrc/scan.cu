@@ -17,7 +17,8 @@ namespace dqrm {
 constexpr int kScanThreads = 256;
 constexpr int kScanVec = 4;                                   // float4 loads in flight per thread
 constexpr int kScanTile = kScanThreads * kScanVec * 4;        // floats per tile (16 KiB)
-constexpr int kScanCtasPerSm = 8;
+constexpr int kScanCtasPerSm = 8;                             // launch bound (most that can be resident)
+constexpr int kScanCtasDefault = 4;                           // launched: 64 KiB in flight per SM; measured 6.93 TB/s vs 6.82 at 8
 
 struct ScanArgs {
   const float* w[DQRM_MAX_TABLES];
@@ -133,11 +134,18 @@ extern "C" int dqrm_table_absmax_scale(int num_tables, const float* const* weigh
   // pass (the bottom MLP does not depend on it) -- 46 KiB in flight per SM already covers HBM latency x bandwidth
   static const int ctas_per_sm = [] {
     const char* e = getenv("DQRM_SCAN_CTAS_PER_SM");
-    const int v = e ? atoi(e) : kScanCtasPerSm;
+    const int v = e ? atoi(e) : kScanCtasDefault;
     return v < 1 ? 1 : (v > kScanCtasPerSm ? kScanCtasPerSm : v);
   }();
   long long grid = tiles < (long long)kSMs * ctas_per_sm ? tiles : (long long)kSMs * ctas_per_sm;
   if (grid < 1) grid = 1;
+  // The pass streams every byte once (no L1 reuse), so it asks for the LARGEST shared-memory carve-out: an SM's
+  // L1/shared split can only change while the SM is empty, and with the default (max L1) split a kernel that needs
+  // shared memory -- the bottom-MLP GEMMs that run beside this pass -- waited ~290 us for the pass to drain
+  // (measured, profiles/r02_timeline_overlap_*.txt).
+  static const cudaError_t carve = cudaFuncSetAttribute(table_absmax_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                        (int)cudaSharedmemCarveoutMaxShared);
+  (void)carve;
   table_absmax_kernel<<<(unsigned)grid, kScanThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       a, acc, counter, absmax, scale, inv_scale, bits, (int)tiles);
   DQRM_LAUNCH_CHECK("table_absmax_kernel");

@@ -91,6 +91,8 @@ class DenseArena:
         self.error_compensation = False
         self.ec = None
         self.lr_dev = None                 # device fp32 [1]: when set, apply() reads the learning rate from it
+        self.fuse_local = False            # world 1: quantize_exchange() + apply() as ONE launch (graph_step sets it)
+        self._local_pending = None
         self._bind_scale_views()
 
     def _bind_scale_views(self):
@@ -234,6 +236,9 @@ class DenseArena:
         if self.slot_world != 0:
             self.scale_local = torch.zeros(self.num_chan, dtype=torch.float32, device=self.device)
             self.slot_world = 0
+        if world == 1 and self.fuse_local:
+            self._local_pending = bits       # scale + quantise + update in ONE launch, issued by apply()
+            return
         self.local_scale(bits)
         if world > 1 and live:
             dist.all_reduce(self.scale_local, group=process_group)
@@ -274,6 +279,15 @@ class DenseArena:
         """MLP half of weight_update_parallel_comm (sgd_quantized_gradients_parallel_comm.py:630-663)."""
         st = _lib.stream_ptr()
         ec = self._ec_ptr() if quantized else None
+        if self._local_pending is not None:
+            bits, self._local_pending = self._local_pending, None
+            assert quantized and world == 1
+            rc = self.lib.dqrm_dense_quant_apply_local(self.flat.data_ptr(), self.flat_grad.data_ptr(), ec,
+                                                       self.chan_begin.data_ptr(), self.num_chan, bits,
+                                                       self.scale_local.data_ptr(), self.codes.data_ptr(),
+                                                       self.scale_mean.data_ptr(), float(lr), _lib.ptr(self.lr_dev), st)
+            _lib.check(rc, "dqrm_dense_quant_apply_local")
+            return
         comp = self.flat_grad.data_ptr() if ec is not None else None        # = grad + ec since local_scale()
         if quantized and getattr(self, "exchanged_gathered", False):
             rc = self.lib.dqrm_dense_apply_gathered(self.flat.data_ptr(), self._code_slots.data_ptr(),

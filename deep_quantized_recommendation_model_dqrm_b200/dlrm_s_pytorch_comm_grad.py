@@ -300,14 +300,20 @@ class DLRM_Net(nn.Module):
             raise NotImplementedError("activation quantisation is outside the hot path")
         return R, None
 
-    def forward(self, dense_x, lS_o, lS_i, test_mode=False):
+    def forward_bottom(self, dense_x):
+        """The part of the forward that does not depend on the embedding scales: MLP weight fake-quantisation and the
+        bottom MLP (dlrm_s_pytorch_comm_grad.py:855).  graph_step runs it on its own stream beside the table scan and
+        hands the result to forward(x_bottom=...)."""
         if not self.quantization_flag or self.quantize_activation:
             raise NotImplementedError("only the --quantization_flag --linear_channel flow is built "
                                       "(dlrm_s_pytorch_comm_grad.py:855-859)")
         self._mlp_arena = self._fused_mlp_arena() if dense_x.shape[0] <= self.fuse_mlp_max_batch else None
         if self._mlp_arena is not None:
             self._mlp_arena.fakequant_all()          # all 7 layers' weights + biases, one launch
-        x = self.apply_mlp(dense_x, self.bot_l, prev_act_scaling_factor=None)
+        return self.apply_mlp(dense_x, self.bot_l, prev_act_scaling_factor=None)
+
+    def forward(self, dense_x, lS_o, lS_i, test_mode=False, x_bottom=None):
+        x = self.forward_bottom(dense_x) if x_bottom is None else x_bottom
         ly = self.apply_emb(lS_o, lS_i, self.emb_l, self.v_W_l, test_mode=test_mode)
         z, feature_scaling_factor = self.interact_features(x, ly)
         p = self.apply_mlp(z, self.top_l, prev_act_scaling_factor=feature_scaling_factor)

@@ -61,6 +61,8 @@ class GraphedTrainStep:
         self.group.lr_dev = self.lr_dev
         from .sgd_quantized_gradients_parallel_comm import _dense_arena as _arena_of
         _arena_of(dlrm).lr_dev = self.lr_dev
+        # one rank: nothing to exchange between the MLP gradient quantisation and the update -> one launch, same bits
+        _arena_of(dlrm).fuse_local = world_size == 1 and os.environ.get("DQRM_FUSE_LOCAL_DENSE", "1") != "0"
         self.pipelined = self.group.scale_policy == "pipelined"
         # row-sharded scan: the absmax exchange + scale are issued right before the embedding forward (inside the
         # graph, after the bottom MLP) instead of right behind the scan -- its round trip is off the critical path
@@ -69,6 +71,8 @@ class GraphedTrainStep:
         # all-gathers + pack with the bottom-MLP backward; grad_update_parallel_comm then only joins
         self.group.eager_exchange = (world_size > 1 and self.group.grad_bit == grad_bits and not self.pipelined and
                                      os.environ.get("DQRM_EAGER_EXCHANGE", "1") != "0")
+        # ... and the de-duplicating backward kernel itself: the bottom-MLP backward does not depend on it
+        self.group.side_backward = not self.pipelined and os.environ.get("DQRM_SIDE_BACKWARD", "1") != "0"
         self.stream = torch.cuda.Stream(device=dev, priority=-1)
         if self.pipelined:
             # measured on B200: a graph with forked branches is not co-scheduled with the side-stream pass (its
@@ -76,7 +80,29 @@ class GraphedTrainStep:
             from .sgd_quantized_gradients_parallel_comm import _dense_arena
             _dense_arena(dlrm).side_stream = None
         dlrm.external_scan = True
-        self.graph = self.graph_b = None
+        self.graph = self.graph_b = self.graph_pre = None
+        self._xb = None
+        # The bottom MLP (and the MLP weight fake-quantisation) does not depend on the table scales: when the scan is
+        # long enough to hide them (>= 400 MB per rank ~ 60 us at HBM speed) they are captured into their OWN linear
+        # graph and replayed on a second stream beside the scan kernel -- which launches 4 of its 8 possible CTAs per
+        # SM for exactly this reason (csrc/scan.cu).  Below the tensor-core batch threshold the layers take the
+        # serial-slice FFMA kernel: the same bits as the cluster split-K kernel, but no cluster launch (a cluster grid
+        # was measured not to become co-resident with a long-running grid).
+        from . import _lib as _l
+        scan_rows = sum(int(w.shape[0]) for w in self.group.weights)
+        scan_bytes = scan_rows * self.group.dim * 4 // (world_size if (world_size > 1 and dlrm.shard_scan) else 1)
+        mode = os.environ.get("DQRM_OVERLAP_BOTTOM", "1")          # 0: never, force: regardless of the scan size (tests)
+        self.overlap_bottom = (use_graph and self.group.scale_policy == "full" and mode != "0" and
+                               (scan_bytes >= 400_000_000 or mode == "force") and
+                               X.shape[0] <= dlrm.fuse_mlp_max_batch and dlrm._fused_mlp_arena() is not None)
+        if self.overlap_bottom:
+            self.pre_stream = torch.cuda.Stream(device=dev, priority=-1)
+            self._pre_done = torch.cuda.Event()
+            tc_min = int(os.environ.get("DQRM_MLP_TC_MIN_BATCH", "256"))
+            if _l.linear_path == _l.LINEAR_FFMA or (_l.linear_path == _l.LINEAR_AUTO and X.shape[0] < tc_min):
+                for layer in dlrm.bot_l:
+                    if hasattr(layer, "forward_fused"):
+                        layer.fwd_path = _l.LINEAR_FFMA_SERIAL
         torch.cuda.synchronize()
         with torch.cuda.stream(self.stream):
             self.group.pipe_external_join = False
@@ -99,6 +125,14 @@ class GraphedTrainStep:
                     self.graph_b = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self.graph_b, pool=self.graph.pool(), stream=self.stream):
                         self._body_b()
+                elif self.overlap_bottom:
+                    self.graph_pre = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph_pre, stream=self.pre_stream):
+                        self._xb = self.dlrm.forward_bottom(self.X)
+                    with torch.cuda.graph(self.graph, pool=self.graph_pre.pool(), stream=self.stream):
+                        self._body_a()                    # forward(x_bottom=self._xb): the rest of the step
+                        self._body_b()
+                    self._xb = None
                 else:
                     with torch.cuda.graph(self.graph, stream=self.stream):
                         self._body_a()
@@ -114,7 +148,7 @@ class GraphedTrainStep:
 
     def _body_a(self):
         d = self.dlrm
-        Z = d(self.X, self.lS_o, self.lS_i)
+        Z = d(self.X, self.lS_o, self.lS_i, x_bottom=self._xb)
         if self.fused_loss:
             # BCELoss(mean) + the first backward step in ONE launch (ATen: 8 small kernels), loss written in place
             Zd = Z.detach()
@@ -176,7 +210,18 @@ class GraphedTrainStep:
 
     def run(self, events=None):
         """scan + (graph replay | eager body); returns the device loss tensor (no sync)."""
-        self.scan(events)
+        if self.graph_pre is not None:
+            # fake-quant + bottom MLP on their own stream, beside the scan: ordered after everything already queued on
+            # the current stream (the previous step's update, this step's input copy), joined before the replay
+            cur = torch.cuda.current_stream()
+            self.pre_stream.wait_stream(cur)
+            with torch.cuda.stream(self.pre_stream):
+                self.graph_pre.replay()
+                self._pre_done.record()
+            self.scan(events)
+            cur.wait_event(self._pre_done)
+        else:
+            self.scan(events)
         self.replay()
         return self.loss
 

@@ -47,9 +47,14 @@ class EmbBagGroupFunction(Function):
             dout = dout.contiguous()
         ste_done = getattr(g, "ste_done_for", None) == dout.data_ptr()      # fused into the interaction backward
         g.ste_done_for = None
-        g.backward(dout, world=g.dp_world, last=ctx.last, ste_done=ste_done)
-        if g.eager_exchange and g.dp_world > 1:
-            g.start_exchange()           # overlaps with the bottom-MLP backward that autograd runs next
+        if g.side_backward:
+            # de-duplicating backward (+ the exchange / pack) on the group's side stream: the bottom-MLP backward that
+            # autograd runs next only needs the interaction's OTHER output; finish_exchange() joins
+            g.backward_async(dout, last=ctx.last, ste_done=ste_done)
+        else:
+            g.backward(dout, world=g.dp_world, last=ctx.last, ste_done=ste_done)
+            if g.eager_exchange and g.dp_world > 1:
+                g.start_exchange()           # overlaps with the bottom-MLP backward that autograd runs next
         if g.materialize_grads:
             grads = tuple(g.sparse_grad(t) for t in range(g.T))
         else:
@@ -216,8 +221,8 @@ class _FusedQuantLinearFunction(Function):
         out_f, in_f = weight.shape
         out = torch.empty((B, out_f), dtype=torch.float32, device=x.device)
         rc = lib.dqrm_linear_fwd(x.data_ptr(), module._w_int.data_ptr(), _lib.ptr(module._b_int),
-                                 module._fc_scale.data_ptr(), B, out_f, in_f, act, out.data_ptr(), _lib.linear_path,
-                                 _lib.stream_ptr())
+                                 module._fc_scale.data_ptr(), B, out_f, in_f, act, out.data_ptr(),
+                                 _lib.linear_path if module.fwd_path is None else module.fwd_path, _lib.stream_ptr())
         _lib.check(rc, "dqrm_linear_fwd")
         ctx.save_for_backward(x, out)
         ctx.module, ctx.act = module, act
@@ -260,6 +265,9 @@ class _FusedQuantLinearFunction(Function):
 class QuantLinear(Module):
     """Per-channel INT-k weight + bias QAT linear layer (quant_modules_not_quantize_grad.py:20-211).
     Returns a tuple ``(y, None)`` like the reference (quantize_activation=False path)."""
+
+    fwd_path = None      # forward contraction engine of the fused kernel (None: _lib.linear_path); graph_step sets
+                         # LINEAR_FFMA_SERIAL on the bottom MLP when it runs beside the table scan (same bits)
 
     def __init__(self, weight_bit=4, bias_bit=None, full_precision_flag=False, quant_mode="symmetric",
                  per_channel=False, fix_flag=False, weight_percentile=0, quantize_activation=False):

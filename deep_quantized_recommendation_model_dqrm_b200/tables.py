@@ -81,6 +81,8 @@ class EmbeddingTableGroup:
         self._bm_wptrs = None
         self.p2p = None             # PeerArena of the NVLink exchange (world > 1, DQRM_EXCHANGE=p2p)
         self.eager_exchange = False  # start the embedding exchange from inside the backward, on xchg_stream
+        self.side_backward = False   # run the de-duplicating backward itself on xchg_stream (graph_step sets it)
+        self._bwd_forked = None
         self.xchg_stream = None
         self.exchange_started = False
         self.dp_world, self.dp_rank = 1, 0
@@ -593,13 +595,29 @@ class EmbeddingTableGroup:
             self.exchange(world=self.world, rank=self.dp_rank)
         self.exchange_started = True
 
+    def backward_async(self, dout, last=None, ste_done=False):
+        """backward() -- and the exchange when it may start eagerly (always at world 1, where it is just the pack) --
+        on the side stream, forked from the current one.  `dout` is kept alive until finish_exchange() joins: inside
+        a graph capture its block must not be handed to an allocation of the parallel branch."""
+        main = torch.cuda.current_stream()
+        if self.xchg_stream is None:
+            self.xchg_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.xchg_stream.wait_stream(main)
+        with torch.cuda.stream(self.xchg_stream):
+            self.backward(dout, world=self.dp_world, last=last, ste_done=ste_done)
+            if self.dp_world == 1 or self.eager_exchange:
+                self.exchange(world=self.world, rank=self.dp_rank)
+                self.exchange_started = True
+        self._bwd_forked = dout
+
     def finish_exchange(self):
-        """True if an exchange started by start_exchange() was joined into the current stream."""
-        if not self.exchange_started:
+        """Join the side stream (backward_async / start_exchange) into the current one.  True if an exchange was
+        started there and is now complete."""
+        if not self.exchange_started and self._bwd_forked is None:
             return False
         torch.cuda.current_stream().wait_stream(self.xchg_stream)
-        self.exchange_started = False
-        return True
+        started, self.exchange_started, self._bwd_forked = self.exchange_started, False, None
+        return started
 
     def stage_scale(self, rank=0):
         """Phase 1: this rank's 26 local gradient scales into row `rank` of gathered_scales."""

@@ -357,6 +357,7 @@ DQRM_API int dqrm_linear_fakequant(const float* W, const float* b, int out_featu
 #define DQRM_LINEAR_AUTO 0
 #define DQRM_LINEAR_FFMA 1
 #define DQRM_LINEAR_TC 2
+#define DQRM_LINEAR_FFMA_SERIAL 3 /* forward: the FFMA kernel's K-slices walked by ONE CTA (no cluster launch), same bits */
 DQRM_API int dqrm_mlp_fakequant_all(int num_layers, const float* const* W, const float* const* b,
                                     const int32_t* out_features, const int32_t* in_features, int bits,
                                     float* const* W_int, float* const* b_int, float* const* scale_row, void* stream);
@@ -401,6 +402,16 @@ DQRM_API int dqrm_dense_grad_quant(const float* grad, const int64_t* chan_begin,
 DQRM_API int dqrm_dense_apply(float* param, const float* code_sum, const int64_t* chan_begin, int num_chan,
                      const float* scale_mean, float inv_world, float lr, const float* lr_dev, const float* comp_grad,
                      float* error_comp_out, void* stream);
+
+/* Single rank (world 1): dqrm_dense_grad_scale + dqrm_dense_grad_quant (inv_world 1) + dqrm_dense_apply in ONE launch --
+ * the same operations in the same order on the same buffers (scale_local, scale_mean, codes, grad (+= error_comp in
+ * place), param, error_comp <- comp_grad - code * s_bar), so every result is bit-identical to the three calls; it
+ * removes two launches from the tail of the step.  error_comp may be NULL.
+ * Replaces quantize_linear_grad/quantize_bias_grad + the MLP half of weight_update_parallel_comm
+ * (sgd_quantized_gradients_parallel_comm.py:892-961, 630-663) when there is nothing to exchange. */
+DQRM_API int dqrm_dense_quant_apply_local(float* param, float* grad, float* error_comp, const int64_t* chan_begin,
+                                 int num_chan, int bits, float* scale_local, float* codes, float* scale_mean,
+                                 float lr, const float* lr_dev, void* stream);
 
 /* BCE loss (mean reduction) and its gradient in one launch: torch.nn.BCELoss()(Z, T) + E.backward() of the
  * reference loop (loss_fn_wrap, dlrm_s_pytorch_comm_grad.py:192-211; :1938).

@@ -30,9 +30,16 @@ def test_bce_loss_grad_kernel_matches_aten(n):
     assert torch.equal(dz, zr.grad)                                            # same operation order as ATen: bit-exact
 
 
-@pytest.mark.parametrize("use_graph", [True, False])
-def test_graph_step_matches_eager_iteration(use_graph):
+@pytest.mark.parametrize("use_graph", [True, False, "overlap"])
+def test_graph_step_matches_eager_iteration(use_graph, monkeypatch):
+    """"overlap": the bottom MLP + weight fake-quantisation replayed as their own graph on a second stream beside the
+    table scan (forced here; by default only when the scan is long enough to hide them) -- same bits."""
     from helpers import C_SMALL, build_cuda_model
+    if use_graph == "overlap":
+        monkeypatch.setenv("DQRM_OVERLAP_BOTTOM", "force")
+        use_graph = True
+    else:
+        monkeypatch.setenv("DQRM_OVERLAP_BOTTOM", "0")
     from deep_quantized_recommendation_model_dqrm_b200 import synthetic
     from deep_quantized_recommendation_model_dqrm_b200 import dlrm_s_pytorch_comm_grad as drv
     from deep_quantized_recommendation_model_dqrm_b200.graph_step import GraphedTrainStep
@@ -45,6 +52,7 @@ def test_graph_step_matches_eager_iteration(use_graph):
     m = build_cuda_model(C_SMALL, seed=9)
     snapshot = {k: v.detach().clone() for k, v in m.named_parameters()}
     step = GraphedTrainStep(m, *batches[0], lr=0.2, warmup=1, use_graph=use_graph)   # warm-up iterations train: rewind
+    assert (step.graph_pre is not None) == (os.environ["DQRM_OVERLAP_BOTTOM"] == "force")
     with torch.no_grad():
         for k, v in m.named_parameters():
             v.copy_(snapshot[k])

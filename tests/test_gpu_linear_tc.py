@@ -78,3 +78,25 @@ def test_tensor_core_linear_vs_fp64_and_ffma(shape):
     again = _run(_lib.LINEAR_TC, x, Wi, bi, s, dout, act)
     for a, b in zip(tc, again):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("shape", [(128, 512, 13, 1), (128, 256, 512, 1), (128, 64, 256, 1), (128, 16, 64, 1),
+                                   (128, 512, 367, 1), (100, 1, 256, 2), (37, 40, 24, 0)])
+def test_serial_slice_forward_has_the_bits_of_the_cluster_kernel(shape):
+    """DQRM_LINEAR_FFMA_SERIAL (one CTA walks the K-slices a cluster would have split, slice sums added in rank order:
+    the variant that can run beside the table scan) must equal the cluster split-K kernel bit for bit."""
+    B, out_f, in_f, act = shape
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(B + out_f + in_f)
+    x = torch.randn((B, in_f), device="cuda", generator=g)
+    Wi = torch.randint(-8, 8, (out_f, in_f), device="cuda", generator=g).float()
+    bi = torch.randint(-8, 8, (out_f,), device="cuda", generator=g).float()
+    s = torch.rand((out_f,), device="cuda", generator=g) * 0.05 + 0.01
+    outs = []
+    for path in (_lib.LINEAR_FFMA, _lib.LINEAR_FFMA_SERIAL):
+        out = torch.empty((B, out_f), device="cuda")
+        _lib.check(lib.dqrm_linear_fwd(x.data_ptr(), Wi.data_ptr(), bi.data_ptr(), s.data_ptr(), B, out_f, in_f, act,
+                                       out.data_ptr(), path, _lib.stream_ptr()), "fwd")
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])

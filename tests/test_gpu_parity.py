@@ -517,3 +517,43 @@ def test_unquantized_exchange_emulated_ranks(world):
             assert np.array_equal(cpu(g.updated_rows[t, :nu])[order], union)
             assert bits_equal(cpu(g.qbar[t, :nu])[order], gmean)
             assert bits_equal(cpu(g.weights[t]), Wn)
+
+
+@pytest.mark.parametrize("with_ec", [False, True])
+def test_dense_local_one_launch_equals_three(with_ec):
+    """dqrm_dense_quant_apply_local (world 1: scale + quantise + update in one launch) against dqrm_dense_grad_scale ->
+    dqrm_dense_grad_quant -> dqrm_dense_apply on the same data: every buffer bit-identical, with and without
+    error compensation (sgd_quantized_gradients_parallel_comm.py:892-961, 630-663)."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(77)
+    lens = [13, 512, 367, 1, 64, 200, 5, 129, 128, 1024]
+    cb = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device="cuda")
+    n, C = int(cb[-1]), len(lens)
+    st = _lib.stream_ptr()
+    lr_dev = torch.full((1,), 0.37, device="cuda")
+
+    def fresh():
+        gg = torch.Generator(device="cuda").manual_seed(78)
+        param = torch.randn(n, device="cuda", generator=gg)
+        grad = torch.randn(n, device="cuda", generator=gg) * 1e-3
+        grad[cb[3]:cb[4]] = 0.0                                          # an all-zero channel: scale floor 1e-8
+        ec = torch.randn(n, device="cuda", generator=gg) * 1e-5 if with_ec else None
+        return param, grad, ec, torch.zeros(C, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(C, device="cuda")
+
+    p1, g1, e1, sl1, co1, sm1 = fresh()
+    _lib.check(lib.dqrm_dense_grad_scale(g1.data_ptr(), _lib.ptr(e1), cb.data_ptr(), C, 8, sl1.data_ptr(), st), "scale")
+    _lib.check(lib.dqrm_dense_grad_quant(g1.data_ptr(), cb.data_ptr(), C, sl1.data_ptr(), 1.0, 8, co1.data_ptr(),
+                                         sm1.data_ptr(), st), "quant")
+    _lib.check(lib.dqrm_dense_apply(p1.data_ptr(), co1.data_ptr(), cb.data_ptr(), C, sm1.data_ptr(), 1.0, 0.0,
+                                    lr_dev.data_ptr(), g1.data_ptr() if with_ec else None, _lib.ptr(e1), st), "apply")
+    p2, g2, e2, sl2, co2, sm2 = fresh()
+    _lib.check(lib.dqrm_dense_quant_apply_local(p2.data_ptr(), g2.data_ptr(), _lib.ptr(e2), cb.data_ptr(), C, 8,
+                                                sl2.data_ptr(), co2.data_ptr(), sm2.data_ptr(), 0.0, lr_dev.data_ptr(), st),
+               "fused")
+    torch.cuda.synchronize()
+    for a, b, what in ((p1, p2, "param"), (g1, g2, "grad"), (sl1, sl2, "scale_local"), (co1, co2, "codes"), (sm1, sm2, "scale_mean")):
+        assert torch.equal(a, b), what
+    if with_ec:
+        assert torch.equal(e1, e2)
+    assert float(co1.abs().max()) == 127.0
