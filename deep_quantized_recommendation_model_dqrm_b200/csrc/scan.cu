@@ -139,13 +139,9 @@ extern "C" int dqrm_table_absmax_scale(int num_tables, const float* const* weigh
   }();
   long long grid = tiles < (long long)kSMs * ctas_per_sm ? tiles : (long long)kSMs * ctas_per_sm;
   if (grid < 1) grid = 1;
-  // The pass streams every byte once (no L1 reuse), so it asks for the LARGEST shared-memory carve-out: an SM's
-  // L1/shared split can only change while the SM is empty, and with the default (max L1) split a kernel that needs
-  // shared memory -- the bottom-MLP GEMMs that run beside this pass -- waited ~290 us for the pass to drain
-  // (measured, profiles/r02_timeline_overlap_*.txt).
-  static const cudaError_t carve = cudaFuncSetAttribute(table_absmax_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                        (int)cudaSharedmemCarveoutMaxShared);
-  (void)carve;
+  // (Measured, not adopted: asking for the max shared-memory carve-out so that kernels needing shared memory could
+  // become resident beside the pass -- an SM's L1/shared split only changes while the SM is empty -- cuts the pass to
+  // 5.5 TB/s, and the co-running latency-bound kernels crawl under the saturated memory system: DESIGN.md 5b.)
   table_absmax_kernel<<<(unsigned)grid, kScanThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       a, acc, counter, absmax, scale, inv_scale, bits, (int)tiles);
   DQRM_LAUNCH_CHECK("table_absmax_kernel");

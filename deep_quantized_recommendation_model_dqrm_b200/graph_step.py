@@ -82,16 +82,18 @@ class GraphedTrainStep:
         dlrm.external_scan = True
         self.graph = self.graph_b = self.graph_pre = None
         self._xb = None
-        # The bottom MLP (and the MLP weight fake-quantisation) does not depend on the table scales: when the scan is
-        # long enough to hide them (>= 400 MB per rank ~ 60 us at HBM speed) they are captured into their OWN linear
-        # graph and replayed on a second stream beside the scan kernel -- which launches 4 of its 8 possible CTAs per
-        # SM for exactly this reason (csrc/scan.cu).  Below the tensor-core batch threshold the layers take the
-        # serial-slice FFMA kernel: the same bits as the cluster split-K kernel, but no cluster launch (a cluster grid
-        # was measured not to become co-resident with a long-running grid).
+        # The bottom MLP (and the MLP weight fake-quantisation) does not depend on the table scales, so they CAN be
+        # captured into their own linear graph and replayed on a second stream beside the scan kernel
+        # (DQRM_OVERLAP_BOTTOM=1, or =force regardless of the scan size; serial-slice FFMA forward: the bits of the
+        # cluster split-K kernel without a cluster launch).  Measured on B200 and OFF by default: with
+        # the scan's default L1/shared split the GEMMs cannot become resident before the pass drains (an SM's split only
+        # changes while it is empty: step 0.440 -> 0.453 ms), and with a shared-heavy split the pass drops to 5.5 TB/s
+        # while every dependent load of the co-running kernels sees the loaded HBM latency (fake-quant 4 -> 88 us, one
+        # 512x256 layer 24 -> 229 us: step 0.497 ms).
         from . import _lib as _l
         scan_rows = sum(int(w.shape[0]) for w in self.group.weights)
         scan_bytes = scan_rows * self.group.dim * 4 // (world_size if (world_size > 1 and dlrm.shard_scan) else 1)
-        mode = os.environ.get("DQRM_OVERLAP_BOTTOM", "1")          # 0: never, force: regardless of the scan size (tests)
+        mode = os.environ.get("DQRM_OVERLAP_BOTTOM", "0")          # 0: never (default), 1: long scans, force: always (tests)
         self.overlap_bottom = (use_graph and self.group.scale_policy == "full" and mode != "0" and
                                (scan_bytes >= 400_000_000 or mode == "force") and
                                X.shape[0] <= dlrm.fuse_mlp_max_batch and dlrm._fused_mlp_arena() is not None)
