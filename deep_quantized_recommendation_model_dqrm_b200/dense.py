@@ -75,6 +75,13 @@ class DenseArena:
         import os
         self.side_stream = torch.cuda.Stream(device=device, priority=-1) \
             if (self.flat.is_cuda and not os.environ.get("DQRM_NO_SIDE_STREAM")) else None
+        # the 7 weight-gradient GEMMs are independent of each other (each needs only its layer's dout): two more
+        # streams, used round-robin, let one start the moment its dout exists instead of queueing behind the previous
+        # layer's (on ONE side stream they had become the step's critical path: 55 us back to back at batch 128)
+        n_side = max(1, min(4, int(os.environ.get("DQRM_DW_STREAMS", "3"))))
+        self.side_streams = ([self.side_stream] + [torch.cuda.Stream(device=device, priority=-1) for _ in range(n_side - 1)]) \
+            if self.side_stream is not None else []
+        self._side_rr = 0
         self.keepalive = []
         for l in self.layers:
             l._arena = self
@@ -93,6 +100,7 @@ class DenseArena:
         self.lr_dev = None                 # device fp32 [1]: when set, apply() reads the learning rate from it
         self.fuse_local = False            # world 1: quantize_exchange() + apply() as ONE launch (graph_step sets it)
         self._local_pending = None
+        self.lazy_zero = False             # zero_grad() only marks the layers clean (see zero_grad)
         self._bind_scale_views()
 
     def _bind_scale_views(self):
@@ -142,12 +150,27 @@ class DenseArena:
     def join(self):
         """Make the current stream wait for the side-stream weight-gradient kernels of this step."""
         if self.side_stream is not None and self.keepalive:
-            torch.cuda.current_stream().wait_stream(self.side_stream)
+            cur = torch.cuda.current_stream()
+            for st in self.side_streams:
+                cur.wait_stream(st)
             self.keepalive.clear()
+            self._side_rr = 0
+
+    def next_side_stream(self):
+        """Stream for the next weight-gradient GEMM (None: run it in line)."""
+        if self.side_stream is None:
+            return None
+        st = self.side_streams[self._side_rr % len(self.side_streams)]
+        self._side_rr += 1
+        return st
 
     def zero_grad(self):
+        """clear_gradients() for the MLP arena.  The fused backward OVERWRITES a clean layer's gradient (accumulate = 0),
+        so when every layer's fused backward is known to run before the gradients are read (graph_step sets
+        `lazy_zero`), marking the layers clean is all there is to do: no fill kernel in the step."""
         self.join()
-        self.flat_grad.zero_()
+        if not self.lazy_zero:
+            self.flat_grad.zero_()
         for l in self.layers:
             l._grad_dirty = False
 

@@ -63,6 +63,8 @@ class GraphedTrainStep:
         _arena_of(dlrm).lr_dev = self.lr_dev
         # one rank: nothing to exchange between the MLP gradient quantisation and the update -> one launch, same bits
         _arena_of(dlrm).fuse_local = world_size == 1 and os.environ.get("DQRM_FUSE_LOCAL_DENSE", "1") != "0"
+        # every step runs the fused backward of all 7 layers, which overwrites clean gradients: no zero-fill launch
+        _arena_of(dlrm).lazy_zero = X.shape[0] <= dlrm.fuse_mlp_max_batch and dlrm._fused_mlp_arena() is not None
         self.pipelined = self.group.scale_policy == "pipelined"
         # row-sharded scan: the absmax exchange + scale are issued right before the embedding forward (inside the
         # graph, after the bottom MLP) instead of right behind the scan -- its round trip is off the critical path
@@ -73,6 +75,10 @@ class GraphedTrainStep:
                                      os.environ.get("DQRM_EAGER_EXCHANGE", "1") != "0")
         # ... and the de-duplicating backward kernel itself: the bottom-MLP backward does not depend on it
         self.group.side_backward = not self.pipelined and os.environ.get("DQRM_SIDE_BACKWARD", "1") != "0"
+        # ... and, behind the exchange on that stream, the row update (lr comes from lr_dev)
+        self.group.eager_apply = (self.group.side_backward and self.group.grad_bit == grad_bits and
+                                  (world_size == 1 or self.group.eager_exchange) and
+                                  os.environ.get("DQRM_EAGER_APPLY", "1") != "0")
         self.stream = torch.cuda.Stream(device=dev, priority=-1)
         if self.pipelined:
             # measured on B200: a graph with forked branches is not co-scheduled with the side-stream pass (its

@@ -243,7 +243,7 @@ class _FusedQuantLinearFunction(Function):
                 in_f, ctx.act)
         wg, bg = m.weight.grad.data_ptr(), _lib.ptr(m.bias.grad if m.bias is not None else None)
         arena = getattr(m, "_arena", None)
-        side = arena.side_stream if arena is not None else None
+        side = arena.next_side_stream() if arena is not None else None
         if side is None:
             rc = lib.dqrm_linear_bwd(*args, _lib.ptr(dx), wg, bg, accumulate, _lib.linear_path, _lib.stream_ptr())
             _lib.check(rc, "dqrm_linear_bwd")

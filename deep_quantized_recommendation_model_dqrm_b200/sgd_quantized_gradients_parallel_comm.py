@@ -102,9 +102,22 @@ def grad_update_parallel_comm(model, number_of_gpus, emb_grad_quantized=True, nu
     if world != number_of_gpus:
         raise ValueError(f"number_of_gpus={number_of_gpus} but the process group has {world} ranks")
     with torch.no_grad():
-        for g in _emb_groups(model):
+        groups = _emb_groups(model)
+        arena = _dense_arena(model)
+        if groups and arena.status is not groups[0].status:
+            arena.status = groups[0].status          # ONE status word: a timeout on any site stops every update
+        # a group whose backward (and exchange) already runs on its side stream (graph_step: backward_async) is joined
+        # AFTER the dense exchange has been issued: the two do not depend on each other, and inside a captured graph
+        # the position of the join is the dependency
+        running = [g for g in groups if emb_grad_quantized and g.grad_bit == num_bits and
+                   (g.exchange_started or g._bwd_forked is not None)]
+        for g in groups:
+            if g in running:
+                continue
             if emb_grad_quantized:
-                started = g.finish_exchange()        # already running on the side stream (graph_step eager mode)
+                started = g.finish_exchange()        # (a side-stream run with another code width: join, redo)
+                if g.applied_eagerly:
+                    raise RuntimeError("embedding update already applied with a different gradient bit width")
                 if g.grad_bit != num_bits:
                     g.set_grad_bit(num_bits)
                     started = False
@@ -115,14 +128,19 @@ def grad_update_parallel_comm(model, number_of_gpus, emb_grad_quantized=True, nu
                         e.emb_scaling_factor = g.grad_scale_mean[t:t + 1]
             elif world > 1:
                 # emb_grad_quantized=False (sgd:319-329): same slots, fp32 payload, summed in rank order
+                g.finish_exchange()
                 if g.grad_bit != 32:
                     g.set_grad_bit(32)
                 g.exchange(world=world, rank=rank)
-        arena = _dense_arena(model)
-        groups = _emb_groups(model)
-        if groups and arena.status is not groups[0].status:
-            arena.status = groups[0].status          # ONE status word: a timeout on any site stops every update
+            else:
+                g.finish_exchange()
         arena.quantize_exchange(world=world, bits=8, quantized=mlp_layer_quantized)
+        for g in running:
+            if not g.finish_exchange():
+                g.exchange(world=world, rank=rank)
+            if g.modules is not None:
+                for t, e in enumerate(g.modules):
+                    e.emb_scaling_factor = g.grad_scale_mean[t:t + 1]
 
 
 def weight_update_parallel_comm(model, lr, emb_grad_quantized=True, update_embedding=True, num_gpus=1,
@@ -131,9 +149,14 @@ def weight_update_parallel_comm(model, lr, emb_grad_quantized=True, update_embed
     if ranking_range or use_ec:
         raise NotImplementedError("ranking_range / error compensation are not called by the reference drivers")
     with torch.no_grad():
+        for g in _emb_groups(model):
+            if g.applied_eagerly and not (update_embedding and emb_grad_quantized):
+                raise RuntimeError("the embedding update already ran behind the exchange (eager_apply)")
         if update_embedding:
             for g in _emb_groups(model):
-                if emb_grad_quantized or num_gpus > 1:
+                if g.applied_eagerly:                # done on the side stream, joined by grad_update_parallel_comm
+                    g.applied_eagerly = False
+                elif emb_grad_quantized or num_gpus > 1:
                     g.merge_apply(lr)
                 else:
                     g.sgd_apply(lr, inv_world=1.0)

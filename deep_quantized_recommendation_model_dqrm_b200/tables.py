@@ -83,6 +83,8 @@ class EmbeddingTableGroup:
         self.eager_exchange = False  # start the embedding exchange from inside the backward, on xchg_stream
         self.side_backward = False   # run the de-duplicating backward itself on xchg_stream (graph_step sets it)
         self._bwd_forked = None
+        self.eager_apply = False     # ... and merge_apply() right behind the exchange, on the same stream
+        self.applied_eagerly = False
         self.xchg_stream = None
         self.exchange_started = False
         self.dp_world, self.dp_rank = 1, 0
@@ -608,6 +610,12 @@ class EmbeddingTableGroup:
             if self.dp_world == 1 or self.eager_exchange:
                 self.exchange(world=self.world, rank=self.dp_rank)
                 self.exchange_started = True
+                if self.eager_apply and self.lr_dev is not None:
+                    # ... and the row update itself (learning rate read from lr_dev): nothing else in the step touches
+                    # the tables any more, so it need not wait for the dense exchange on the main stream.
+                    # weight_update_parallel_comm() sees applied_eagerly and skips this group.
+                    self.merge_apply(0.0)
+                    self.applied_eagerly = True
         self._bwd_forked = dout
 
     def finish_exchange(self):

@@ -1,0 +1,7 @@
+#!/bin/bash
+O=gpurun_out/r2_34; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 > $O/tests.log
+timeout 600 python bench.py --no-cpu-baseline > $O/bench.json 2> $O/bench.err
+DQRM_DW_STREAMS=1 timeout 600 python bench.py --no-cpu-baseline --no-extras > $O/bench_dw1.json 2> $O/bench_dw1.err
+DQRM_DW_STREAMS=2 timeout 600 python bench.py --no-cpu-baseline --no-extras > $O/bench_dw2.json 2> $O/bench_dw2.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29533 tools/mgpu_timeline.py > $O/timeline_n1.txt 2>&1
