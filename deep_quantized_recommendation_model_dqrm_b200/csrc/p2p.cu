@@ -62,11 +62,16 @@ p2p_allgather_kernel(const __grid_constant__ PeerPtrs peers, int world, int rank
   const size_t my_off = data_off + (size_t)rank * slot_bytes;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
   const uint4* src = reinterpret_cast<const uint4*>(local + my_off);        // slot_bytes is a multiple of 16
-  for (size_t i = tid; i < (slot_bytes >> 4); i += nthr) {
-    const uint4 v = src[i];
+  const size_t n16 = slot_bytes >> 4;
+  for (size_t i0 = tid; i0 < n16; i0 += 4 * nthr) {        // four 128-bit loads in flight, then the remote stores
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const size_t i = i0 + j * nthr; v[j] = src[i < n16 ? i : n16 - 1]; }
     for (int k = 1; k < world; ++k) {
       const int p = (rank + k) % world;      // every rank starts on a different peer
-      reinterpret_cast<uint4*>(peers.base[p] + my_off)[i] = v;
+      uint4* dst = reinterpret_cast<uint4*>(peers.base[p] + my_off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const size_t i = i0 + j * nthr; if (i < n16) dst[i] = v[j]; }
     }
   }
   __threadfence_system();                    // my remote stores are ordered before anything I signal later
@@ -250,8 +255,8 @@ extern "C" int dqrm_p2p_allgather(void* const* peer_base, int world, int rank, s
   }
   size_t flag_off, data_off, stride;
   dqrm_p2p_site_layout(world, slot_bytes, &flag_off, &data_off, &stride);
-  long long grid = ceil_div((long long)stride * (world - 1), 32 * 1024);      // ~32 KiB of remote stores per CTA
-  if (grid > 64) grid = 64;
+  long long grid = ceil_div((long long)stride, 16 * 1024);                    // one trip of the 4-deep copy loop per CTA
+  if (grid > kSMs) grid = kSMs;
   if (grid < 1) grid = 1;
   p2p_allgather_kernel<<<(unsigned)grid, kP2PThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       pp, world, rank, site_off, site_off + flag_off, site_off + data_off, stride, p2p_timeout_cycles(), status);

@@ -69,6 +69,10 @@ class GraphedTrainStep:
         # row-sharded scan: the absmax exchange + scale are issued right before the embedding forward (inside the
         # graph, after the bottom MLP) instead of right behind the scan -- its round trip is off the critical path
         self.group.defer_scan_reduce = world_size > 1 and self.group.scale_policy == "full"
+        # better still (graph replays): the exchange runs on its own stream BESIDE the bottom MLP, which is replayed
+        # from its own small graph between the scan launch and the join (pre_mode "after_scan", below)
+        self.group.side_scan_reduce = (self.group.defer_scan_reduce and use_graph and dlrm.shard_scan and
+                                       os.environ.get("DQRM_SIDE_SCAN_REDUCE", "1") != "0")
         # multi-rank: launch the embedding exchange from inside the backward (side stream), overlapping the two
         # all-gathers + pack with the bottom-MLP backward; grad_update_parallel_comm then only joins
         self.group.eager_exchange = (world_size > 1 and self.group.grad_bit == grad_bits and not self.pipelined and
@@ -87,6 +91,7 @@ class GraphedTrainStep:
             _dense_arena(dlrm).side_stream = None
         dlrm.external_scan = True
         self.graph = self.graph_b = self.graph_pre = None
+        self.scan_in_graph = False
         self._xb = None
         # The bottom MLP (and the MLP weight fake-quantisation) does not depend on the table scales, so they CAN be
         # captured into their own linear graph and replayed on a second stream beside the scan kernel
@@ -103,6 +108,10 @@ class GraphedTrainStep:
         self.overlap_bottom = (use_graph and self.group.scale_policy == "full" and mode != "0" and
                                (scan_bytes >= 400_000_000 or mode == "force") and
                                X.shape[0] <= dlrm.fuse_mlp_max_batch and dlrm._fused_mlp_arena() is not None)
+        self.pre_after_scan = (self.group.side_scan_reduce and not self.overlap_bottom and
+                               X.shape[0] <= dlrm.fuse_mlp_max_batch and dlrm._fused_mlp_arena() is not None)
+        if not self.pre_after_scan:
+            self.group.side_scan_reduce = False
         if self.overlap_bottom:
             self.pre_stream = torch.cuda.Stream(device=dev, priority=-1)
             self._pre_done = torch.cuda.Event()
@@ -133,16 +142,22 @@ class GraphedTrainStep:
                     self.graph_b = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self.graph_b, pool=self.graph.pool(), stream=self.stream):
                         self._body_b()
-                elif self.overlap_bottom:
+                elif self.overlap_bottom or self.pre_after_scan:
                     self.graph_pre = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(self.graph_pre, stream=self.pre_stream):
+                    with torch.cuda.graph(self.graph_pre, stream=self.pre_stream if self.overlap_bottom else self.stream):
                         self._xb = self.dlrm.forward_bottom(self.X)
+                    self.group.finish_scan()              # (pre_after_scan: join the eager absmax exchange)
                     with torch.cuda.graph(self.graph, pool=self.graph_pre.pool(), stream=self.stream):
                         self._body_a()                    # forward(x_bottom=self._xb): the rest of the step
                         self._body_b()
                     self._xb = None
                 else:
+                    # DQRM_SCAN_IN_GRAPH=1 (experiment): the scan kernel as the first node of the step graph, so no graph
+                    # launch sits between it and the forward (bench.py then cannot bracket it with events)
+                    self.scan_in_graph = world_size == 1 and os.environ.get("DQRM_SCAN_IN_GRAPH", "0") == "1"
                     with torch.cuda.graph(self.graph, stream=self.stream):
+                        if self.scan_in_graph:
+                            self.scan()
                         self._body_a()
                         self._body_b()
                 torch.cuda.synchronize()
@@ -218,7 +233,13 @@ class GraphedTrainStep:
 
     def run(self, events=None):
         """scan + (graph replay | eager body); returns the device loss tensor (no sync)."""
-        if self.graph_pre is not None:
+        if self.graph_pre is not None and self.pre_after_scan:
+            # row-sharded scan: scan kernel -> [absmax exchange + scale on scan_stream] beside [fake-quant + bottom MLP
+            # replayed here] -> join -> the rest of the step
+            self.scan(events)
+            self.graph_pre.replay()
+            self.group.finish_scan()
+        elif self.graph_pre is not None:
             # fake-quant + bottom MLP on their own stream, beside the scan: ordered after everything already queued on
             # the current stream (the previous step's update, this step's input copy), joined before the replay
             cur = torch.cuda.current_stream()
@@ -228,8 +249,10 @@ class GraphedTrainStep:
                 self._pre_done.record()
             self.scan(events)
             cur.wait_event(self._pre_done)
-        else:
+        elif not self.scan_in_graph:
             self.scan(events)
+        elif events is not None:                                    # (no kernel in between: reads as 0)
+            events[0].record(); events[1].record()
         self.replay()
         return self.loss
 

@@ -96,6 +96,8 @@ class EmbeddingTableGroup:
         self.lr_dev = None                 # device fp32 [1]: when set, the update kernels read the learning rate from it
         self.defer_scan_reduce = False     # sharded scan: leave the MAX over ranks to finish_scan() (called by forward)
         self._scan_reduce_pending = None
+        self.side_scan_reduce = False      # ... or run it on scan_stream right behind the scan kernel (graph_step)
+        self.scan_stream = None
 
     # ---- helpers --------------------------------------------------------
     def _wptrs(self):
@@ -288,7 +290,17 @@ class EmbeddingTableGroup:
             events[1].record()
         _lib.check(rc, "dqrm_table_absmax_scale")
         if sharded:
-            if self.defer_scan_reduce:
+            if self.side_scan_reduce:
+                # the absmax exchange + scale on their own stream, right behind the scan kernel: they run beside the
+                # bottom MLP and cost the step nothing; finish_scan() (before the embedding forward) joins
+                cur = torch.cuda.current_stream()
+                if self.scan_stream is None:
+                    self.scan_stream = torch.cuda.Stream(device=self.device, priority=-1)
+                self.scan_stream.wait_stream(cur)
+                with torch.cuda.stream(self.scan_stream):
+                    self._allreduce_absmax_to_scale(process_group)
+                self._scan_reduce_pending = "side"
+            elif self.defer_scan_reduce:
                 # the cross-rank MAX + scale only has to be done before the embedding forward: the bottom MLP runs in
                 # between (dlrm_s_pytorch_comm_grad.py:855-857), which hides this exchange's round trip and rank skew
                 self._scan_reduce_pending = (process_group,)
@@ -298,7 +310,10 @@ class EmbeddingTableGroup:
 
     def finish_scan(self):
         """Complete a row-sharded scan whose cross-rank reduction was deferred (defer_scan_reduce)."""
-        if self._scan_reduce_pending is not None:
+        if self._scan_reduce_pending == "side":
+            self._scan_reduce_pending = None
+            torch.cuda.current_stream().wait_stream(self.scan_stream)
+        elif self._scan_reduce_pending is not None:
             (pg,), self._scan_reduce_pending = self._scan_reduce_pending, None
             self._allreduce_absmax_to_scale(pg)
 
