@@ -51,6 +51,8 @@ class GraphedTrainStep:
         for v, src in zip(views, (X, lS_o, lS_i, T)):
             v.copy_(src)
         self.loss = torch.zeros((), device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self._copy_done, self._copy_pending = torch.cuda.Event(), False
         # the learning rate lives in device memory: the update kernels read it at run time, so set_lr() takes effect on
         # the next replay of the captured graph (LRPolicyScheduler warm-up / decay without re-capture)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
@@ -218,8 +220,21 @@ class GraphedTrainStep:
         return buf
 
     def load_packed(self, packed):
-        """Refill all static inputs with ONE (H2D or D2D) copy of a pack_host()-shaped buffer; asynchronous."""
-        self._stage.copy_(packed, non_blocking=True)
+        """Refill all static inputs with ONE (H2D or D2D) copy of a pack_host()-shaped buffer; asynchronous.
+        The copy is issued on a copy stream, ordered after everything queued on the current stream (the previous step
+        still reads the inputs) -- the table scan that run() launches next does not need the batch, so the transfer
+        (a PCIe round trip from pinned host memory) hides behind it; run() joins before the first consumer."""
+        cur = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.copy_stream):
+            self._stage.copy_(packed, non_blocking=True)
+            self._copy_done.record()
+        self._copy_pending = True
+
+    def _join_copy(self):
+        if self._copy_pending:
+            torch.cuda.current_stream().wait_event(self._copy_done)
+            self._copy_pending = False
 
     def replay(self):
         """Everything after the scan launch, on the current stream."""
@@ -237,9 +252,11 @@ class GraphedTrainStep:
             # row-sharded scan: scan kernel -> [absmax exchange + scale on scan_stream] beside [fake-quant + bottom MLP
             # replayed here] -> join -> the rest of the step
             self.scan(events)
+            self._join_copy()
             self.graph_pre.replay()
             self.group.finish_scan()
         elif self.graph_pre is not None:
+            self._join_copy()
             # fake-quant + bottom MLP on their own stream, beside the scan: ordered after everything already queued on
             # the current stream (the previous step's update, this step's input copy), joined before the replay
             cur = torch.cuda.current_stream()
@@ -253,6 +270,7 @@ class GraphedTrainStep:
             self.scan(events)
         elif events is not None:                                    # (no kernel in between: reads as 0)
             events[0].record(); events[1].record()
+        self._join_copy()
         self.replay()
         return self.loss
 
