@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqrm_b200.so")
 
 MAX_TABLES = 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 BWD_CTA_MAX_LOOKUPS = 16384
 STATUS_INDEX_RANGE, STATUS_OFFSET_ORDER, STATUS_CAPACITY, STATUS_P2P_TIMEOUT = 1, 2, 4, 8
 
@@ -72,6 +72,10 @@ SIGNATURES = {
     "dqrm_dense_grad_quant_gathered": (_i32, [_p, _p, _i32, _p, _sz, _i32, _i32, _p, _p, _p]),
     "dqrm_dense_apply_gathered": (_i32, [_p, _p, _sz, _i32, _p, _i32, _p, _f32, _p, _p, _p, _p, _p]),
     "dqrm_scale_from_absmax_gathered": (_i32, [_i32, _p, _sz, _i32, _i32, _p, _p, _p, _p]),
+    "dqrm_dense_exchange_smem_bytes": (_sz, [_i32, _i32]),
+    "dqrm_dense_exchange_debug": (_i32, [_p]),
+    "dqrm_dense_exchange_apply": (_i32, [_p, _i32, _i32, _sz, _sz, _sz, _sz, _sz, _sz, _p, _p, _p, _p, _p, _i32, _i32, _i32,
+                                         _i32, _p, _p, _f32, _p, _p, _p]),
 }
 
 LINEAR_AUTO, LINEAR_FFMA, LINEAR_TC, LINEAR_FFMA_SERIAL = 0, 1, 2, 3
@@ -90,7 +94,7 @@ LAUNCHING = ("dqrm_table_absmax_scale", "dqrm_scale_from_absmax", "dqrm_embbag_f
              "dqrm_shadow_refresh", "dqrm_shadow_update_rows", "dqrm_embbag_fwd_shadow",
              "dqrm_dense_grad_scale", "dqrm_dense_grad_quant", "dqrm_dense_apply", "dqrm_dense_quant_apply_local",
              "dqrm_bce_loss_grad", "dqrm_p2p_allgather", "dqrm_dense_grad_quant_gathered", "dqrm_dense_apply_gathered",
-             "dqrm_scale_from_absmax_gathered")
+             "dqrm_scale_from_absmax_gathered", "dqrm_dense_exchange_apply")
 launch_counts = {}
 
 

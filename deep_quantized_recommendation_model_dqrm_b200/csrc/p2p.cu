@@ -52,6 +52,12 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ctl = {counter, arrive, -, -} (local), flags = world x u32 (written by peers), data = world x slot_bytes
 __global__ void __launch_bounds__(kP2PThreads)
 p2p_allgather_kernel(const __grid_constant__ PeerPtrs peers, int world, int rank, size_t ctl_off, size_t flag_off,
@@ -74,25 +80,28 @@ p2p_allgather_kernel(const __grid_constant__ PeerPtrs peers, int world, int rank
       for (int j = 0; j < 4; ++j) { const size_t i = i0 + j * nthr; if (i < n16) dst[i] = v[j]; }
     }
   }
-  __threadfence_system();                    // my remote stores are ordered before anything I signal later
+  // One system-scope fence per CTA, not per thread: the barrier orders every thread's remote stores before thread 0's
+  // fence, which is cumulative (the pattern of a cooperative grid barrier); 256 threads x fence.sys cost 2-4 us a piece.
   __syncthreads();
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
-    __threadfence_system();                  // release side of the arrive counter, in the thread that bumps it
-    s_last = (atomicAdd(&ctl[1], 1u) == gridDim.x - 1);
+    s_last = true;
+    if (gridDim.x > 1) {
+      __threadfence_system();                // release side of the arrive counter, in the thread that bumps it
+      s_last = (atomicAdd(&ctl[1], 1u) == gridDim.x - 1);
+      __threadfence();                       // acquire side: the other CTAs' fences happened before their arrivals
+    }
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();
-  if (threadIdx.x < world && threadIdx.x != rank)
-    st_release_sys(reinterpret_cast<unsigned*>(peers.base[threadIdx.x] + flag_off) + rank, seq);
   if (threadIdx.x < world && threadIdx.x != rank) {
+    st_release_sys(reinterpret_cast<unsigned*>(peers.base[threadIdx.x] + flag_off) + rank, seq);   // (release: cumulative)
     const unsigned* f = reinterpret_cast<const unsigned*>(local + flag_off) + threadIdx.x;
     const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(f) - seq) < 0) {
+    while ((int)(ld_relaxed_sys(f) - seq) < 0) {
       if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) { atomicOr(status, DQRM_STATUS_P2P_TIMEOUT); break; }
-      __nanosleep(64);
     }
+    (void)ld_acquire_sys(f);
   }
   __syncthreads();
   if (threadIdx.x == 0) { ctl[1] = 0u; ctl[0] = seq; }

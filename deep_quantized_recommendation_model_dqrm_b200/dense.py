@@ -100,6 +100,11 @@ class DenseArena:
         self.lr_dev = None                 # device fp32 [1]: when set, apply() reads the learning rate from it
         self.fuse_local = False            # world 1: quantize_exchange() + apply() as ONE launch (graph_step sets it)
         self._local_pending = None
+        # world > 1 over NVLink: scale -> exchange -> quantise -> exchange -> update as ONE launch issued by apply()
+        # (csrc/dense_xchg.cu; graph_step sets it -- between the two calls scale_mean is not up to date yet)
+        self.fuse_xchg = False             # (lr_dev set: issued by quantize_exchange() already, beside the embedding exchange)
+        self._xchg_pending = None
+        self._xchg_plan = None
         self.lazy_zero = False             # zero_grad() only marks the layers clean (see zero_grad)
         self._bind_scale_views()
 
@@ -174,6 +179,32 @@ class DenseArena:
         for l in self.layers:
             l._grad_dirty = False
 
+    def xchg_partition(self, num_ctas=None):
+        """Contiguous runs of channels for the CTAs of the one-kernel exchange, balanced by elements + a per-channel
+        cost; the same on every rank (pure function of the layer shapes).  -> (cta_chan list, max elems, max chans)"""
+        cb = self.chan_begin.cpu().tolist()
+        cost = [cb[c + 1] - cb[c] + 24 for c in range(self.num_chan)]
+        tot = sum(cost)
+        if num_ctas is None:
+            num_ctas = max(1, min(148, tot // 2048))
+        num_ctas = max(1, min(int(num_ctas), self.num_chan))
+        pre = [0]
+        for x in cost:
+            pre.append(pre[-1] + x)
+        import bisect
+        cuts = [0]
+        for b in range(1, num_ctas):                              # cut b at the channel boundary nearest b/num_ctas
+            target = tot * b / num_ctas
+            c = bisect.bisect_left(pre, target)
+            if c > 0 and target - pre[c - 1] < pre[min(c, self.num_chan)] - target:
+                c -= 1
+            c = min(max(c, cuts[-1] + 1), self.num_chan - (num_ctas - b))    # every CTA owns at least one channel
+            cuts.append(c)
+        cuts.append(self.num_chan)
+        elems = max(cb[cuts[b + 1]] - cb[cuts[b]] for b in range(num_ctas))
+        chans = max(cuts[b + 1] - cuts[b] for b in range(num_ctas))
+        return cuts, elems, chans
+
     def _ensure_slots(self, world):
         """Per-rank slots of the two MLP exchange sites (channel scales fp32, codes int8): views of this rank's peer
         arena (NVLink form, collective on first use) or plain device buffers gathered by NCCL.  Same layout, same
@@ -186,8 +217,9 @@ class DenseArena:
         a = None
         if live and _p2p.backend() == "p2p":
             try:
-                a = _p2p.PeerArena({"mlp_scale": self.num_chan * 4, "mlp_codes": self.total}, world, dist.get_rank(),
-                                   self.device)
+                cuts, elems, chans = self.xchg_partition()
+                a = _p2p.PeerArena({"mlp_scale": self.num_chan * 4, "mlp_codes": self.total,
+                                    "mlp_xflag": 2 * (len(cuts) - 1) * 4}, world, dist.get_rank(), self.device)
             except _p2p.P2PUnavailable as e:         # raised on every rank together
                 _p2p.fall_back_to_nccl(e)
         if a is not None:
@@ -195,6 +227,7 @@ class DenseArena:
             self._scale_slots = a.slots("mlp_scale", torch.float32)
             self._code_slots = a.slots("mlp_codes", torch.int8)
             rank = a.rank
+            self.bind_xchg(a, cuts, elems, chans)
         else:
             pad = lambda n: (n + 15) // 16 * 16
             self._scale_slots = torch.zeros((world, pad(self.num_chan * 4) // 4), dtype=torch.float32, device=self.device)
@@ -204,9 +237,31 @@ class DenseArena:
         self.scale_local = self._scale_slots[rank, :self.num_chan]
         self._codes_mine = self._code_slots[rank, :self.total]
 
+    def bind_xchg(self, arena, cuts, elems, chans):
+        """Plan of the one-kernel exchange on `arena` (sites mlp_scale / mlp_codes / mlp_xflag): the per-CTA channel
+        runs and the device-side sequence numbers (zero like the fresh arena's flags)."""
+        self._xchg_plan = dict(arena=arena, num_ctas=len(cuts) - 1, elems=int(elems), chans=int(chans),
+                               cta_chan=torch.tensor(cuts, dtype=torch.int32, device=self.device),
+                               seq=torch.zeros(len(cuts) - 1, dtype=torch.int32, device=self.device))
+
+    def exchange_apply_fused(self, lr, bits=8):
+        """quantize_exchange() + apply() of a multi-rank step in ONE launch (csrc/dense_xchg.cu); bit-identical to
+        local_scale -> all-gather -> dqrm_dense_grad_quant_gathered -> all-gather -> dqrm_dense_apply_gathered."""
+        pl = self._xchg_plan
+        a = pl["arena"]
+        sc, co, fl = a.sites["mlp_scale"], a.sites["mlp_codes"], a.sites["mlp_xflag"]
+        rc = self.lib.dqrm_dense_exchange_apply(a.ptrs, a.world, a.rank, sc["data_off"], sc["stride"], co["data_off"],
+                                                co["stride"], fl["data_off"], fl["stride"], self.flat.data_ptr(),
+                                                self.flat_grad.data_ptr(), self._ec_ptr(), self.chan_begin.data_ptr(),
+                                                pl["cta_chan"].data_ptr(), pl["num_ctas"], pl["elems"], pl["chans"],
+                                                int(bits), self.scale_mean.data_ptr(), pl["seq"].data_ptr(), float(lr),
+                                                _lib.ptr(self.lr_dev), self.status.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "dqrm_dense_exchange_apply")
+
     def release(self):
         """Close the MLP exchange arena (barrier first: no rank may still be storing into it).  Collective."""
         a, self.p2p = self.p2p, None
+        self._xchg_plan = None
         if a is None:
             return
         import torch.distributed as dist
@@ -244,6 +299,16 @@ class DenseArena:
         live = world > 1 and dist.is_available() and dist.is_initialized() and dist.get_world_size() == world
         if live and bits <= 8:
             self._ensure_slots(world)
+            if self.fuse_xchg and self.p2p is not None and self._xchg_plan is not None:
+                # the whole exchange + update in ONE launch.  With the learning rate in device memory it is issued HERE
+                # (grad_update_parallel_comm: before the embedding streams are joined, so it runs beside the embedding
+                # exchange) and apply() has nothing left to do; otherwise apply() issues it with its lr argument.
+                if self.lr_dev is not None:
+                    self.exchange_apply_fused(0.0, bits)
+                    self._xchg_pending = "done"
+                else:
+                    self._xchg_pending = bits
+                return
             self.local_scale(bits)                                  # -> this rank's slot of the scale site
             self._allgather("mlp_scale", self._scale_slots, process_group)
             rc = self.lib.dqrm_dense_grad_quant_gathered(self.flat_grad.data_ptr(), self.chan_begin.data_ptr(),
@@ -302,6 +367,12 @@ class DenseArena:
         """MLP half of weight_update_parallel_comm (sgd_quantized_gradients_parallel_comm.py:630-663)."""
         st = _lib.stream_ptr()
         ec = self._ec_ptr() if quantized else None
+        if self._xchg_pending is not None:
+            bits, self._xchg_pending = self._xchg_pending, None
+            assert quantized and world == self.slot_world
+            if bits != "done":
+                self.exchange_apply_fused(lr, bits)
+            return
         if self._local_pending is not None:
             bits, self._local_pending = self._local_pending, None
             assert quantized and world == 1

@@ -65,6 +65,9 @@ class GraphedTrainStep:
         _arena_of(dlrm).lr_dev = self.lr_dev
         # one rank: nothing to exchange between the MLP gradient quantisation and the update -> one launch, same bits
         _arena_of(dlrm).fuse_local = world_size == 1 and os.environ.get("DQRM_FUSE_LOCAL_DENSE", "1") != "0"
+        # N ranks over NVLink: the five launches of the dense exchange (scale, all-gather, quantise, all-gather, update)
+        # as ONE kernel whose CTAs synchronise pairwise with their peers (csrc/dense_xchg.cu), same bits
+        _arena_of(dlrm).fuse_xchg = world_size > 1 and os.environ.get("DQRM_FUSE_DENSE_XCHG", "1") != "0"
         # every step runs the fused backward of all 7 layers, which overwrites clean gradients: no zero-fill launch
         _arena_of(dlrm).lazy_zero = X.shape[0] <= dlrm.fuse_mlp_max_batch and dlrm._fused_mlp_arena() is not None
         self.pipelined = self.group.scale_policy == "pipelined"

@@ -140,3 +140,86 @@ def test_scale_from_gathered_absmax():
     sc2, inv2 = torch.zeros(T, device="cuda"), torch.zeros(T, device="cuda")
     _lib.check(lib.dqrm_scale_from_absmax(T, want.data_ptr(), 4, sc2.data_ptr(), inv2.data_ptr(), _lib.stream_ptr()), "plain")
     assert torch.equal(am, want) and torch.equal(sc, sc2) and torch.equal(inv, inv2)
+
+
+@pytest.mark.parametrize("world,num_ctas,ec", [(1, 3, False), (2, 5, False), (4, 7, True), (8, 4, False)])
+def test_one_kernel_dense_exchange_matches_the_five_launch_form(world, num_ctas, ec):
+    """dqrm_dense_exchange_apply (csrc/dense_xchg.cu: per-CTA pairwise flags, scales and int8 codes stored straight into
+    the peers' arenas) == dense_grad_scale -> gather -> dense_grad_quant_gathered -> gather -> dense_apply_gathered:
+    parameters, mean scales and error-compensation residuals bit-identical, over several replays (device-side
+    sequence numbers) -- W arenas in this process, the W ranks on W streams."""
+    import ctypes as C
+    from deep_quantized_recommendation_model_dqrm_b200 import _lib, p2p
+    from deep_quantized_recommendation_model_dqrm_b200.dense import DenseArena
+    lib = _lib.load()
+    rng = np.random.RandomState(11 + world)
+    sizes = [(64, 13), (64,), (48, 37), (48,), (16, 479), (16,), (1, 16), (1,)]       # odd row lengths: unaligned runs
+    chan, off = [0], 0
+    for s in sizes:
+        n = int(np.prod(s))
+        if len(s) == 2:
+            chan += [off + (r + 1) * s[1] for r in range(s[0])]
+        else:
+            chan.append(off + n)
+        off += n
+    total, nch = off, len(chan) - 1
+    chan_t = torch.tensor(chan, dtype=torch.int64, device="cuda")
+    plan = DenseArena.__new__(DenseArena)
+    plan.chan_begin, plan.num_chan = chan_t, nch
+    cuts, elems, chans = plan.xchg_partition(num_ctas)
+    G = len(cuts) - 1
+    cta_chan = torch.tensor(cuts, dtype=torch.int32, device="cuda")
+    arenas = p2p.PeerArena.local_group({"mlp_scale": nch * 4, "mlp_codes": total, "mlp_xflag": 2 * G * 4}, world)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    status = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    seq = [torch.zeros(G, dtype=torch.int32, device="cuda") for _ in range(world)]
+    param0 = torch.tensor(rng.randn(total).astype(np.float32), device="cuda")
+    pa = [param0.clone() for _ in range(world)]                     # five-launch form, per rank
+    pb = [param0.clone() for _ in range(world)]                     # one-kernel form
+    eca = [torch.zeros(total, device="cuda") for _ in range(world)] if ec else [None] * world
+    ecb = [torch.zeros(total, device="cuda") for _ in range(world)] if ec else [None] * world
+    mean_a = [torch.zeros(nch, device="cuda") for _ in range(world)]
+    mean_b = [torch.zeros(nch, device="cuda") for _ in range(world)]
+    st = _lib.stream_ptr
+    for it in range(4):
+        grads = [torch.tensor(rng.randn(total).astype(np.float32) * 10.0 ** rng.uniform(-4, 0), device="cuda")
+                 for _ in range(world)]
+        # ---- reference: the five-launch form on plain buffers
+        ga = [g.clone() for g in grads]
+        scales = torch.zeros((world, nch + 3), dtype=torch.float32, device="cuda")
+        stride = (total + 15) // 16 * 16 + 16
+        codes = torch.zeros((world, stride), dtype=torch.int8, device="cuda")
+        for r in range(world):
+            _lib.check(lib.dqrm_dense_grad_scale(ga[r].data_ptr(), _lib.ptr(eca[r]), chan_t.data_ptr(), nch, 8,
+                                                 scales[r].data_ptr(), st()), "scale")
+        for r in range(world):
+            _lib.check(lib.dqrm_dense_grad_quant_gathered(ga[r].data_ptr(), chan_t.data_ptr(), nch, scales.data_ptr(),
+                                                          scales.stride(0), world, 8, codes[r].data_ptr(),
+                                                          mean_a[r].data_ptr(), st()), "quant_g")
+        for r in range(world):
+            _lib.check(lib.dqrm_dense_apply_gathered(pa[r].data_ptr(), codes.data_ptr(), stride, world, chan_t.data_ptr(), nch,
+                                                     mean_a[r].data_ptr(), 0.1, None, ga[r].data_ptr() if ec else None,
+                                                     _lib.ptr(eca[r]), None, st()), "apply_g")
+        torch.cuda.synchronize()
+        # ---- one kernel per rank, the ranks on their own streams (they wait for each other: co-resident)
+        gb = [g.clone() for g in grads]
+        torch.cuda.synchronize()
+        for r, a in enumerate(arenas):
+            sc, co, fl = a.sites["mlp_scale"], a.sites["mlp_codes"], a.sites["mlp_xflag"]
+            with torch.cuda.stream(streams[r]):
+                rc = lib.dqrm_dense_exchange_apply(a.ptrs, world, r, sc["data_off"], sc["stride"], co["data_off"], co["stride"],
+                                                   fl["data_off"], fl["stride"], pb[r].data_ptr(), gb[r].data_ptr(),
+                                                   _lib.ptr(ecb[r]), chan_t.data_ptr(), cta_chan.data_ptr(), G, elems, chans, 8,
+                                                   mean_b[r].data_ptr(), seq[r].data_ptr(), 0.1, None, status[r].data_ptr(),
+                                                   st())
+                _lib.check(rc, "dqrm_dense_exchange_apply")
+        torch.cuda.synchronize()
+        assert all(int(s) == 0 for s in status)
+        for r in range(world):
+            assert torch.equal(mean_a[r], mean_b[r]), (it, r)
+            assert torch.equal(pa[r], pb[r]), (it, r)
+            assert torch.equal(arenas[r].slots("mlp_codes", torch.int8)[:, :total], codes[:, :total]), (it, r)
+            if ec:
+                assert torch.equal(eca[r], ecb[r]) and torch.equal(ga[r], gb[r]), (it, r)
+        assert all(torch.equal(pb[0], p) for p in pb[1:])
+        assert all(int(s[0]) == it + 1 for s in seq)
