@@ -74,7 +74,7 @@ SIGNATURES = {
     "dqrm_scale_from_absmax_gathered": (_i32, [_i32, _p, _sz, _i32, _i32, _p, _p, _p, _p]),
     "dqrm_dense_exchange_smem_bytes": (_sz, [_i32, _i32]),
     "dqrm_dense_exchange_debug": (_i32, [_p]),
-    "dqrm_dense_exchange_apply": (_i32, [_p, _i32, _i32, _sz, _sz, _sz, _sz, _sz, _sz, _p, _p, _p, _p, _p, _i32, _i32, _i32,
+    "dqrm_dense_exchange_apply": (_i32, [_p, _i32, _i32, _sz, _sz, _sz, _sz, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32,
                                          _i32, _p, _p, _f32, _p, _p, _p]),
 }
 

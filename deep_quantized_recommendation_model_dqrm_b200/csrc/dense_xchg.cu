@@ -10,19 +10,27 @@
 // Channels are independent, so no grid-wide step is needed anywhere: CTA b owns a contiguous run of channels (the same
 // run on every rank) and only ever talks to CTA b of the peers --
 //   1. load grad (+ error compensation) of its elements into shared memory, per-channel max-abs -> local scales,
-//      stored into slot[rank] of the scale site in EVERY arena (remote stores), fence, flag[0][b] = seq on every peer;
-//   2. spin on the peers' flag[0][b]; s_bar = (sum_r s_r) * (1/N) in rank order; int8 codes -> slot[rank] of the code
-//      site in every arena, fence, flag[1][b] = seq;
-//   3. spin on flag[1][b]; integer sum of the N code slots in rank order; W += (-lr * (sum/N)) * s_bar (and the
+//      stored into slot[rank] of the scale site of every PEER arena (remote stores);
+//   2. wait for the peers' scales; s_bar = (sum_r s_r) * (1/N) in rank order; int8 codes -> slot[rank] of the code
+//      site of every peer arena;
+//   3. wait for the peers' codes; integer sum of the N code sets in rank order; W += (-lr * (sum/N)) * s_bar (and the
 //      error-compensation residual).
 // Same arithmetic, same order as dense_grad_scale / dense_grad_quant_gathered / dense_apply_gathered: bit-identical
 // parameters (tests/test_gpu_p2p.py; tools/p2p_check.py against the NCCL transport on real GPUs).
 //
-// Single buffering: rank r overwrites its scale slot at peer p in step s+1 only after it saw p's flag[1][b](s), which p
-// stores after its last read of the scale slots of step s; it overwrites its code slot only after p's flag[0][b](s+1),
-// which p stores after its apply of step s.  Slots are read with ld.global.cg (L2): the SM's L1 may still hold the
-// previous step's lines.  All CTAs of the launch must be able to become resident (num_ctas <= 148); a peer that never
-// arrives trips the same watchdog / sticky status bit as dqrm_p2p_allgather and this CTA skips its apply.
+// Transport: every 8-byte word in a slot carries its payload AND the step's sequence number -- {fp32 scale, u32 seq} or
+// {seven int8 codes, u8 seq} -- written with ONE 64-bit store and polled by the reader until the sequence is this
+// step's (the idea of NCCL's low-latency protocol).  Payload and flag arrive together, so there is no system-scope
+// fence and no separate flag: a wait costs one NVLink one-way trip.  The first version (data stores, st.release.sys flag
+// per CTA, ld.acquire poll) measured 4.4-6.4 us per wait at two GPUs (profiles/r02_dense_xchg_phases_n2_fence.txt)
+// against ~2.5 us of work per phase.  The codes pay 8/7 of their bytes (0.54 MB per peer at Kaggle shape); a stale word
+// always carries the previous step's sequence, so one byte of it is enough.
+//
+// Single buffering: rank r overwrites its scale words at peer p in step s+1 only after it received p's codes of step s,
+// which p computed from those scales; it overwrites its code words only after p's scales of step s+1, which p sends
+// after its kernel of step s (the reader of the codes) retired.  Words are read with 64-bit relaxed system-scope loads
+// (L2).  All CTAs of the launch must be able to become resident (num_ctas <= 148); a peer that never arrives trips the
+// same watchdog / sticky status bit as dqrm_p2p_allgather and this CTA skips its apply.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -35,46 +43,44 @@ constexpr int kXMaxWorld = 16;
 struct XPeers { unsigned char* base[kXMaxWorld]; };
 
 struct XSites {
-  size_t scale_off, scale_stride;     // data area of the scale site (bytes), stride between rank slots
-  size_t code_off, code_stride;
-  size_t flag_off, flag_stride;       // slot[src rank] = u32 [2][num_ctas]
+  size_t scale_off, scale_stride;     // data area of the scale site (bytes), stride between rank slots: u64 [num_chan]
+  size_t code_off, code_stride;       // u64 [cta_word[num_ctas]]: seven codes per word, every CTA's run padded to a word
 };
 
-__device__ __forceinline__ void x_st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+constexpr int kXCodesPerWord = 7;
+
+__device__ __forceinline__ void x_st_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned x_ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long x_ld_word(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
-__device__ __forceinline__ unsigned x_ld_relaxed_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Everything this CTA stored so far is visible to a peer that sees the flag; then wait for every peer's flag.
-// ONE system-scope release per signalling thread: the barrier orders the CTA's (remote) stores before it and the release
-// is cumulative -- the pattern of a cooperative grid barrier.  A fence.sys in every thread (first version) cost 2-4 us
-// per fence with 148 x 256 threads issuing it: 44 us per launch at two GPUs.  The poll is a relaxed load; one acquire
-// load after it orders the slot reads that follow the second barrier.
-__device__ __forceinline__ bool x_signal_and_wait(const XPeers& peers, const XSites& st, int world, int rank, int slot,
-                                                  unsigned seq, long long timeout_cycles, int* status) {
-  __syncthreads();
-  const int t = threadIdx.x;
-  if (t < world && t != rank) {
-    x_st_release_sys(reinterpret_cast<unsigned*>(peers.base[t] + st.flag_off + (size_t)rank * st.flag_stride) + slot, seq);
-    const unsigned* f = reinterpret_cast<const unsigned*>(peers.base[rank] + st.flag_off + (size_t)t * st.flag_stride) + slot;
-    const long long t0 = clock64();
-    while ((int)(x_ld_relaxed_sys(f) - seq) < 0) {
-      if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) { atomicOr(status, DQRM_STATUS_P2P_TIMEOUT); break; }
+// Poll word `idx` of every peer's slot in the LOCAL arena until the top SEQ_BITS of each equal `seq`; all loads of a round
+// are in flight together.  The words land in w[r] (w[rank] untouched).  false: the watchdog fired.
+template <int SEQ_BITS>
+__device__ __forceinline__ bool x_wait_words(const unsigned char* slots, size_t stride, long long idx, int world, int rank,
+                                             unsigned seq, long long timeout_cycles, int* status, unsigned long long* w) {
+  const unsigned long long want = (unsigned long long)(seq & (unsigned)((1ull << SEQ_BITS) - 1ull));
+  bool all = false;
+  long long t0 = 0;
+  while (!all) {
+#pragma unroll
+    for (int r = 0; r < kXMaxWorld; ++r)
+      if (r < world && r != rank) w[r] = x_ld_word(reinterpret_cast<const unsigned long long*>(slots + (size_t)r * stride) + idx);
+    all = true;
+#pragma unroll
+    for (int r = 0; r < kXMaxWorld; ++r)
+      if (r < world && r != rank) all = all && (w[r] >> (64 - SEQ_BITS)) == want;
+    if (!all) {
+      if (t0 == 0) t0 = clock64();
+      if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) { atomicOr(status, DQRM_STATUS_P2P_TIMEOUT); return false; }
+      __nanosleep(100);                     // thousands of threads poll: leave the L2 to the kernels running beside this one
     }
-    (void)x_ld_acquire_sys(f);
   }
-  __syncthreads();
-  return (*reinterpret_cast<volatile int*>(status) & DQRM_STATUS_P2P_TIMEOUT) == 0;
+  return true;
 }
 
 __device__ __forceinline__ void x_stamp(unsigned long long* dbg, int k) {      // phase time stamps (debug hook, NULL = off)
@@ -88,10 +94,11 @@ __device__ __forceinline__ void x_stamp(unsigned long long* dbg, int k) {      /
 __global__ void __launch_bounds__(kXThreads)
 dense_exchange_apply_kernel(const __grid_constant__ XPeers peers, const __grid_constant__ XSites st, int world, int rank,
                             float* __restrict__ param, float* __restrict__ grad, float* error_comp,
-                            const long long* __restrict__ chan_begin, const int* __restrict__ cta_chan, int elem_cap,
-                            int chan_cap, int bits, float inv_world, float* __restrict__ scale_mean,
-                            unsigned* __restrict__ seq_dev, float neg_lr_arg, const float* __restrict__ lr_dev,
-                            long long timeout_cycles, int* status, unsigned long long* dbg) {
+                            const long long* __restrict__ chan_begin, const int* __restrict__ cta_chan,
+                            const int* __restrict__ cta_word, int elem_cap, int chan_cap, int bits, float inv_world,
+                            float* __restrict__ scale_mean, unsigned* __restrict__ seq_dev, float neg_lr_arg,
+                            const float* __restrict__ lr_dev, long long timeout_cycles, int* status,
+                            unsigned long long* dbg) {
   extern __shared__ uint4 x_smem[];
   // g_s fp32 [elem_cap] | sbar_s fp32 [chan_cap] | inv_s fp32 [chan_cap] | cb_s i32 [chan_cap + 4] | qsum_s i16
   // [elem_cap + 32] | chrel_s u16 [elem_cap] | q_s i8 [elem_cap + 32]     (elem_cap % 16 == 0, chan_cap % 4 == 0)
@@ -103,18 +110,18 @@ dense_exchange_apply_kernel(const __grid_constant__ XPeers peers, const __grid_c
   unsigned short* chrel_s = reinterpret_cast<unsigned short*>(qsum_s + elem_cap + 32);
   signed char* q_s = reinterpret_cast<signed char*>(chrel_s + elem_cap);
 
-  const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c0 = cta_chan[b], c1 = cta_chan[b + 1], nch = c1 - c0;
+  const long long w0 = cta_word[b];
   const unsigned seq = seq_dev[b] + 1u;
   const long long e0 = chan_begin[c0], e1 = chan_begin[c1];
-  const int n = (int)(e1 - e0);
-  const int mis = (int)(e0 & 15);                       // q_s / qsum_s index of element e0: slot bytes keep their
-  const long long base_al = e0 - mis;                   // 16-byte phase, so whole chunks move as uint4
-  const int nchunk = (mis + n + 15) >> 4;
-  unsigned char* local = peers.base[rank];
+  const int n = (int)(e1 - e0), nw = (n + kXCodesPerWord - 1) / kXCodesPerWord;
+  const unsigned char* local = peers.base[rank];
+  __shared__ int s_bad;
+  if (tid == 0) s_bad = 0;
 
   x_stamp(dbg, 0);
-  // ---- 1. gradients (+ error compensation) -> shared memory; per-channel max-abs -> local scales -> every arena
+  // ---- 1. gradients (+ error compensation) -> shared memory; per-channel max-abs -> local scales -> every peer
   for (int k = tid; k <= nch; k += kXThreads) cb_s[k] = (int)(chan_begin[c0 + k] - e0);
   for (int i0 = tid; i0 < n; i0 += 4 * kXThreads) {
     float w[4], c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -142,67 +149,68 @@ dense_exchange_apply_kernel(const __grid_constant__ XPeers peers, const __grid_c
     if (lane == 0) sbar_s[k] = scale_of(__uint_as_float(m), bits);
   }
   __syncthreads();
-  for (int k = 1; k <= world; ++k) {                                      // (k == world: this rank's own arena)
-    const int p = (rank + k) % world;
-    float* dst = reinterpret_cast<float*>(peers.base[p] + st.scale_off + (size_t)rank * st.scale_stride) + c0;
-    for (int i = tid; i < nch; i += kXThreads) dst[i] = sbar_s[i];
+  for (int k = 1; k < world; ++k) {
+    const int p = (rank + k) % world;                                     // every rank starts on a different peer
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(peers.base[p] + st.scale_off + (size_t)rank * st.scale_stride) + c0;
+    for (int i = tid; i < nch; i += kXThreads) x_st_u64(dst + i, ((unsigned long long)seq << 32) | __float_as_uint(sbar_s[i]));
   }
   x_stamp(dbg, 1);
-  bool ok = x_signal_and_wait(peers, st, world, rank, b, seq, timeout_cycles, status);
-  x_stamp(dbg, 2);
 
-  // ---- 2. mean scale in rank order; int8 codes -> every arena
+  // ---- 2. the peers' scales; mean scale in rank order; int8 codes -> every peer
   for (int k = tid; k < nch; k += kXThreads) {
-    const float* sl = reinterpret_cast<const float*>(local + st.scale_off) + c0 + k;
-    float acc = __ldcg(sl);
-    for (int r = 1; r < world; ++r)
-      acc = __fadd_rn(acc, __ldcg(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(sl) + (size_t)r * st.scale_stride)));
+    unsigned long long sc[kXMaxWorld];
+    if (!x_wait_words<32>(local + st.scale_off, st.scale_stride, c0 + k, world, rank, seq, timeout_cycles, status, sc)) s_bad = 1;
+    const float own = sbar_s[k];
+    float acc = rank == 0 ? own : __uint_as_float((unsigned)sc[0]);       // (static indices only: sc[] stays in registers)
+#pragma unroll
+    for (int r = 1; r < kXMaxWorld; ++r)
+      if (r < world) acc = __fadd_rn(acc, r == rank ? own : __uint_as_float((unsigned)sc[r]));
     const float s_bar = __fmul_rn(acc, inv_world);
     sbar_s[k] = s_bar;
     inv_s[k] = __fdiv_rn(1.0f, s_bar);
     scale_mean[c0 + k] = s_bar;
   }
   __syncthreads();
+  x_stamp(dbg, 2);
   {
     const float hi = qmax_of(bits), lo = -hi - 1.0f;
-    for (int i = tid; i < n; i += kXThreads) q_s[mis + i] = (signed char)quant_code(g_s[i], inv_s[chrel_s[i]], lo, hi);
+    for (int i = tid; i < kXCodesPerWord * nw; i += kXThreads)
+      q_s[i] = i < n ? (signed char)quant_code(g_s[i], inv_s[chrel_s[i]], lo, hi) : (signed char)0;
   }
   __syncthreads();
-  for (int k = 1; k <= world; ++k) {
+  for (int k = 1; k < world; ++k) {
     const int p = (rank + k) % world;
-    unsigned char* dst = peers.base[p] + st.code_off + (size_t)rank * st.code_stride + base_al;
-    for (int ck = tid; ck < nchunk; ck += kXThreads) {
-      const int lo_b = ck << 4;
-      if (lo_b >= mis && lo_b + 16 <= mis + n) {
-        *reinterpret_cast<uint4*>(dst + lo_b) = *reinterpret_cast<const uint4*>(q_s + lo_b);
-      } else {                                                             // first / last chunk: only this CTA's bytes
-        for (int j = max(lo_b, mis); j < min(lo_b + 16, mis + n); ++j) dst[j] = (unsigned char)q_s[j];
-      }
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(peers.base[p] + st.code_off + (size_t)rank * st.code_stride) + w0;
+    for (int w = tid; w < nw; w += kXThreads) {
+      unsigned long long v = (unsigned long long)(seq & 0xffu) << 56;
+#pragma unroll
+      for (int j = 0; j < kXCodesPerWord; ++j) v |= (unsigned long long)(unsigned char)q_s[kXCodesPerWord * w + j] << (8 * j);
+      x_st_u64(dst + w, v);
     }
   }
   x_stamp(dbg, 3);
-  ok = x_signal_and_wait(peers, st, world, rank, G + b, seq, timeout_cycles, status) && ok;
-  x_stamp(dbg, 4);
-  if (tid == 0) seq_dev[b] = seq;
-  if (!ok) return;                                                         // a peer timed out: never apply stale slots
 
-  // ---- 3. exact integer sum of the code slots in rank order; SGD update (and the error-compensation residual)
-  for (int ck = tid; ck < nchunk; ck += kXThreads) {
-    short acc[16];
+  // ---- 3. the peers' codes; exact integer sum in rank order; SGD update (and the error-compensation residual)
+  for (int w = tid; w < nw; w += kXThreads) {
+    unsigned long long cw[kXMaxWorld];
+    if (!x_wait_words<8>(local + st.code_off, st.code_stride, w0 + w, world, rank, seq, timeout_cycles, status, cw)) s_bad = 1;
+    short acc[kXCodesPerWord];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0;
-    const unsigned char* src = local + st.code_off + base_al + ((size_t)ck << 4);
-#pragma unroll 2
-    for (int r = 0; r < world; ++r) {
-      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)r * st.code_stride));
-      const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+    for (int j = 0; j < kXCodesPerWord; ++j) acc[j] = 0;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] += (short)(signed char)((wds[j >> 2] >> ((j & 3) * 8)) & 0xffu);
+    for (int r = 0; r < kXMaxWorld; ++r) {
+      if (r >= world) continue;
+#pragma unroll
+      for (int j = 0; j < kXCodesPerWord; ++j)
+        acc[j] += r == rank ? (short)q_s[kXCodesPerWord * w + j] : (short)(signed char)((cw[r] >> (8 * j)) & 0xffu);
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) qsum_s[(ck << 4) + j] = acc[j];
+    for (int j = 0; j < kXCodesPerWord; ++j) qsum_s[kXCodesPerWord * w + j] = acc[j];
   }
   __syncthreads();
+  x_stamp(dbg, 4);
+  if (tid == 0) seq_dev[b] = seq;
+  if (s_bad || (*reinterpret_cast<volatile int*>(status) & DQRM_STATUS_P2P_TIMEOUT)) return;   // never apply stale slots
   const float neg_lr = lr_dev ? -(*lr_dev) : neg_lr_arg;
   for (int i0 = tid; i0 < n; i0 += 4 * kXThreads) {
     float p[4];
@@ -213,7 +221,7 @@ dense_exchange_apply_kernel(const __grid_constant__ XPeers peers, const __grid_c
       const int i = i0 + j * kXThreads;
       if (i >= n) continue;
       const float s = sbar_s[chrel_s[i]];
-      const float g = __fmul_rn((float)qsum_s[mis + i], inv_world);       // all_reduce(SUM) * (1/N)
+      const float g = __fmul_rn((float)qsum_s[i], inv_world);             // all_reduce(SUM) * (1/N)
       const float u = __fmul_rn(__fmul_rn(neg_lr, g), s);                 // (-lr * grad) * s     (:642-643)
       param[e0 + i] = __fadd_rn(p[j], u);
       if (error_comp) error_comp[e0 + i] = __fsub_rn(g_s[i], __fmul_rn(g, s));   // weight - grad_up * s (:926-927)
@@ -250,11 +258,11 @@ extern "C" size_t dqrm_dense_exchange_smem_bytes(int max_cta_elems, int max_cta_
 
 extern "C" int dqrm_dense_exchange_apply(void* const* peer_base, int world, int rank, size_t scale_data_off,
                                          size_t scale_stride_bytes, size_t code_data_off, size_t code_stride_bytes,
-                                         size_t flag_data_off, size_t flag_stride_bytes, float* param, float* grad,
+                                         float* param, float* grad,
                                          float* error_comp, const int64_t* chan_begin, const int32_t* cta_chan,
-                                         int num_ctas, int max_cta_elems, int max_cta_chans, int bits, float* scale_mean,
+                                         const int32_t* cta_word, int num_ctas, int max_cta_elems, int max_cta_chans, int bits, float* scale_mean,
                                          uint32_t* seq, float lr, const float* lr_dev, int32_t* status, void* stream) {
-  DQRM_REQUIRE(peer_base && param && grad && chan_begin && cta_chan && scale_mean && seq && status, -EINVAL,
+  DQRM_REQUIRE(peer_base && param && grad && chan_begin && cta_chan && cta_word && scale_mean && seq && status, -EINVAL,
                "dense_exchange_apply: null argument");
   DQRM_REQUIRE(world >= 1 && world <= kXMaxWorld && rank >= 0 && rank < world, -EINVAL,
                "dense_exchange_apply: rank %d / world %d", rank, world);
@@ -264,9 +272,7 @@ extern "C" int dqrm_dense_exchange_apply(void* const* peer_base, int world, int 
                num_ctas, kSMs);
   DQRM_REQUIRE(max_cta_elems >= 1 && max_cta_chans >= 1 && max_cta_chans < 65536, -EINVAL,
                "dense_exchange_apply: max_cta_elems=%d max_cta_chans=%d", max_cta_elems, max_cta_chans);
-  DQRM_REQUIRE(flag_stride_bytes >= (size_t)num_ctas * 8, -EINVAL, "dense_exchange_apply: flag slot of %zu bytes < 2 x %d x 4",
-               flag_stride_bytes, num_ctas);
-  DQRM_REQUIRE(((scale_data_off | scale_stride_bytes | code_data_off | code_stride_bytes | flag_data_off | flag_stride_bytes) & 15u) == 0,
+  DQRM_REQUIRE(((scale_data_off | scale_stride_bytes | code_data_off | code_stride_bytes) & 15u) == 0,
                -EINVAL, "dense_exchange_apply: site offsets / strides must be multiples of 16");
   XPeers pp;
   for (int r = 0; r < world; ++r) {
@@ -281,10 +287,10 @@ extern "C" int dqrm_dense_exchange_apply(void* const* peer_base, int world, int 
     DQRM_REQUIRE(e == cudaSuccess, -EIO, "dense_exchange_apply: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     attr_set = smem;
   }
-  XSites st{scale_data_off, scale_stride_bytes, code_data_off, code_stride_bytes, flag_data_off, flag_stride_bytes};
+  XSites st{scale_data_off, scale_stride_bytes, code_data_off, code_stride_bytes};
   const int cap = (max_cta_elems + 15) / 16 * 16;
   dense_exchange_apply_kernel<<<num_ctas, kXThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      pp, st, world, rank, param, grad, error_comp, reinterpret_cast<const long long*>(chan_begin), cta_chan, cap,
+      pp, st, world, rank, param, grad, error_comp, reinterpret_cast<const long long*>(chan_begin), cta_chan, cta_word, cap,
       (max_cta_chans + 3) & ~3, bits, (float)(1.0 / world), scale_mean, seq, -lr, lr_dev, x_timeout_cycles(), status, g_x_dbg);
   DQRM_LAUNCH_CHECK("dense_exchange_apply_kernel");
   return 0;

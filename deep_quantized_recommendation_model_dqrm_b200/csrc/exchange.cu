@@ -138,14 +138,18 @@ grad_merge_apply_kernel(const __grid_constant__ TableSet ts, int dim4, int group
         const bool use = r2 < world && r2 != r;
         const unsigned char* o = gathered + (size_t)(use ? r2 : r) * lay.bytes;
         lst[i] = reinterpret_cast<const int*>(o + lay.rows_off) + (long long)t * capacity;
-        n2[i] = use ? min(__ldg(reinterpret_cast<const int*>(o) + t), (int)capacity) : 0;
+        n2[i] = 0;
+        if (use) n2[i] = min(__ldg(reinterpret_cast<const int*>(o) + t), (int)capacity);
       }
 #pragma unroll
       for (int i = 0; i < kMergeRanks; ++i) { lo[i] = 0; hi[i] = n2[i]; }
       for (int it = 0; it < search_iters; ++it) {
         int v[kMergeRanks];
 #pragma unroll
-        for (int i = 0; i < kMergeRanks; ++i) v[i] = __ldg(lst[i] + ((lo[i] + hi[i]) >> 1));   // (mid <= capacity - 1)
+        for (int i = 0; i < kMergeRanks; ++i) {                           // (mid <= capacity - 1; closed searches load nothing)
+          v[i] = 0;
+          if (lo[i] < hi[i]) v[i] = __ldg(lst[i] + ((lo[i] + hi[i]) >> 1));
+        }
 #pragma unroll
         for (int i = 0; i < kMergeRanks; ++i) {
           const int mid = (lo[i] + hi[i]) >> 1;
@@ -155,7 +159,10 @@ grad_merge_apply_kernel(const __grid_constant__ TableSet ts, int dim4, int group
       }
       int at[kMergeRanks];
 #pragma unroll
-      for (int i = 0; i < kMergeRanks; ++i) at[i] = __ldg(lst[i] + min(lo[i], (int)capacity - 1));
+      for (int i = 0; i < kMergeRanks; ++i) {
+        at[i] = -1;
+        if (lo[i] < n2[i]) at[i] = __ldg(lst[i] + lo[i]);
+      }
       bool found[kMergeRanks];
 #pragma unroll
       for (int i = 0; i < kMergeRanks; ++i) {

@@ -203,7 +203,10 @@ class DenseArena:
         cuts.append(self.num_chan)
         elems = max(cb[cuts[b + 1]] - cb[cuts[b]] for b in range(num_ctas))
         chans = max(cuts[b + 1] - cuts[b] for b in range(num_ctas))
-        return cuts, elems, chans
+        words = [0]                                               # seven int8 codes per exchanged word, runs padded to a word
+        for b in range(num_ctas):
+            words.append(words[-1] + (cb[cuts[b + 1]] - cb[cuts[b]] + 6) // 7)
+        return dict(cta_chan=cuts, cta_word=words, elems=elems, chans=chans)
 
     def _ensure_slots(self, world):
         """Per-rank slots of the two MLP exchange sites (channel scales fp32, codes int8): views of this rank's peer
@@ -217,9 +220,10 @@ class DenseArena:
         a = None
         if live and _p2p.backend() == "p2p":
             try:
-                cuts, elems, chans = self.xchg_partition()
+                part = self.xchg_partition()
                 a = _p2p.PeerArena({"mlp_scale": self.num_chan * 4, "mlp_codes": self.total,
-                                    "mlp_xflag": 2 * (len(cuts) - 1) * 4}, world, dist.get_rank(), self.device)
+                                    "mlp_xscale": self.num_chan * 8, "mlp_xcodes": part["cta_word"][-1] * 8},
+                                   world, dist.get_rank(), self.device)
             except _p2p.P2PUnavailable as e:         # raised on every rank together
                 _p2p.fall_back_to_nccl(e)
         if a is not None:
@@ -227,7 +231,7 @@ class DenseArena:
             self._scale_slots = a.slots("mlp_scale", torch.float32)
             self._code_slots = a.slots("mlp_codes", torch.int8)
             rank = a.rank
-            self.bind_xchg(a, cuts, elems, chans)
+            self.bind_xchg(a, part)
         else:
             pad = lambda n: (n + 15) // 16 * 16
             self._scale_slots = torch.zeros((world, pad(self.num_chan * 4) // 4), dtype=torch.float32, device=self.device)
@@ -237,23 +241,25 @@ class DenseArena:
         self.scale_local = self._scale_slots[rank, :self.num_chan]
         self._codes_mine = self._code_slots[rank, :self.total]
 
-    def bind_xchg(self, arena, cuts, elems, chans):
-        """Plan of the one-kernel exchange on `arena` (sites mlp_scale / mlp_codes / mlp_xflag): the per-CTA channel
-        runs and the device-side sequence numbers (zero like the fresh arena's flags)."""
-        self._xchg_plan = dict(arena=arena, num_ctas=len(cuts) - 1, elems=int(elems), chans=int(chans),
-                               cta_chan=torch.tensor(cuts, dtype=torch.int32, device=self.device),
-                               seq=torch.zeros(len(cuts) - 1, dtype=torch.int32, device=self.device))
+    def bind_xchg(self, arena, part):
+        """Plan of the one-kernel exchange on `arena` (sites mlp_xscale / mlp_xcodes): the per-CTA channel runs
+        (xchg_partition) and the device-side sequence numbers (zero like the fresh arena's words)."""
+        G = len(part["cta_chan"]) - 1
+        self._xchg_plan = dict(arena=arena, num_ctas=G, elems=int(part["elems"]), chans=int(part["chans"]),
+                               cta_chan=torch.tensor(part["cta_chan"], dtype=torch.int32, device=self.device),
+                               cta_word=torch.tensor(part["cta_word"], dtype=torch.int32, device=self.device),
+                               seq=torch.zeros(G, dtype=torch.int32, device=self.device))
 
     def exchange_apply_fused(self, lr, bits=8):
         """quantize_exchange() + apply() of a multi-rank step in ONE launch (csrc/dense_xchg.cu); bit-identical to
         local_scale -> all-gather -> dqrm_dense_grad_quant_gathered -> all-gather -> dqrm_dense_apply_gathered."""
         pl = self._xchg_plan
         a = pl["arena"]
-        sc, co, fl = a.sites["mlp_scale"], a.sites["mlp_codes"], a.sites["mlp_xflag"]
+        sc, co = a.sites["mlp_xscale"], a.sites["mlp_xcodes"]
         rc = self.lib.dqrm_dense_exchange_apply(a.ptrs, a.world, a.rank, sc["data_off"], sc["stride"], co["data_off"],
-                                                co["stride"], fl["data_off"], fl["stride"], self.flat.data_ptr(),
-                                                self.flat_grad.data_ptr(), self._ec_ptr(), self.chan_begin.data_ptr(),
-                                                pl["cta_chan"].data_ptr(), pl["num_ctas"], pl["elems"], pl["chans"],
+                                                co["stride"], self.flat.data_ptr(), self.flat_grad.data_ptr(),
+                                                self._ec_ptr(), self.chan_begin.data_ptr(), pl["cta_chan"].data_ptr(),
+                                                pl["cta_word"].data_ptr(), pl["num_ctas"], pl["elems"], pl["chans"],
                                                 int(bits), self.scale_mean.data_ptr(), pl["seq"].data_ptr(), float(lr),
                                                 _lib.ptr(self.lr_dev), self.status.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "dqrm_dense_exchange_apply")

@@ -464,24 +464,28 @@ DQRM_API int dqrm_scale_from_absmax_gathered(int n_scales, const float* gathered
  * dqrm_dense_grad_scale -> allgather -> dqrm_dense_grad_quant_gathered -> allgather -> dqrm_dense_apply_gathered
  * (quantize_linear_grad / quantize_bias_grad + the MLP part of weight_update_parallel_comm,
  * sgd_quantized_gradients_parallel_comm.py:892-961,630-663) with the same arithmetic in the same order, so the
- * parameters are bit-identical.  CTA b owns channels [cta_chan[b], cta_chan[b+1]) on every rank and synchronises only
- * with CTA b of the peers through per-CTA flags (no grid-wide step): scales and int8 codes are stored straight into
- * slot[rank] of every arena.  Sites (data areas of dqrm_p2p_site_layout sites, byte offsets from the arena base,
- * multiples of 16): scale slots fp32 [num_chan], code slots int8 [total], flag slots u32 [2][num_ctas].
- *   cta_chan       dev int32 [num_ctas + 1], the same on every rank; max_cta_elems / max_cta_chans bound one CTA's run
+ * parameters are bit-identical.  CTA b owns channels [cta_chan[b], cta_chan[b+1]) on every rank and exchanges only
+ * with CTA b of the peers (no grid-wide step).  Every 8-byte word of a slot carries its payload and the step's sequence number and is
+ * written with one 64-bit remote store / polled by the reader: no fence, no separate flag.  Sites (data areas of
+ * dqrm_p2p_site_layout sites, byte offsets from the arena base, multiples of 16):
+ *   scale slots  u64 [num_chan]                 payload = the rank's local fp32 scale of the channel
+ *   code slots   u64 [cta_word[num_ctas]]       seven int8 codes + the low byte of the sequence number; CTA b's run
+ *                                               starts at word cta_word[b]
+ *   cta_chan, cta_word   dev int32 [num_ctas + 1], the same on every rank (cta_word[b+1] - cta_word[b] =
+ *                  ceil(elements of run b / 7)); max_cta_elems / max_cta_chans bound one CTA's run
  *   seq            dev u32 [num_ctas], zero-initialised together with the arena; advanced by the kernel (replayable)
  *   error_comp     dev or NULL: grad += error_comp in place before the scales, residual written back (:899-900,926-927)
  * num_ctas <= 148: every CTA has to be resident, they wait for their peers.  Watchdog / status as dqrm_p2p_allgather;
  * a CTA that saw the timeout bit does not touch the parameters. */
 DQRM_API size_t dqrm_dense_exchange_smem_bytes(int max_cta_elems, int max_cta_chans);
-/* debug hook: dev u64 [num_ctas][8] (or NULL = off, the default): %globaltimer of thread 0 of every CTA at launch, before
- * / after the first wait, before / after the second wait and at the end -- where a launch spends its time */
+/* debug hook: dev u64 [num_ctas][8] (or NULL = off, the default): %globaltimer of thread 0 of every CTA at launch, after
+ * the scale stores, after the scale wait, after the code stores, after the code wait and at the end -- where a launch spends its time */
 DQRM_API int dqrm_dense_exchange_debug(uint64_t* stamps);
 DQRM_API int dqrm_dense_exchange_apply(void* const* peer_base, int world, int rank, size_t scale_data_off,
                                        size_t scale_stride_bytes, size_t code_data_off, size_t code_stride_bytes,
-                                       size_t flag_data_off, size_t flag_stride_bytes, float* param, float* grad,
+                                       float* param, float* grad,
                                        float* error_comp, const int64_t* chan_begin, const int32_t* cta_chan,
-                                       int num_ctas, int max_cta_elems, int max_cta_chans, int bits, float* scale_mean,
+                                       const int32_t* cta_word, int num_ctas, int max_cta_elems, int max_cta_chans, int bits, float* scale_mean,
                                        uint32_t* seq, float lr, const float* lr_dev, int32_t* status, void* stream);
 
 #ifdef __cplusplus

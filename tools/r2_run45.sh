@@ -1,0 +1,8 @@
+#!/bin/bash
+O=gpurun_out/r2_45; mkdir -p $O
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533"
+timeout 300 python -m pytest tests/test_gpu_p2p.py -q -x 2>&1 | tail -5 > $O/tests_p2p.log
+timeout 240 $T tools/p2p_check.py > $O/p2p_check.log 2>&1
+timeout 400 $T bench.py --gpus 2 --no-extras > $O/bench_n2.json 2> $O/bench_n2.err
+timeout 200 $T tools/xchg_phases.py > $O/xchg_phases.txt 2>&1
+timeout 120 $T tools/mgpu_timeline.py > $O/timeline_n2.txt 2>&1
