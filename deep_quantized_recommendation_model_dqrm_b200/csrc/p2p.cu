@@ -264,7 +264,9 @@ extern "C" int dqrm_p2p_allgather(void* const* peer_base, int world, int rank, s
   }
   size_t flag_off, data_off, stride;
   dqrm_p2p_site_layout(world, slot_bytes, &flag_off, &data_off, &stride);
-  long long grid = ceil_div((long long)stride, 16 * 1024);                    // one trip of the 4-deep copy loop per CTA
+  // one 16-byte chunk per thread while the SMs last: remote stores drain slowly per SM (66 kB to seven peers took 18 us
+  // from 5 CTAs), so spread them over as many SMs as there are chunks
+  long long grid = ceil_div((long long)stride, 16 * kP2PThreads);
   if (grid > kSMs) grid = kSMs;
   if (grid < 1) grid = 1;
   p2p_allgather_kernel<<<(unsigned)grid, kP2PThreads, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -105,6 +105,10 @@ class DenseArena:
         self.fuse_xchg = False             # (lr_dev set: issued by quantize_exchange() already, beside the embedding exchange)
         self._xchg_pending = None
         self._xchg_plan = None
+        self.xchg_early = False            # ... and the top MLP's share already from inside the backward (after_dw)
+        self.early_from_layer = 0          # index of the first top-MLP layer in `layers` (graph_step sets both)
+        self.xchg_stream = None
+        self._xchg_early_done = False
         self.lazy_zero = False             # zero_grad() only marks the layers clean (see zero_grad)
         self._bind_scale_views()
 
@@ -179,34 +183,45 @@ class DenseArena:
         for l in self.layers:
             l._grad_dirty = False
 
-    def xchg_partition(self, num_ctas=None):
+    def xchg_partition(self, num_ctas=None, split_chan=None):
         """Contiguous runs of channels for the CTAs of the one-kernel exchange, balanced by elements + a per-channel
-        cost; the same on every rank (pure function of the layer shapes).  -> (cta_chan list, max elems, max chans)"""
+        cost; the same on every rank (pure function of the layer shapes).  With `split_chan` no run crosses that
+        channel, so the CTAs before / from `split_cta` can be launched on their own (late / early bucket).
+        -> dict(cta_chan, cta_word, elems, chans, split_cta)"""
+        import bisect
         cb = self.chan_begin.cpu().tolist()
         cost = [cb[c + 1] - cb[c] + 24 for c in range(self.num_chan)]
-        tot = sum(cost)
-        if num_ctas is None:
-            num_ctas = max(1, min(148, tot // 2048))
-        num_ctas = max(1, min(int(num_ctas), self.num_chan))
         pre = [0]
         for x in cost:
             pre.append(pre[-1] + x)
-        import bisect
-        cuts = [0]
-        for b in range(1, num_ctas):                              # cut b at the channel boundary nearest b/num_ctas
-            target = tot * b / num_ctas
-            c = bisect.bisect_left(pre, target)
-            if c > 0 and target - pre[c - 1] < pre[min(c, self.num_chan)] - target:
-                c -= 1
-            c = min(max(c, cuts[-1] + 1), self.num_chan - (num_ctas - b))    # every CTA owns at least one channel
-            cuts.append(c)
-        cuts.append(self.num_chan)
-        elems = max(cb[cuts[b + 1]] - cb[cuts[b]] for b in range(num_ctas))
-        chans = max(cuts[b + 1] - cuts[b] for b in range(num_ctas))
+        tot = pre[-1]
+        if num_ctas is None:
+            num_ctas = max(1, min(148, tot // 2048))
+        num_ctas = max(1, min(int(num_ctas), self.num_chan))
+
+        def cut(c_lo, c_hi, k):                                   # k runs over channels [c_lo, c_hi)
+            cuts = [c_lo]
+            for b in range(1, k):                                 # cut b at the channel boundary nearest b/k of the cost
+                target = pre[c_lo] + (pre[c_hi] - pre[c_lo]) * b / k
+                c = bisect.bisect_left(pre, target)
+                if c > 0 and target - pre[c - 1] < pre[min(c, self.num_chan)] - target:
+                    c -= 1
+                cuts.append(min(max(c, cuts[-1] + 1), c_hi - (k - b)))    # every CTA owns at least one channel
+            return cuts
+
+        if split_chan is None or not (0 < split_chan < self.num_chan) or num_ctas < 2:
+            cuts, split_cta = cut(0, self.num_chan, num_ctas) + [self.num_chan], 0
+        else:
+            k_lo = min(max(1, round(num_ctas * pre[split_chan] / tot)), num_ctas - 1, split_chan)
+            k_hi = min(num_ctas - k_lo, self.num_chan - split_chan)
+            cuts, split_cta = cut(0, split_chan, k_lo) + cut(split_chan, self.num_chan, k_hi) + [self.num_chan], k_lo
+        n = len(cuts) - 1
+        elems = max(cb[cuts[b + 1]] - cb[cuts[b]] for b in range(n))
+        chans = max(cuts[b + 1] - cuts[b] for b in range(n))
         words = [0]                                               # seven int8 codes per exchanged word, runs padded to a word
-        for b in range(num_ctas):
+        for b in range(n):
             words.append(words[-1] + (cb[cuts[b + 1]] - cb[cuts[b]] + 6) // 7)
-        return dict(cta_chan=cuts, cta_word=words, elems=elems, chans=chans)
+        return dict(cta_chan=cuts, cta_word=words, elems=elems, chans=chans, split_cta=split_cta)
 
     def _ensure_slots(self, world):
         """Per-rank slots of the two MLP exchange sites (channel scales fp32, codes int8): views of this rank's peer
@@ -220,7 +235,7 @@ class DenseArena:
         a = None
         if live and _p2p.backend() == "p2p":
             try:
-                part = self.xchg_partition()
+                part = self.xchg_partition(split_chan=self._early_split_chan())
                 a = _p2p.PeerArena({"mlp_scale": self.num_chan * 4, "mlp_codes": self.total,
                                     "mlp_xscale": self.num_chan * 8, "mlp_xcodes": part["cta_word"][-1] * 8},
                                    world, dist.get_rank(), self.device)
@@ -248,21 +263,51 @@ class DenseArena:
         self._xchg_plan = dict(arena=arena, num_ctas=G, elems=int(part["elems"]), chans=int(part["chans"]),
                                cta_chan=torch.tensor(part["cta_chan"], dtype=torch.int32, device=self.device),
                                cta_word=torch.tensor(part["cta_word"], dtype=torch.int32, device=self.device),
-                               seq=torch.zeros(G, dtype=torch.int32, device=self.device))
+                               seq=torch.zeros(G, dtype=torch.int32, device=self.device),
+                               split_cta=int(part.get("split_cta", 0)))
 
-    def exchange_apply_fused(self, lr, bits=8):
+    def _early_split_chan(self):
+        """First channel of layer `early_from_layer` (the top MLP): the early bucket of the exchange (0: no split)."""
+        k = self.early_from_layer
+        if not k or k >= len(self.layers):
+            return None
+        return sum(l.weight.shape[0] + (1 if l.bias is not None else 0) for l in self.layers[:k])
+
+    def exchange_apply_fused(self, lr, bits=8, part="all"):
         """quantize_exchange() + apply() of a multi-rank step in ONE launch (csrc/dense_xchg.cu); bit-identical to
-        local_scale -> all-gather -> dqrm_dense_grad_quant_gathered -> all-gather -> dqrm_dense_apply_gathered."""
+        local_scale -> all-gather -> dqrm_dense_grad_quant_gathered -> all-gather -> dqrm_dense_apply_gathered.
+        part = "early" / "late": only the CTAs from / before the plan's split (channels are independent)."""
         pl = self._xchg_plan
         a = pl["arena"]
+        b0, b1 = {"all": (0, pl["num_ctas"]), "late": (0, pl["split_cta"]), "early": (pl["split_cta"], pl["num_ctas"])}[part]
+        if b1 <= b0:
+            return
         sc, co = a.sites["mlp_xscale"], a.sites["mlp_xcodes"]
         rc = self.lib.dqrm_dense_exchange_apply(a.ptrs, a.world, a.rank, sc["data_off"], sc["stride"], co["data_off"],
                                                 co["stride"], self.flat.data_ptr(), self.flat_grad.data_ptr(),
-                                                self._ec_ptr(), self.chan_begin.data_ptr(), pl["cta_chan"].data_ptr(),
-                                                pl["cta_word"].data_ptr(), pl["num_ctas"], pl["elems"], pl["chans"],
-                                                int(bits), self.scale_mean.data_ptr(), pl["seq"].data_ptr(), float(lr),
-                                                _lib.ptr(self.lr_dev), self.status.data_ptr(), _lib.stream_ptr())
+                                                self._ec_ptr(), self.chan_begin.data_ptr(),
+                                                pl["cta_chan"].data_ptr() + 4 * b0, pl["cta_word"].data_ptr() + 4 * b0,
+                                                b1 - b0, pl["elems"], pl["chans"], int(bits), self.scale_mean.data_ptr(),
+                                                pl["seq"].data_ptr() + 4 * b0, float(lr), _lib.ptr(self.lr_dev),
+                                                self.status.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "dqrm_dense_exchange_apply")
+
+    def after_dw(self, module):
+        """Called by the fused backward right after a layer's weight-gradient GEMM was issued.  When the LAST top-MLP
+        layer (in backward order) is through, the top MLP's share of the dense exchange + update (4/5 of the bytes at
+        Kaggle shape) starts on its own stream, beside the interaction / bottom-MLP backward, instead of behind the last
+        bottom-layer GEMM; quantize_exchange() then only issues the bottom MLP's share.  Safe: the backward reads the
+        fake-quantised copies (flat_int), never the parameters this updates."""
+        if not (self.xchg_early and self.fuse_xchg and self.lr_dev is not None and self._xchg_plan is not None
+                and self._xchg_plan["split_cta"] > 0 and module is self.layers[self.early_from_layer]):
+            return
+        if self.xchg_stream is None:
+            self.xchg_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        for st in self.side_streams[:min(self._side_rr, len(self.side_streams))]:     # (only streams used this step: an
+            self.xchg_stream.wait_stream(st)                                          # idle one is outside a graph capture)
+        with torch.cuda.stream(self.xchg_stream):
+            self.exchange_apply_fused(0.0, 8, part="early")
+        self._xchg_early_done = True
 
     def release(self):
         """Close the MLP exchange arena (barrier first: no rank may still be storing into it).  Collective."""
@@ -310,7 +355,10 @@ class DenseArena:
                 # (grad_update_parallel_comm: before the embedding streams are joined, so it runs beside the embedding
                 # exchange) and apply() has nothing left to do; otherwise apply() issues it with its lr argument.
                 if self.lr_dev is not None:
-                    self.exchange_apply_fused(0.0, bits)
+                    early, self._xchg_early_done = self._xchg_early_done and bits == 8, False
+                    self.exchange_apply_fused(0.0, bits, part="late" if early else "all")
+                    if early:                    # (inside a captured graph the position of this join is the dependency)
+                        torch.cuda.current_stream().wait_stream(self.xchg_stream)
                     self._xchg_pending = "done"
                 else:
                     self._xchg_pending = bits

@@ -27,6 +27,10 @@ def _packed_layout(X, lS_o, lS_i, T):
     return lay, off
 
 
+def self_pipelined(dlrm):
+    return dlrm._ensure_group().scale_policy == "pipelined"
+
+
 class GraphedTrainStep:
     def __init__(self, dlrm, X, lS_o, lS_i, T, lr, world_size=1, rank=0, grad_bits=8, warmup=3, use_graph=True,
                  mlp_layer_quantized=True):
@@ -68,6 +72,14 @@ class GraphedTrainStep:
         # N ranks over NVLink: the five launches of the dense exchange (scale, all-gather, quantise, all-gather, update)
         # as ONE kernel whose CTAs synchronise pairwise with their peers (csrc/dense_xchg.cu), same bits
         _arena_of(dlrm).fuse_xchg = world_size > 1 and os.environ.get("DQRM_FUSE_DENSE_XCHG", "1") != "0"
+        # ... optionally (DQRM_DENSE_XCHG_EARLY=1) the top MLP's share of it is issued from inside the backward, as soon
+        # as the top MLP's weight gradients exist (DenseArena.after_dw).  Measured at two GPUs and OFF by default: the
+        # launch is latency-, not byte-bound, so the bottom MLP's share left for the tail takes as long as the whole
+        # (18 us), while the early launch slows the bottom-MLP backward it runs beside (step 0.293 -> 0.341 ms)
+        from .quantization_supp.quant_modules import QuantLinear as _QL
+        _arena_of(dlrm).early_from_layer = sum(1 for l in dlrm.bot_l if isinstance(l, _QL))
+        _arena_of(dlrm).xchg_early = (world_size > 1 and mlp_layer_quantized and not self_pipelined(dlrm) and
+                                      os.environ.get("DQRM_DENSE_XCHG_EARLY", "0") == "1")
         # every step runs the fused backward of all 7 layers, which overwrites clean gradients: no zero-fill launch
         _arena_of(dlrm).lazy_zero = X.shape[0] <= dlrm.fuse_mlp_max_batch and dlrm._fused_mlp_arena() is not None
         self.pipelined = self.group.scale_policy == "pipelined"

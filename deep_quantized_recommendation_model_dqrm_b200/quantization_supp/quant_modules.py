@@ -258,6 +258,7 @@ class _FusedQuantLinearFunction(Function):
             _lib.check(lib.dqrm_linear_bwd(*args, None, wg, bg, accumulate, _lib.linear_path, side.cuda_stream),
                        "dqrm_linear_bwd")
             arena.keepalive.append((x, out, dout))        # these must outlive the side-stream kernel
+            arena.after_dw(m)
         m._grad_dirty = True
         return dx, None, None, None, None
 

@@ -142,12 +142,14 @@ def test_scale_from_gathered_absmax():
     assert torch.equal(am, want) and torch.equal(sc, sc2) and torch.equal(inv, inv2)
 
 
-@pytest.mark.parametrize("world,num_ctas,ec", [(1, 3, False), (2, 5, False), (4, 7, True), (8, 4, False)])
-def test_one_kernel_dense_exchange_matches_the_five_launch_form(world, num_ctas, ec):
+@pytest.mark.parametrize("world,num_ctas,ec,split", [(1, 3, False, False), (2, 5, False, False), (4, 7, True, False),
+                                                     (8, 4, False, False), (4, 6, True, True)])
+def test_one_kernel_dense_exchange_matches_the_five_launch_form(world, num_ctas, ec, split):
     """dqrm_dense_exchange_apply (csrc/dense_xchg.cu: CTA b exchanges with CTA b of the peers, scales and int8 codes travel as
     {payload, sequence} words stored straight into the peers' arenas) == dense_grad_scale -> gather -> dense_grad_quant_gathered -> gather -> dense_apply_gathered:
     parameters, mean scales and error-compensation residuals bit-identical, over several replays (device-side
-    sequence numbers) -- W arenas in this process, the W ranks on W streams."""
+    sequence numbers) -- W arenas in this process, the W ranks on W streams.  split: the CTAs of the top layers and of
+    the bottom layers as two launches (the early / late buckets of DenseArena.after_dw)."""
     import ctypes as C
     from deep_quantized_recommendation_model_dqrm_b200 import _lib, p2p
     from deep_quantized_recommendation_model_dqrm_b200.dense import DenseArena
@@ -166,7 +168,8 @@ def test_one_kernel_dense_exchange_matches_the_five_launch_form(world, num_ctas,
     chan_t = torch.tensor(chan, dtype=torch.int64, device="cuda")
     plan = DenseArena.__new__(DenseArena)
     plan.chan_begin, plan.num_chan = chan_t, nch
-    part = plan.xchg_partition(num_ctas)
+    part = plan.xchg_partition(num_ctas, split_chan=64 + 1 + 48 + 1 if split else None)
+    assert (part["split_cta"] > 0) == split
     G, elems, chans = len(part["cta_chan"]) - 1, part["elems"], part["chans"]
     cta_chan = torch.tensor(part["cta_chan"], dtype=torch.int32, device="cuda")
     cta_word = torch.tensor(part["cta_word"], dtype=torch.int32, device="cuda")
@@ -207,14 +210,16 @@ def test_one_kernel_dense_exchange_matches_the_five_launch_form(world, num_ctas,
         torch.cuda.synchronize()
         for r, a in enumerate(arenas):
             sc, co = a.sites["mlp_xscale"], a.sites["mlp_xcodes"]
+            k = part["split_cta"]
             with torch.cuda.stream(streams[r]):
-                rc = lib.dqrm_dense_exchange_apply(a.ptrs, world, r, sc["data_off"], sc["stride"], co["data_off"], co["stride"],
-                                                   pb[r].data_ptr(), gb[r].data_ptr(),
-                                                   _lib.ptr(ecb[r]), chan_t.data_ptr(), cta_chan.data_ptr(),
-                                                   cta_word.data_ptr(), G, elems, chans, 8,
-                                                   mean_b[r].data_ptr(), seq[r].data_ptr(), 0.1, None, status[r].data_ptr(),
-                                                   st())
-                _lib.check(rc, "dqrm_dense_exchange_apply")
+                for b0, b1 in ([(k, G), (0, k)] if split else [(0, G)]):
+                    rc = lib.dqrm_dense_exchange_apply(a.ptrs, world, r, sc["data_off"], sc["stride"], co["data_off"],
+                                                       co["stride"], pb[r].data_ptr(), gb[r].data_ptr(), _lib.ptr(ecb[r]),
+                                                       chan_t.data_ptr(), cta_chan.data_ptr() + 4 * b0,
+                                                       cta_word.data_ptr() + 4 * b0, b1 - b0, elems, chans, 8,
+                                                       mean_b[r].data_ptr(), seq[r].data_ptr() + 4 * b0, 0.1, None,
+                                                       status[r].data_ptr(), st())
+                    _lib.check(rc, "dqrm_dense_exchange_apply")
         torch.cuda.synchronize()
         assert all(int(s) == 0 for s in status)
         for r in range(world):
