@@ -365,12 +365,18 @@ int launch_gemm_tc(int mode, const float* x, const float* W_int, const float* b_
                    int accumulate, cudaStream_t st);
 
 // path: DQRM_LINEAR_AUTO / _FFMA / _TC.  AUTO: tensor cores from DQRM_MLP_TC_MIN_BATCH rows (default 256) -- below
-// that a layer is a handful of tiles and the cluster split-K FFMA kernel's shorter prologue wins.
-static bool use_tc(int path, int batch) {
+// that a layer is a handful of tiles and the cluster split-K FFMA kernel's shorter prologue wins -- and only for layers
+// whose weight matrix is at least DQRM_MLP_TC_MIN_DIM (default 32) in both directions: the 13-wide first bottom layer and
+// the 1-wide last top layer would pad a 128 x 64 x 32 tensor-core tile with 60-98 % zeros (batch 2048: 18.5 us for
+// 2048 x 512 x 13, 12.2 us for 2048 x 1 x 256 on the tensor-core kernel; profiles/r02_timeline_n1_batch2048.txt).
+// The weight gradient contracts over the batch: from 1024 rows on the FFMA kernel's 8-way cluster split leaves slices too
+// long (512 x 13 x 2048: 28 us against 20 us), so it stays on the tensor cores whatever the layer's shape.
+static bool use_tc(int path, int batch, int out_f, int in_f, bool weight_grad = false) {
   static const int min_batch = [] { const char* e = getenv("DQRM_MLP_TC_MIN_BATCH"); return e ? atoi(e) : 256; }();
+  static const int min_dim = [] { const char* e = getenv("DQRM_MLP_TC_MIN_DIM"); return e ? atoi(e) : 32; }();
   if (path == DQRM_LINEAR_FFMA || path == DQRM_LINEAR_FFMA_SERIAL) return false;
   if (path == DQRM_LINEAR_TC) return true;
-  return batch >= min_batch;
+  return batch >= min_batch && ((out_f >= min_dim && in_f >= min_dim) || (weight_grad && batch >= 1024));
 }
 
 }  // namespace dqrm
@@ -406,7 +412,7 @@ extern "C" int dqrm_linear_fwd(const float* x, const float* W_int, const float* 
   DQRM_REQUIRE(x && W_int && scale_row && out, -EINVAL, "linear_fwd: null argument");
   DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_fwd: bad shape/act");
   DQRM_REQUIRE(path >= 0 && path <= 3, -EINVAL, "linear_fwd: path=%d", path);
-  if (use_tc(path, batch))
+  if (use_tc(path, batch, out_features, in_features))
     return launch_gemm_tc(0, x, W_int, b_int, scale_row, nullptr, nullptr, out, nullptr, batch, out_features, in_features,
                           act, 0, static_cast<cudaStream_t>(stream));
   return launch_gemm<0>(x, W_int, b_int, scale_row, nullptr, nullptr, out, nullptr, batch, out_features, in_features, act,
@@ -420,7 +426,8 @@ extern "C" int dqrm_linear_bwd(const float* x, const float* W_int, const float* 
   DQRM_REQUIRE(batch >= 1 && out_features >= 1 && in_features >= 1 && act >= 0 && act <= 2, -EINVAL, "linear_bwd: bad shape/act");
   DQRM_REQUIRE(path >= 0 && path <= 3, -EINVAL, "linear_bwd: path=%d", path);     // (_SERIAL: same as _FFMA here)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool tcp = use_tc(path, batch);
+  const bool tcp = use_tc(path, batch, out_features, in_features);
+  const bool tcw = use_tc(path, batch, out_features, in_features, true);
   if (dx) {
     const int rc = tcp ? launch_gemm_tc(1, x, W_int, nullptr, scale_row, dout, out, dx, nullptr, batch, out_features,
                                         in_features, act, 0, st)
@@ -429,7 +436,7 @@ extern "C" int dqrm_linear_bwd(const float* x, const float* W_int, const float* 
     if (rc) return rc;
   }
   if (!dW) return 0;                                      // dx only (the caller runs dW on another stream)
-  if (tcp)
+  if (tcw)
     return launch_gemm_tc(2, x, W_int, nullptr, scale_row, dout, out, dW, db, batch, out_features, in_features, act,
                           accumulate ? 1 : 0, st);
   return launch_gemm<2>(x, W_int, nullptr, scale_row, dout, out, dW, db, batch, out_features, in_features, act,
