@@ -8,7 +8,10 @@ Per grid point (rows N, dim D, pooling P, batch B) it times, with CUDA events af
   scan      dqrm_table_absmax_scale                          bytes N*D*4
   fwd       dqrm_embbag_fwd (scale given)                    bytes L(4D+8) + B(8+4D) + B*D (int8 codes)
   fwd_int4  dqrm_embbag_fwd_int4 on bit-packed tables        bytes L(D/2+8) + B(8+4D)
-  bwd       dqrm_embbag_bwd + grad_pack + grad_merge_apply   bytes B*4D + L*8 + U*8D   
+  bwd       dqrm_embbag_bwd + grad_pack + grad_merge_apply   bytes B*4D + L*8 + U*8D   (the data-parallel
+            path at world 1: INT8 codes through the exchange slot)
+  bwd_sgd   dqrm_embbag_bwd_sgd (sort + de-duplicate + SGD row update in place, the single-process path a5+a10)
+                                                             bytes B*4D + L*8 + U*8D
 and reports achieved GB/s on those ALGORITHMIC bytes (U = unique rows, counted on the device).
 Tables are larger than the 126 MB L2 for N >= 4M (D=16) so no flush is needed there; for smaller tables a
 256 MB buffer is written between iterations.
@@ -58,6 +61,9 @@ def gpu_point(g, N, D, P, B, iters=5, flush=None):
     def run_bwd():
         g.backward(dout, world=1); g.exchange(world=1, rank=0); g.merge_apply(1e-6)
 
+    def run_bwd_sgd():
+        g.backward_sgd(dout, 1e-6)
+
     def run_int4():
         g.forward_int4(idx, off, ib, B, out=out)
 
@@ -67,7 +73,7 @@ def gpu_point(g, N, D, P, B, iters=5, flush=None):
     g.shadow = None
     g.scan_scales()
     g.pack_int4()
-    phases = {"scan": run_scan, "fwd": run_fwd, "bwd": run_bwd, "fwd_int4": run_int4}
+    phases = {"scan": run_scan, "fwd": run_fwd, "bwd": run_bwd, "bwd_sgd": run_bwd_sgd, "fwd_int4": run_int4}
     graphs = {}
     side = torch.cuda.Stream()
 
@@ -109,13 +115,15 @@ def gpu_point(g, N, D, P, B, iters=5, flush=None):
     U = int(g.uniq_count[0].item())
     ms = {k: float(np.median(v)) for k, v in t.items()}
     by = {"scan": N * D * 4, "fwd": L * (4 * D + 8) + B * (8 + 4 * D) + B * D, "bwd": B * 4 * D + L * 8 + U * 8 * D}
+    by["bwd_sgd"] = by["bwd"]
     by["fwd_int4"] = L * (D // 2 + 8) + B * (8 + 4 * D)
     if "fwd_shadow" in ms:
         by["fwd_shadow"] = L * (D // 2 + 8) + B * (8 + 4 * D) + B * D
     res = {"rows": N, "dim": D, "pooling": P, "batch": B, "lookups": L, "unique_rows": U, "ms": ms, "bytes": by,
            "GBps": {k: by[k] / (ms[k] * 1e-3) / 1e9 for k in ms},
            "fwd_bwd_GBps_with_scan": sum(by[k] for k in ("scan", "fwd", "bwd")) / (sum(ms[k] for k in ("scan", "fwd", "bwd")) * 1e-3) / 1e9,
-           "fwd_bwd_GBps_gather_only": (by["fwd"] + by["bwd"]) / ((ms["fwd"] + ms["bwd"]) * 1e-3) / 1e9}
+           "fwd_bwd_GBps_gather_only": (by["fwd"] + by["bwd"]) / ((ms["fwd"] + ms["bwd"]) * 1e-3) / 1e9,
+           "fwd_bwd_sgd_GBps_gather_only": (by["fwd"] + by["bwd_sgd"]) / ((ms["fwd"] + ms["bwd_sgd"]) * 1e-3) / 1e9}
     g.shadow = g._shadow_buf = None
     return res
 

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqrm_b200.so")
 
 MAX_TABLES = 64
-ABI_VERSION = 4
+ABI_VERSION = 5
 BWD_CTA_MAX_LOOKUPS = 16384
 STATUS_INDEX_RANGE, STATUS_OFFSET_ORDER, STATUS_CAPACITY, STATUS_P2P_TIMEOUT = 1, 2, 4, 8
 
@@ -44,6 +44,8 @@ SIGNATURES = {
     "dqrm_embbag_bwd": (_i32, [_i32, _p, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p, _i32, _p,
                                _p, _p, _sz, _p]),
     "dqrm_grad_absmax_scale": (_i32, [_i32, _i32, _p, _p, _i64, _i32, _p, _p]),
+    "dqrm_embbag_bwd_sgd": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p,
+                                   _f32, _p, _f32, _p, _f32, _p, _p, _sz, _p]),
     "dqrm_sgd_rows": (_i32, [_i32, _p, _p, _i32, _p, _p, _p, _i64, _f32, _p, _f32, _p, _f32, _p]),
     "dqrm_slot_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "dqrm_slot_layout": (_i32, [_i32, _i64, _i32, _i32, C.POINTER(_sz), C.POINTER(_sz)]),
@@ -86,7 +88,7 @@ _lib = None
 
 # entry points that enqueue at least one of OUR kernels per call (bench.py's gpu_launches claim)
 LAUNCHING = ("dqrm_table_absmax_scale", "dqrm_scale_from_absmax", "dqrm_embbag_fwd", "dqrm_embbag_bwd",
-             "dqrm_grad_absmax_scale", "dqrm_sgd_rows", "dqrm_grad_pack", "dqrm_grad_topk", "dqrm_grad_merge_apply",
+             "dqrm_grad_absmax_scale", "dqrm_sgd_rows", "dqrm_embbag_bwd_sgd", "dqrm_grad_pack", "dqrm_grad_topk", "dqrm_grad_merge_apply",
              "dqrm_interact_fwd", "dqrm_interact_bwd", "dqrm_linear_fakequant", "dqrm_fake_quant",
              "dqrm_mlp_fakequant_all", "dqrm_linear_fwd", "dqrm_linear_bwd",
              "dqrm_blockmax_build", "dqrm_blockmax_update", "dqrm_blockmax_scan", "dqrm_blockmax_update_shard",

@@ -104,6 +104,17 @@ inline int fill_tables(TableSet& ts, int num_tables, const float* const* weight,
   return 0;
 }
 
+// Fused in-place row update of the de-duplicating backward (dqrm_embbag_bwd_sgd): plain SGD, or row-wise sparse
+// Adagrad when `mom` is set; the arithmetic of sgd_rows_kernel (embbag_bwd.cu).
+struct RowUpdate {
+  float* W;
+  float* mom;
+  float neg_lr;
+  const float* lr_dev;
+  float inv_world;
+  float eps;
+};
+
 // lanes cooperating on one row: dim/4 float4 columns, rounded up to a power of two (<= 32);
 // wider rows give each lane several columns.
 struct RowLanes { int group; int cols; };

@@ -430,16 +430,25 @@ int embbag_bwd_large(int t, long long rows, long long idx_begin, long long idx_e
                      const float* dout, int64_t dts, int64_t dbs, const float* fwd_scale,
                      int64_t capacity, int32_t* uniq_rows, int32_t* uniq_count, float* grad_sums,
                      int grad_bits, float* grad_scale_local, int32_t* status,
-                     void* workspace, size_t workspace_bytes, cudaStream_t st);   // embbag_bwd_large.cu
+                     void* workspace, size_t workspace_bytes, cudaStream_t st, const RowUpdate* upd);   // embbag_bwd_large.cu
 }
 
-extern "C" int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
-                               const int64_t* indices, const int64_t* offsets, const int64_t* idx_begin, int64_t bags,
-                               const float* dout, int64_t dout_table_stride, int64_t dout_bag_stride,
-                               const float* fwd_scale,
-                               int64_t capacity, int32_t* uniq_rows, int32_t* uniq_count, float* grad_sums,
-                               int grad_bits, float* grad_scale_local,
-                               int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+struct FusedUpdate {                   // dqrm_embbag_bwd_sgd: the row update that follows the de-duplication
+  float* const* weight;
+  float* const* momentum;
+  float lr;
+  const float* lr_dev;
+  float inv_world;
+  float eps;
+};
+
+static int bwd_impl(int num_tables, const int64_t* rows, int dim,
+                    const int64_t* indices, const int64_t* offsets, const int64_t* idx_begin, int64_t bags,
+                    const float* dout, int64_t dout_table_stride, int64_t dout_bag_stride,
+                    const float* fwd_scale,
+                    int64_t capacity, int32_t* uniq_rows, int32_t* uniq_count, float* grad_sums,
+                    int grad_bits, float* grad_scale_local,
+                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream, const FusedUpdate* fu) {
   DQRM_REQUIRE(rows && indices && offsets && idx_begin && dout && uniq_rows && uniq_count && grad_sums && status,
                -EINVAL, "embbag_bwd: null argument");
   DQRM_REQUIRE(num_tables >= 1 && num_tables <= DQRM_MAX_TABLES, -E2BIG, "embbag_bwd: num_tables=%d", num_tables);
@@ -469,9 +478,12 @@ extern "C" int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
       (lmax > DQRM_BWD_CTA_MAX_LOOKUPS || workspace_bytes >= dqrm::bwd_large_workspace_bytes(lmax, dim))) {
     // one persistent whole-chip radix-sort + fold launch per table
     for (int k = 0; k < num_tables; ++k) {
+      RowUpdate upd{};
+      if (fu) upd = RowUpdate{fu->weight[k], fu->momentum ? fu->momentum[k] : nullptr, -fu->lr, fu->lr_dev, fu->inv_world, fu->eps};
       int rc = embbag_bwd_large(k, rows[k], idx_begin[k], idx_begin[k + 1], dim, indices, offsets, bags, dout,
                                 dout_table_stride, dout_bag_stride, fwd_scale, capacity, uniq_rows, uniq_count,
-                                grad_sums, grad_bits, grad_scale_local, status, workspace, workspace_bytes, st);
+                                grad_sums, grad_bits, grad_scale_local, status, workspace, workspace_bytes, st,
+                                fu ? &upd : nullptr);
       if (rc) return rc;
     }
     return 0;
@@ -510,7 +522,41 @@ extern "C" int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
   else DQRM_BWD(4);
 #undef DQRM_BWD
   DQRM_LAUNCH_CHECK("embbag_bwd_cta_kernel");
+  if (fu)                                // few lookups per table: the single-CTA de-duplication, then the row update
+    return dqrm_sgd_rows(num_tables, fu->weight, rows, dim, uniq_rows, uniq_count, grad_sums, capacity, fu->lr, fu->lr_dev,
+                         fu->inv_world, fu->momentum, fu->eps, stream);
   return 0;
+}
+
+extern "C" int dqrm_embbag_bwd(int num_tables, const int64_t* rows, int dim,
+                               const int64_t* indices, const int64_t* offsets, const int64_t* idx_begin, int64_t bags,
+                               const float* dout, int64_t dout_table_stride, int64_t dout_bag_stride,
+                               const float* fwd_scale,
+                               int64_t capacity, int32_t* uniq_rows, int32_t* uniq_count, float* grad_sums,
+                               int grad_bits, float* grad_scale_local,
+                               int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_impl(num_tables, rows, dim, indices, offsets, idx_begin, bags, dout, dout_table_stride, dout_bag_stride,
+                  fwd_scale, capacity, uniq_rows, uniq_count, grad_sums, grad_bits, grad_scale_local, status, workspace,
+                  workspace_bytes, stream, nullptr);
+}
+
+extern "C" int dqrm_embbag_bwd_sgd(int num_tables, float* const* weight, const int64_t* rows, int dim,
+                                   const int64_t* indices, const int64_t* offsets, const int64_t* idx_begin, int64_t bags,
+                                   const float* dout, int64_t dout_table_stride, int64_t dout_bag_stride,
+                                   const float* fwd_scale,
+                                   int64_t capacity, int32_t* uniq_rows, int32_t* uniq_count, float* grad_sums,
+                                   float lr, const float* lr_dev, float inv_world, float* const* momentum, float eps,
+                                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  DQRM_REQUIRE(weight, -EINVAL, "embbag_bwd_sgd: null argument");
+  for (int k = 0; k < num_tables && k < DQRM_MAX_TABLES; ++k) {
+    DQRM_REQUIRE(weight[k] && (reinterpret_cast<uintptr_t>(weight[k]) & 15u) == 0, -EINVAL,
+                 "embbag_bwd_sgd: table %d base pointer is null or not 16-byte aligned", k);
+    DQRM_REQUIRE(!momentum || momentum[k], -EINVAL, "embbag_bwd_sgd: momentum[%d] is null", k);
+  }
+  const FusedUpdate fu{weight, momentum, lr, lr_dev, inv_world, eps};
+  return bwd_impl(num_tables, rows, dim, indices, offsets, idx_begin, bags, dout, dout_table_stride, dout_bag_stride,
+                  fwd_scale, capacity, uniq_rows, uniq_count, grad_sums, 8, nullptr, status, workspace,
+                  workspace_bytes, stream, &fu);
 }
 
 extern "C" int dqrm_grad_absmax_scale(int num_tables, int dim, const float* grad_sums, const int32_t* uniq_count,

@@ -558,6 +558,29 @@ class EmbeddingTableGroup:
                                  self.status.data_ptr(), self._bwd_ws.data_ptr(), self._bwd_ws_bytes, st)
         _lib.check(rc, "dqrm_embbag_bwd")
 
+    def backward_sgd(self, dout, lr, inv_world=1.0, momentum=None, eps=1e-10, last=None, ste_done=False):
+        """(a5 + a10 in one call) de-duplicate the row gradients of a forward and apply the single-process row update
+        in place -- SGD, or RW-Adagrad with `momentum` -- without the sums travelling through memory on the
+        radix-sort path.  Same table bits as backward() followed by sgd_apply()."""
+        lib, st = self.lib, _lib.stream_ptr()
+        indices, offsets, idx_begin, ib, bags, full_precision = last if last is not None else self.last
+        cap = max(max(idx_begin[k + 1] - idx_begin[k] for k in range(self.T)), 1)
+        if self.fixed_capacity is not None:
+            if cap > self.fixed_capacity:
+                raise _lib.DqrmLibraryError(f"{cap} lookups on one table exceed fixed_capacity={self.fixed_capacity}")
+            cap = self.fixed_capacity
+        self._ensure_step_buffers(cap, 1)
+        mom = _lib.ptr_array(momentum) if momentum is not None else None
+        rc = lib.dqrm_embbag_bwd_sgd(self.T, self._wptrs(), self._rows_arr, self.dim, indices.data_ptr(),
+                                     offsets.data_ptr(), ib, bags, dout.data_ptr(), dout.stride(0), dout.stride(1),
+                                     None if (full_precision or ste_done) else self.scale.data_ptr(),
+                                     self.capacity, self.uniq_rows.data_ptr(), self.uniq_count.data_ptr(),
+                                     self.grad_sums.data_ptr(), float(lr), _lib.ptr(self.lr_dev), float(inv_world), mom,
+                                     float(eps), self.status.data_ptr(), self._bwd_ws.data_ptr(), self._bwd_ws_bytes, st)
+        _lib.check(rc, "dqrm_embbag_bwd_sgd")
+        self._shadow_update_rows(from_slots=False)
+        self._tracker_update(from_slots=False)
+
     def set_grad_bit(self, bits):
         """Change the gradient code width after a backward: re-size the slots, refresh the local scale."""
         self.grad_bit = int(bits)

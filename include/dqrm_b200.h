@@ -49,7 +49,7 @@ extern "C" {
 /* `lr_dev` (dqrm_sgd_rows, dqrm_grad_merge_apply, dqrm_dense_apply, dqrm_dense_apply_gathered): when not NULL the
  * learning rate is read from this device fp32 scalar at kernel run time instead of the by-value `lr`, so a captured
  * CUDA graph follows an LR schedule (LRPolicyScheduler, dlrm_s_pytorch_comm_grad.py:221-255) without re-capture. */
-#define DQRM_ABI_VERSION 4
+#define DQRM_ABI_VERSION 5
 #define DQRM_MAX_TABLES 64           /* tables per call (kernel-parameter descriptor size) */
 #define DQRM_BWD_CTA_MAX_LOOKUPS 16384 /* per-table lookups handled by the single-CTA sort path */
 #define DQRM_FOLD_BLOCK 64            /* duplicate-row gradients: left fold in lookup order; rows with more duplicates
@@ -222,6 +222,26 @@ DQRM_API int dqrm_grad_absmax_scale(int num_tables, int dim, const float* grad_s
 DQRM_API int dqrm_sgd_rows(int num_tables, float* const* weight, const int64_t* rows, int dim,
                   const int32_t* uniq_rows, const int32_t* uniq_count, const float* grad_sums, int64_t capacity,
                   float lr, const float* lr_dev, float inv_world, float* const* momentum, float eps, void* stream);
+
+/* -------------------------------------------------------- (a5 + a10, fused) --
+ * De-duplicating backward WITH the row update applied in place (the single-process path: ATen sparse EmbeddingBag
+ * backward, dlrm_s_pytorch_comm_grad.py:1938, then torch.optim.SGD.step() on the sparse gradient,
+ * dlrm_s_pytorch_single_gpu.py:1944-1946 / W.add_(-lr*grad), sgd...parallel_comm.py:626; with `momentum` the
+ * row-wise sparse Adagrad of optim/rwsadagrad.py:97-113).  Same arguments as dqrm_embbag_bwd + dqrm_sgd_rows and the
+ * same table bits as calling the two in turn: duplicates are summed first (the fixed fold order above), then
+ * W[row] += (-lr) * (sum * inv_world).  On the radix-sort path the update runs inside the fold of the same kernel --
+ * the table row is fetched beside the dOut gathers and the sums never travel through memory; tables with few lookups
+ * take the single-CTA de-duplication followed by the row-update kernel.
+ *   uniq_rows / uniq_count   out, as in dqrm_embbag_bwd (the rows that changed: scale tracker, INT4 shadow)
+ *   grad_sums                scratch [num_tables, capacity, dim]; contents undefined afterwards
+ */
+DQRM_API int dqrm_embbag_bwd_sgd(int num_tables, float* const* weight, const int64_t* rows, int dim,
+                    const int64_t* indices, const int64_t* offsets, const int64_t* idx_begin, int64_t bags,
+                    const float* dout, int64_t dout_table_stride, int64_t dout_bag_stride,
+                    const float* fwd_scale,
+                    int64_t capacity, int32_t* uniq_rows, int32_t* uniq_count, float* grad_sums,
+                    float lr, const float* lr_dev, float inv_world, float* const* momentum, float eps,
+                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ----------------------------------------------------------- (a7 steps 3-4) --
  * Quantise this rank's de-duplicated row gradients into its exchange slot.

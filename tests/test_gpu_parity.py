@@ -357,6 +357,77 @@ def test_sgd_rows_and_rwsadagrad():
         np.testing.assert_allclose(cpu(g.weights[t]), Wn, rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("case", ["zipf_onehot", "three_rows", "ragged_multihot", "dim64", "dim128", "small_cta"])
+@pytest.mark.parametrize("adagrad", [False, True])
+def test_bwd_sgd_fused(case, adagrad):
+    """dqrm_embbag_bwd_sgd (north-star kernel 3: sort + de-duplicate + row update in ONE kernel on the radix-sort
+    path): updated-row lists equal to the oracle's coalesce, tables bit-identical to backward() + sgd_apply() and to
+    the oracle's W.add_(-lr * coalesced grad) (sgd_quantized_gradients_parallel_comm.py:626); RW-Adagrad state and
+    tables against optim/rwsadagrad.py:97-113 as restated by the oracle (fp32 rounding of the row mean allowed)."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    rng = np.random.RandomState(17)
+    dim = {"dim64": 64, "dim128": 128}.get(case, 16)
+    if case == "zipf_onehot":
+        rows, B = 300, 40000
+        idx = torch.from_numpy(np.minimum(rng.zipf(1.1, size=B) - 1, rows - 1).astype(np.int64))
+        off = torch.arange(B, dtype=torch.int64)
+    elif case == "three_rows":
+        rows, B = 3, 50000
+        idx = torch.from_numpy(rng.randint(0, 3, size=B).astype(np.int64))
+        off = torch.arange(B, dtype=torch.int64)
+    elif case == "ragged_multihot":
+        rows, B = 100000, 9000
+        idx, off = synthetic.random_bags(rows, B, 7, rng)
+        off[1000:1100] = off[1000]
+    elif case == "small_cta":
+        rows, B = 5000, 300                              # few lookups: single-CTA de-duplication + row-update kernel
+        idx, off = synthetic.random_bags(rows, B, 3, rng)
+    else:
+        rows, B = 1 << 20, 20000
+        idx, off = synthetic.random_bags(rows, B, 3, rng, fixed=True)
+    W = synthetic.table_weights_numpy(rows, dim, rng)
+    lr = 0.05
+    i2, o2, ib, bags = tables.EmbeddingTableGroup.pack_inputs([idx], [off], "cuda")
+    dout = rng.randn(1, bags, dim).astype(np.float32)
+    res = []
+    for fused in (True, False):
+        g = tables.EmbeddingTableGroup([torch.tensor(W, device="cuda")], embedding_bit=4)
+        mom = [torch.zeros(rows, device="cuda")] if adagrad else None
+        for rep in range(2):                             # two steps: the workspace and the state are reused
+            g.scan_scales()
+            g.forward(i2, o2, ib, bags)
+            d = torch.tensor(dout * (rep + 1), device="cuda")
+            if fused:
+                g.backward_sgd(d, lr, momentum=mom, eps=1e-10)
+            else:
+                g.backward(d, world=1)
+                g.sgd_apply(lr, momentum=mom, eps=1e-10)
+            g.check_status()
+        U = int(g.uniq_count[0])
+        res.append((cpu(g.weights[0]).copy(), cpu(g.uniq_rows[0, :U]).copy(), cpu(mom[0]).copy() if adagrad else None))
+    (Wf, rf, mf), (Wu, ru, mu) = res
+    assert np.array_equal(rf, ru)
+    assert bits_equal(Wf, Wu)
+    if adagrad:
+        assert bits_equal(mf, mu)
+    # against the oracle
+    Wo, mo = W.copy(), np.zeros(rows, dtype=np.float32)
+    for rep in range(2):
+        r0, v0 = O.embbag_backward_spec(dout[0] * np.float32(rep + 1), idx.numpy(), off.numpy(), O.table_scale_spec(Wo, 4))
+        urows, sums = O.coalesce_spec(r0, v0)
+        if adagrad:
+            O.rwsadagrad_rows_spec(Wo, mo, urows, sums, lr, 1e-10)
+        else:
+            O.weight_update_emb_unquantized_spec(Wo, urows, sums, lr)
+    assert np.array_equal(rf, urows)
+    if adagrad:
+        np.testing.assert_allclose(mf, mo, rtol=2e-6, atol=1e-12)
+        np.testing.assert_allclose(Wf, Wo, rtol=1e-5, atol=1e-7)
+    else:
+        assert bits_equal(Wf, Wo)
+
+
+
 def test_rwsadagrad_rows_vs_reference_golden():
     """dqrm_sgd_rows with momentum against 4 steps of the REFERENCE's optim/rwsadagrad.py:97-113
     (tests/golden/rwsadagrad_rows.npz: sparse gradients with duplicate rows, state and weights after every step)."""

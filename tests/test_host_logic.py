@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(raw, name), name
         assert name in _lib.SIGNATURES, f"{name} declared in the header but not bound in _lib.SIGNATURES"
     assert set(_lib.SIGNATURES) == declared
-    assert lib.dqrm_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.dqrm_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_argument_validation_without_a_device():

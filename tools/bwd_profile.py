@@ -8,6 +8,7 @@ from deep_quantized_recommendation_model_dqrm_b200 import synthetic, tables
 p = argparse.ArgumentParser()
 p.add_argument("--rows", type=int, default=10_000_000); p.add_argument("--dim", type=int, default=64)
 p.add_argument("--pooling", type=int, default=16); p.add_argument("--batch", type=int, default=65536)
+p.add_argument("--fused", action="store_true", help="dqrm_embbag_bwd_sgd instead of bwd + pack + merge_apply")
 a = p.parse_args()
 N, D, P, B = a.rows, a.dim, a.pooling, a.batch
 W = torch.empty((N, D), device="cuda"); synthetic.table_weights_(W, 0, 99)
@@ -19,7 +20,8 @@ dout = torch.randn((1, B, D), device="cuda", generator=gen) * 1e-4
 out = torch.empty((1, B, D), device="cuda")
 def step():
     g.scan_scales(); g.forward(idx, off, [0, B * P], B, out=out)
-    g.backward(dout, world=1); g.exchange(world=1, rank=0); g.merge_apply(0.01)
+    if a.fused: g.backward_sgd(dout, 0.01)
+    else: g.backward(dout, world=1); g.exchange(world=1, rank=0); g.merge_apply(0.01)
 for _ in range(3): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:

@@ -1,0 +1,6 @@
+#!/bin/bash
+O=gpurun_out/r2_54; mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "large or bwd_sgd or max_cta" 2>&1 | tail -5 > $O/tests.log
+timeout 200 python tools/bwd_profile.py > $O/prof_unfused.txt 2>&1
+timeout 200 python tools/bwd_profile.py --fused > $O/prof_fused.txt 2>&1
+timeout 200 python tools/bwd_profile.py --fused --dim 16 --pooling 16 > $O/prof_fused_d16p16.txt 2>&1
