@@ -20,6 +20,7 @@ from . import _lib, extend_distributed as ext_dist
 from .quantization_supp.quant_modules import QuantAct, QuantEmbeddingBagTwo, QuantLinear  # noqa: F401
 from .quantization_supp.quant_modules_not_quantize_grad import QuantEmbeddingBagTwo, QuantLinear  # noqa: F401,F811
 from .quantization_supp.quant_modules import EmbBagGroupFunction, _new_group
+from .sgd_quantized_gradients_parallel_comm import _emb_groups
 from .sgd_quantized_gradients_parallel_comm import (clear_gradients, grad_update_parallel_comm,  # noqa: F401
                                                     weight_syncc, weight_update_parallel_comm)
 from .tables import EmbeddingTableGroup
@@ -356,6 +357,9 @@ def train_iteration(dlrm, X, lS_o, lS_i, T, lr, world_size=1, rank=0, device=Non
     Z = dlrm_wrap(dlrm, X, lS_o, lS_i, True, device)
     E = loss_fn_wrap(Z, T, True, device, args)
     clear_gradients(dlrm)
+    for g in _emb_groups(dlrm):
+        if g.fused_update is not None:               # single process, un-quantised: the backward applies the rows itself
+            g.fused_update["lr"] = float(lr)
     E.backward()
     grad_update_parallel_comm(dlrm, world_size, emb_grad_quantized=quantize_embedding_bag_gradient,
                               num_bits=embedding_bag_gradient_bit_num, ranking_range=False, rank_for_debug=rank,

@@ -22,11 +22,15 @@ class RWSAdagrad(Optimizer):
         super().__init__(params, defaults)
         self._groups = []          # (EmbeddingTableGroup, momentum tensors, step counter)
 
-    def attach_table_group(self, group):
-        """Register a fused table group; its tables get row-wise state and are updated by step()."""
+    def attach_table_group(self, group, fused=False):
+        """Register a fused table group; its tables get row-wise state and are updated by step().  With `fused` the
+        row update runs inside the group's de-duplicating backward (dqrm_embbag_bwd_sgd: one kernel sorts,
+        de-duplicates and applies m[row] / W[row]); step() then only advances the learning-rate schedule."""
         init = self.defaults["initial_accumulator_value"]
         mom = [torch.full((n,), init, dtype=torch.float32, device=group.device) for n in group.rows]
         self._groups.append([group, mom, 0])
+        if fused:
+            group.enable_fused_update(self.defaults["lr"], momentum=mom, eps=self.defaults["eps"])
         return mom
 
     @torch.no_grad()
@@ -37,6 +41,10 @@ class RWSAdagrad(Optimizer):
             group, mom, _ = rec
             rec[2] += 1
             clr = d["lr"] / (1.0 + (rec[2] - 1.0) * d["lr_decay"])
+            if group.applied_fused:                  # this step's update ran inside the backward; set the next step's rate
+                group.applied_fused = False
+                group.fused_update["lr"] = d["lr"] / (1.0 + rec[2] * d["lr_decay"])
+                continue
             group.sgd_apply(clr, inv_world=1.0, momentum=mom, eps=d["eps"])
         table_params = {id(w) for rec in self._groups for w in rec[0].weights}
         for pg in self.param_groups:

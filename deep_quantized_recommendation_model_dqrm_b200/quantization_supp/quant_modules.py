@@ -47,6 +47,12 @@ class EmbBagGroupFunction(Function):
             dout = dout.contiguous()
         ste_done = getattr(g, "ste_done_for", None) == dout.data_ptr()      # fused into the interaction backward
         g.ste_done_for = None
+        fu = g.fused_update
+        if fu is not None and g.dp_world == 1 and not g.materialize_grads:
+            # single process, un-quantised: sort + de-duplicate + row update in one call (north-star kernel 3)
+            g.backward_sgd(dout, fu["lr"], momentum=fu["momentum"], eps=fu["eps"], last=ctx.last, ste_done=ste_done)
+            g.applied_fused = True
+            return (None, None, None, None, None, None) + (None,) * g.T
         if g.side_backward:
             # de-duplicating backward (+ the exchange / pack) on the group's side stream: the bottom-MLP backward that
             # autograd runs next only needs the interaction's OTHER output; finish_exchange() joins

@@ -150,11 +150,16 @@ def weight_update_parallel_comm(model, lr, emb_grad_quantized=True, update_embed
         raise NotImplementedError("ranking_range / error compensation are not called by the reference drivers")
     with torch.no_grad():
         for g in _emb_groups(model):
+            if g.applied_fused and (emb_grad_quantized or num_gpus > 1 or not update_embedding):
+                raise RuntimeError("the embedding update already ran inside the backward (fused_update is the "
+                                   "single-process un-quantised path)")
             if g.applied_eagerly and not (update_embedding and emb_grad_quantized):
                 raise RuntimeError("the embedding update already ran behind the exchange (eager_apply)")
         if update_embedding:
             for g in _emb_groups(model):
-                if g.applied_eagerly:                # done on the side stream, joined by grad_update_parallel_comm
+                if g.applied_fused:                  # done inside the de-duplicating backward (dqrm_embbag_bwd_sgd)
+                    g.applied_fused = False
+                elif g.applied_eagerly:              # done on the side stream, joined by grad_update_parallel_comm
                     g.applied_eagerly = False
                 elif emb_grad_quantized or num_gpus > 1:
                     g.merge_apply(lr)

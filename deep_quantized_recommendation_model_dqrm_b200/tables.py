@@ -85,6 +85,8 @@ class EmbeddingTableGroup:
         self._bwd_forked = None
         self.eager_apply = False     # ... and merge_apply() right behind the exchange, on the same stream
         self.applied_eagerly = False
+        self.fused_update = None     # dict(lr, momentum, eps): single-process row update INSIDE the de-duplicating backward
+        self.applied_fused = False   # ... which then already ran when the optimizer / weight_update_parallel_comm is called
         self.xchg_stream = None
         self.exchange_started = False
         self.dp_world, self.dp_rank = 1, 0
@@ -580,6 +582,13 @@ class EmbeddingTableGroup:
         _lib.check(rc, "dqrm_embbag_bwd_sgd")
         self._shadow_update_rows(from_slots=False)
         self._tracker_update(from_slots=False)
+
+    def enable_fused_update(self, lr, momentum=None, eps=1e-10):
+        """Single process, un-quantised row gradients (torch.optim.SGD on the sparse gradient, or RW-Adagrad with
+        `momentum`): let the autograd backward of the group apply the row update itself (dqrm_embbag_bwd_sgd) --
+        weight_update_parallel_comm / RWSAdagrad.step then find it done.  `lr` may be changed between steps
+        (fused_update["lr"]); disable with group.fused_update = None."""
+        self.fused_update = {"lr": float(lr), "momentum": momentum, "eps": float(eps)}
 
     def set_grad_bit(self, bits):
         """Change the gradient code width after a backward: re-size the slots, refresh the local scale."""

@@ -171,3 +171,47 @@ def test_rwsadagrad_optimizer_class():
     for t in range(2):
         np.testing.assert_allclose(mom[t].cpu().numpy(), ref_m[t], rtol=1e-5, atol=1e-12)
         np.testing.assert_allclose(g.weights[t].detach().cpu().numpy(), ref_W[t], rtol=1e-5, atol=1e-7)
+
+
+def test_fused_update_through_autograd_and_optimizer():
+    """group.enable_fused_update / RWSAdagrad.attach_table_group(fused=True): the autograd backward of the table group
+    applies the row update itself (dqrm_embbag_bwd_sgd); tables, row-wise state and the optimizer's schedule come out
+    bit-identical to backward + RWSAdagrad.step (sgd_apply), and plain SGD to weight_update_parallel_comm's
+    un-quantised branch (sgd_quantized_gradients_parallel_comm.py:626)."""
+    from deep_quantized_recommendation_model_dqrm_b200 import synthetic, tables
+    from deep_quantized_recommendation_model_dqrm_b200.optim.rwsadagrad import RWSAdagrad
+    from deep_quantized_recommendation_model_dqrm_b200.quantization_supp.quant_modules import EmbBagGroupFunction
+    rows, dim, B = [500, 7, 30000], 16, 6000           # the 30000-row table takes the one-kernel sort path
+    rng = np.random.RandomState(8)
+    Ws = [synthetic.table_weights_numpy(n, dim, rng) for n in rows]
+    douts = [torch.tensor(rng.randn(3, B, dim).astype(np.float32), device="cuda") for _ in range(3)]
+    for adagrad in (True, False):
+        res = []
+        for fused in (True, False):
+            g = tables.EmbeddingTableGroup([torch.nn.Parameter(torch.tensor(w, device="cuda")) for w in Ws], embedding_bit=4)
+            g.dp_world, g.dp_rank, g.process_group, g.materialize_grads, g.modules = 1, 0, None, False, None
+            if adagrad:
+                opt = RWSAdagrad(g.weights, lr=0.05, lr_decay=0.1, eps=1e-10)
+                mom = opt.attach_table_group(g, fused=fused)
+            elif fused:
+                g.enable_fused_update(0.05)
+            for step in range(3):
+                X, lS_o, lS_i, T = synthetic.criteo_batch(rows, B, seed=30 + step)
+                idx, off, ib, bags = tables.EmbeddingTableGroup.pack_inputs(lS_i, lS_o, "cuda")
+                g.scan_scales()
+                out = EmbBagGroupFunction.apply(g, idx, off, ib, bags, False, *g.weights)
+                if not adagrad and fused:
+                    g.fused_update["lr"] = 0.05 / (step + 1)
+                out.backward(douts[step])
+                assert g.applied_fused == fused
+                if adagrad:
+                    opt.step()
+                elif fused:
+                    g.applied_fused = False
+                else:
+                    g.sgd_apply(0.05 / (step + 1))
+                g.check_status()
+            res.append(([w.detach().cpu().numpy().copy() for w in g.weights],
+                        [m.cpu().numpy().copy() for m in mom] if adagrad else []))
+        for a, b in zip(res[0][0] + res[0][1], res[1][0] + res[1][1]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
