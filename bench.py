@@ -19,8 +19,10 @@ Headline (top-level keys) = BASELINE configs[1]: batch 128 per GPU (weak scaling
            timed region.
   step_ms  median / min / max / p95 of the individual step durations inside the timed region (one CUDA
            event per step), so the spread of the K steps is visible.
-  cpu_baseline / --impl reference: the oracle port of the reference's CPU path (torch CPU ops in the
-           reference's order), all host threads, same config.
+  cpu_baseline / --impl reference: the reference ITSELF (the unmodified files under oracle/_ref, copied there by the
+           committed recipe oracle/make_ref.py: DLRM_Net + clear_gradients + grad_update_parallel_comm +
+           weight_update_parallel_comm, single Gloo rank, all host threads, GPUs hidden), same config;
+           `kind: "reference"`.  Without oracle/_ref: the oracle port of that path (`kind: "port"`).
 Beside the headline, the same JSON line carries the other BASELINE configs measured the same way:
   "configs2_kaggle_global2048"   configs[2]: FIXED global batch 2048 split over the N GPUs (strong scaling)
   "configs3_terabyte_global8192" configs[3]: Terabyte shape (48 GB of tables, dim 64), fixed global batch 8192
@@ -41,6 +43,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"] or "--impl=reference" in sys.argv:
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""       # the reference arm is the reference's CPU path: it must not see a GPU
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -181,23 +186,117 @@ def oracle_arm(cfg, batch, steps, warmup):
     return batch / (ms / 1000.0), ms, torch.get_num_threads(), build_s
 
 
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, "dlrm_s_pytorch_comm_grad.py"))
+
+
+def reference_arm(cfg, batch, steps, warmup):
+    """The UNMODIFIED reference (oracle/_ref, see oracle/make_ref.py) on the host cores: its DLRM_Net, its training
+    step (dlrm_s_pytorch_comm_grad.py:1909-1957: forward, BCE loss, clear_gradients, backward,
+    grad_update_parallel_comm with 8-bit embedding gradients, weight_update_parallel_comm) as ONE Gloo rank -- the
+    loop oracle/make_golden.py drives for the golden vectors.  The only shim: Tensor.cuda() is the identity
+    (quant_utils.py:336 calls .cuda() unconditionally).  Returns (samples_per_s, ms_per_step, cores, build_s)."""
+    from deep_quantized_recommendation_model_dqrm_b200 import synthetic
+    import torch.distributed as dist
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import dlrm_s_pytorch_comm_grad as drv                     # oracle/_ref (the reference's own driver module)
+    import sgd_quantized_gradients_parallel_comm as sgd        # oracle/_ref
+    assert os.path.dirname(os.path.abspath(drv.__file__)) == REF_DIR
+    if not dist.is_initialized():
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    t0 = time.perf_counter()
+    drv.full_precision_flag = False                            # train(): = args.pretrain_and_quantize (drv:1425-1426)
+    rows, dim = cfg["rows"], cfg["dim"]
+    ln_bot, ln_top = np.array(cfg["ln_bot"]), np.array(mlp_sizes(cfg))
+    m = drv.DLRM_Net(dim, np.array(rows), ln_bot, ln_top, arch_interaction_op="dot", sigmoid_bot=-1,
+                     sigmoid_top=ln_top.size - 2, ndevices=-1, loss_function="bce", quantization_flag=True,
+                     embedding_bit=4, weight_bit=4, quantize_act_and_lin=True, mlp_channelwise=True,
+                     quantize_activation=False)
+    rng = np.random.RandomState(123)
+    for k, n in enumerate(rows):                               # same weight law as our arm (host generator)
+        w = torch.empty((n, dim), dtype=torch.float32)
+        synthetic.table_weights_(w, k, 1234)
+        m.emb_l[k].embedding_bag.weight.data = w.requires_grad_(True)
+    for layers, ln in ((m.bot_l, ln_bot), (m.top_l, ln_top)):
+        qls = [l for l in layers if hasattr(l, "weight_bit")]
+        for l, (W, b) in zip(qls, synthetic.mlp_params(ln, rng)):
+            l.weight.data = torch.tensor(W)
+            l.bias.data = torch.tensor(b)
+    build_s = time.perf_counter() - t0
+    loss_fn = torch.nn.BCELoss(reduction="mean")
+    times = []
+    for s in range(warmup + steps):
+        X, lS_o, lS_i, T = synthetic.criteo_batch(rows, batch, seed=1000 + s)
+        t1 = time.perf_counter()
+        Z = m(X, lS_o, lS_i)
+        E = loss_fn(Z, T)
+        sgd.clear_gradients(m)
+        E.backward()
+        sgd.grad_update_parallel_comm(m, 1, emb_grad_quantized=True, num_bits=8, ranking_range=False,
+                                      rank_for_debug=0, iteration_count=s)
+        sgd.weight_update_parallel_comm(m, LR, emb_grad_quantized=True, update_embedding=True, num_gpus=1,
+                                        rank_for_debug=0)
+        float(E.detach())
+        if s >= warmup:
+            times.append(time.perf_counter() - t1)
+    ms = 1000.0 * float(np.mean(times))
+    return batch / (ms / 1000.0), ms, torch.get_num_threads(), build_s
+
+
+def cpu_arm(cfg, batch, steps, warmup):
+    """(value, ms, cores, build_s, kind, what): the reference itself when oracle/_ref travelled, else its oracle port."""
+    if reference_available():
+        try:
+            return reference_arm(cfg, batch, steps, warmup) + ("reference", "the unmodified reference (oracle/_ref), one Gloo rank")
+        except Exception as e:                                 # noqa: BLE001  (report, fall back to the port)
+            print(f"reference arm failed ({type(e).__name__}: {e}); falling back to the oracle port", file=sys.stderr)
+    return oracle_arm(cfg, batch, steps, warmup) + ("port", "oracle port of the reference CPU path, single process")
+
+
+def cpu_baseline_subprocess(args, cfg):
+    """cpu_baseline leg of OUR arm: the reference arm in a fresh process (its Gloo group and hidden GPUs must not
+    meet this process's NCCL group), a bounded sample of the same workload."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1", "--steps", str(args.cpu_steps),
+           "--warmup", "1", "--batch", str(args.batch), "--workload", args.workload]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
+    for ln in reversed(r.stdout.splitlines()):
+        if ln.startswith("{"):
+            d = json.loads(ln)
+            cb = d["cpu_baseline"]
+            cb["ms_per_step"] = d["ms_per_step"]
+            return cb
+    raise RuntimeError("reference arm printed no JSON line: " + r.stderr[-500:])
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (its oracle port: the reference is pure
-    Python and /root/reference does not exist on the GPU box), all host threads, on the SAME config / steps /
-    warm-up as our arm.  Under torchrun rank 0 alone runs; the other ranks exit 0 without work."""
+    """--impl reference: the reference's own CPU implementation of the path (the unmodified files under oracle/_ref --
+    /root/reference does not exist on the GPU box; without them, the oracle port), all host threads, on the SAME
+    config / steps / warm-up as our arm.  Under torchrun rank 0 alone runs; the other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = workload_cfg(args.workload)
     gbatch = args.batch * args.gpus
-    val, ms, cores, build_s = oracle_arm(cfg, gbatch, args.steps, args.warmup)
-    sample = (f"{args.steps} full train steps after {args.warmup} warm-up, global batch {gbatch}, oracle port of the "
-              f"reference CPU path, single process, {cores} threads; tables built in {build_s:.1f}s")
+    val, ms, cores, build_s, kind, what = cpu_arm(cfg, gbatch, args.steps, args.warmup)
+    sample = (f"{args.steps} full train steps after {args.warmup} warm-up, global batch {gbatch}, {what}, "
+              f"{cores} threads; model built in {build_s:.1f}s")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_block(args.workload, cfg, args.batch, args.gpus),
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -531,11 +630,13 @@ def run_ours(args):
         line["nvlink_exchange"] = nvlink
     if world == 1 and not args.no_cpu_baseline:
         torch.cuda.empty_cache()
-        val, ms, cores, build_s = oracle_arm(cfg, args.batch, args.cpu_steps, 1)
-        line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                                "ms_per_step": ms,
-                                "sample": f"{args.cpu_steps} full train steps after 1 warm-up, batch {args.batch}, same "
-                                          f"{args.workload}-shape model on the host ({build_s:.0f}s to build tables)"}
+        try:
+            line["cpu_baseline"] = cpu_baseline_subprocess(args, cfg)
+        except Exception as e:                                 # noqa: BLE001  (never lose the GPU line to the CPU leg)
+            val, ms, cores, build_s = oracle_arm(cfg, args.batch, args.cpu_steps, 1)
+            line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+                                    "sample": f"{args.cpu_steps} full train steps after 1 warm-up, batch {args.batch}, oracle "
+                                              f"port in-process (reference subprocess failed: {type(e).__name__})"}
     print(json.dumps(line), flush=True)
     finish(world)
 

@@ -259,3 +259,24 @@ def test_reference_api_leftovers(capsys):
     e.iteration_nt += 1
     e.set_iteration_bound()
     assert e.iteration_bound.item() == 1000 and "bound increasing to 1000" in capsys.readouterr().out
+
+
+def test_oracle_ref_manifest_matches_files():
+    """oracle/_ref (the unmodified reference files for bench.py's reference arm, oracle/make_ref.py): when present,
+    every file has the size and sha256 its MANIFEST recorded at copy time, and the product package imports none of it."""
+    import hashlib, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "MANIFEST.json")):
+        pytest.skip("oracle/_ref not built (no /root/reference at build time)")
+    man = json.load(open(os.path.join(ref, "MANIFEST.json")))
+    assert "dlrm_s_pytorch_comm_grad.py" in man and "sgd_quantized_gradients_parallel_comm.py" in man
+    for rel, rec in man.items():
+        b = open(os.path.join(ref, rel), "rb").read()
+        assert len(b) == rec["bytes"] and hashlib.sha256(b).hexdigest() == rec["sha256"], rel
+    pkg = os.path.join(root, "deep_quantized_recommendation_model_dqrm_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle._ref" not in src and "oracle/_ref" not in src and "from oracle" not in src, f
