@@ -357,7 +357,8 @@ def test_sgd_rows_and_rwsadagrad():
         np.testing.assert_allclose(cpu(g.weights[t]), Wn, rtol=1e-5, atol=1e-7)
 
 
-@pytest.mark.parametrize("case", ["zipf_onehot", "three_rows", "ragged_multihot", "dim64", "dim128", "small_cta"])
+@pytest.mark.parametrize("case", ["zipf_onehot", "three_rows", "ragged_multihot", "dim64", "dim128", "small_cta", "dim8",
+                                  "dim4_multihot", "dim256", "dim512"])
 @pytest.mark.parametrize("adagrad", [False, True])
 def test_bwd_sgd_fused(case, adagrad):
     """dqrm_embbag_bwd_sgd (north-star kernel 3: sort + de-duplicate + row update in ONE kernel on the radix-sort
@@ -366,7 +367,7 @@ def test_bwd_sgd_fused(case, adagrad):
     tables against optim/rwsadagrad.py:97-113 as restated by the oracle (fp32 rounding of the row mean allowed)."""
     _lib, synthetic, tables, qm, qu = _mods()
     rng = np.random.RandomState(17)
-    dim = {"dim64": 64, "dim128": 128}.get(case, 16)
+    dim = {"dim64": 64, "dim128": 128, "dim8": 8, "dim4_multihot": 4, "dim256": 256, "dim512": 512}.get(case, 16)
     if case == "zipf_onehot":
         rows, B = 300, 40000
         idx = torch.from_numpy(np.minimum(rng.zipf(1.1, size=B) - 1, rows - 1).astype(np.int64))
@@ -375,10 +376,14 @@ def test_bwd_sgd_fused(case, adagrad):
         rows, B = 3, 50000
         idx = torch.from_numpy(rng.randint(0, 3, size=B).astype(np.int64))
         off = torch.arange(B, dtype=torch.int64)
-    elif case == "ragged_multihot":
+    elif case in ("ragged_multihot", "dim4_multihot"):
         rows, B = 100000, 9000
         idx, off = synthetic.random_bags(rows, B, 7, rng)
         off[1000:1100] = off[1000]
+    elif case in ("dim256", "dim512"):                   # wide rows: 2 / 4 float4 columns per lane, fewer rows in flight
+        rows, B = 50000, 20000
+        idx = torch.from_numpy(np.minimum(rng.zipf(1.05, size=B) - 1, rows - 1).astype(np.int64))
+        off = torch.arange(B, dtype=torch.int64)
     elif case == "small_cta":
         rows, B = 5000, 300                              # few lookups: single-CTA de-duplication + row-update kernel
         idx, off = synthetic.random_bags(rows, B, 3, rng)
