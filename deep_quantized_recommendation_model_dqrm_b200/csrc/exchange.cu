@@ -92,8 +92,12 @@ __device__ __forceinline__ int find_row(const int* __restrict__ a, int n, int x)
 
 constexpr int kMergeRanks = 8;          // row lists searched in lock-step (world > 8: in chunks of 8)
 
-template <int COLS, typename CodeT>
-__global__ void __launch_bounds__(256)
+// MULTI = false is the one-rank instantiation (world == 1: nothing to merge): without the lock-step searches it needs
+// half the registers (64 -> full occupancy), which is what a latency-bound random-row read-modify-write lives on
+// (1 M rows x 64 floats: 192 -> 103 us = 5.1 TB/s of row traffic; the lock-step multi-rank searches had doubled the
+// registers of the one-rank case too).
+template <int COLS, typename CodeT, bool MULTI>
+__global__ void __launch_bounds__(256, MULTI ? 4 : 8)
 grad_merge_apply_kernel(const __grid_constant__ TableSet ts, int dim4, int group,
                         const unsigned char* __restrict__ gathered, SlotLayout lay, int world, long long capacity,
                         const float* __restrict__ scale_mean, float neg_lr_arg, const float* __restrict__ lr_dev,
@@ -129,6 +133,7 @@ grad_merge_apply_kernel(const __grid_constant__ TableSet ts, int dim4, int group
         q[c][0] = v.x; q[c][1] = v.y; q[c][2] = v.z; q[c][3] = v.w;
       }
     }
+    if constexpr (MULTI)
     for (int base = 0; world > 1 && base < world; base += kMergeRanks) {  // (block-uniform trip counts throughout)
       const int* lst[kMergeRanks];
       int n2[kMergeRanks], lo[kMergeRanks], hi[kMergeRanks];
@@ -295,9 +300,16 @@ extern "C" int dqrm_grad_merge_apply(int num_tables, float* const* weight, const
   int search_iters = 0;                                       // a binary search over <= capacity entries ends in this many halvings
   while ((1ll << search_iters) <= capacity) ++search_iters;
 #define DQRM_MERGE(COLS, CT)                                                                                         \
-  grad_merge_apply_kernel<COLS, CT><<<grid, 256, 0, st>>>(ts, dim / 4, rl.group, static_cast<const unsigned char*>(gathered), \
-                                                          lay, world, capacity, scale_mean, neg_lr, lr_dev, inv_world, \
-                                                          updated_rows, updated_count, qbar, status, search_iters)
+  do {                                                                                                               \
+    if (world > 1)                                                                                                   \
+      grad_merge_apply_kernel<COLS, CT, true><<<grid, 256, 0, st>>>(ts, dim / 4, rl.group, static_cast<const unsigned char*>(gathered), \
+                                                                    lay, world, capacity, scale_mean, neg_lr, lr_dev, inv_world, \
+                                                                    updated_rows, updated_count, qbar, status, search_iters); \
+    else                                                                                                             \
+      grad_merge_apply_kernel<COLS, CT, false><<<grid, 256, 0, st>>>(ts, dim / 4, rl.group, static_cast<const unsigned char*>(gathered), \
+                                                                     lay, world, capacity, scale_mean, neg_lr, lr_dev, inv_world, \
+                                                                     updated_rows, updated_count, qbar, status, search_iters); \
+  } while (0)
   if (bits == 32) { if (rl.cols == 1) DQRM_MERGE(1, float); else if (rl.cols == 2) DQRM_MERGE(2, float); else DQRM_MERGE(4, float); }
   else if (bits <= 8) { if (rl.cols == 1) DQRM_MERGE(1, int8_t); else if (rl.cols == 2) DQRM_MERGE(2, int8_t); else DQRM_MERGE(4, int8_t); }
   else           { if (rl.cols == 1) DQRM_MERGE(1, int16_t); else if (rl.cols == 2) DQRM_MERGE(2, int16_t); else DQRM_MERGE(4, int16_t); }
