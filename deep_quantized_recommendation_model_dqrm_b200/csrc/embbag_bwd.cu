@@ -17,6 +17,10 @@
 // oracle's coalesce_spec defines exactly this shape), but a row's latency is one block, not the whole chain.  Sort, unique, segmented sum and scale are
 // ONE launch for all tables (the reference: index_select, thrust sort,
 // coalesceValuesKernel, 4 reductions and a host sync per table).
+// Optionally (DQRM_BWD_CLUSTER=2|4|8, off by default -- see the launch code) a thread-block CLUSTER per table: the
+// sort stays in CTA 0, whose keys and segment starts the other CTAs of the cluster read through distributed shared
+// memory while they fold their share of the unique rows.  Same fold order per row, so the same bits.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -45,27 +49,33 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
                       const float* __restrict__ fwd_scale, long long capacity,
                       int* __restrict__ uniq_rows, int* __restrict__ uniq_count, float* __restrict__ grad_sums,
                       int grad_bits, float* __restrict__ grad_scale_local, int* __restrict__ status,
-                      float* __restrict__ partials, long long partial_items) {
+                      float* __restrict__ partials, long long partial_items, int csize, int radix) {
+  namespace cg = cooperative_groups;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp_tot[32];
   __shared__ int s_nvalid, s_unique, s_nlong;
   __shared__ unsigned s_max;
   __shared__ int s_long_j[kMaxLongRows], s_long_start[kMaxLongRows + 1];
 
-  const int t = blockIdx.x;
+  const int t = blockIdx.x / csize, cr = blockIdx.x % csize;              // table, rank of this CTA in the table's cluster
   const int tid = threadIdx.x, nthr = blockDim.x;
   const long long L = a.idx_begin[t + 1] - a.idx_begin[t];
   int n = 2;
   while (n < L) n <<= 1;
+  // shared memory: keys [n] | (radix: second key buffer [n]) | seg_start [n + 4] | (radix: per-warp digit counters, digit totals, digit bases)
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-  int* seg_start = reinterpret_cast<int*>(keys + n);
+  int* seg_start = reinterpret_cast<int*>(keys + (radix ? 2 * n : n));
   const long long* idx = indices + a.idx_begin[t];
   const long long* off = offsets + (long long)t * bags;
   const long long nrows = a.rows[t];
   int bad = 0;
+  if (tid == 0) { s_max = 0u; s_nlong = 0; }
+  int U = 0;
+  if (cr == 0) {                                                         // sort + segments: the cluster's first CTA only
 
-  // 1. keys
-  for (int i = tid; i < n; i += nthr) keys[i] = kPadKey;
+  // 1. keys (lookups no bag covers keep the pad: it sorts last -- the radix form gives it row id `nrows`)
+  const unsigned long long pad = radix ? (((unsigned long long)nrows << 32) | 0xffffffffull) : kPadKey;
+  for (int i = tid; i < n; i += nthr) keys[i] = pad;
   __syncthreads();
   for (long long b = tid; b < bags; b += nthr) {
     long long start = off[b];
@@ -83,7 +93,73 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
   }
   __syncthreads();
 
-  // 2. bitonic sort, ascending
+  // 2. sort ascending by (row, lookup order).  From 1024 keys: stable LSD radix sort by row in shared memory, 8 bits per
+  // pass over the bits of `nrows` (3-4 passes of five block barriers each; the bitonic network needs 55-105 stages) --
+  // the scheme of embbag_bwd_large.cu inside one CTA: a warp walks its contiguous keys 32 at a time, rank = running
+  // per-warp digit counter + match_any rank.  Below that, and from 8192 keys (no room for a second buffer): bitonic.
+  if (radix) {
+    unsigned long long* kin = keys;
+    unsigned long long* kout = keys + n;
+    unsigned* wcnt = reinterpret_cast<unsigned*>(seg_start + n + 4);       // [nwarps][256]
+    const int nwarps = nthr >> 5, warp = tid >> 5, ln = tid & 31;
+    unsigned* hist = wcnt + nwarps * 256;                                  // [256] digit totals
+    unsigned* base = hist + 256;                                           // [256] exclusive digit bases
+    const int Li = (int)L, ipt = (Li + nthr - 1) / nthr, wbeg = warp * 32 * ipt;   // ipt <= 8
+    const unsigned ltm = (1u << ln) - 1u;
+    int key_bits = 1;
+    while ((1ll << key_bits) <= nrows) ++key_bits;                         // covers the pad's row id
+    for (int shift = 0; shift < key_bits; shift += 8) {
+      for (int j = tid; j < nwarps * 256; j += nthr) wcnt[j] = 0u;
+      __syncthreads();
+      unsigned loc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k >= ipt) break;                                               // (block-uniform)
+        const int i = wbeg + k * 32 + ln;
+        const bool live = i < Li;
+        const unsigned d = live ? (((unsigned)(kin[i] >> 32) >> shift) & 255u) : 256u;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned rank = __popc(peers & ltm);
+        const unsigned prev = live ? wcnt[warp * 256 + d] : 0u;
+        loc[k] = prev + rank;
+        __syncwarp();
+        if (live && rank == 0) wcnt[warp * 256 + d] = prev + __popc(peers);
+        __syncwarp();
+      }
+      __syncthreads();
+      for (int d = tid; d < 256; d += nthr) {                              // exclusive prefix over the warps, per digit
+        unsigned run = 0;
+        for (int w = 0; w < nwarps; ++w) { const unsigned c = wcnt[w * 256 + d]; wcnt[w * 256 + d] = run; run += c; }
+        hist[d] = run;
+      }
+      __syncthreads();
+      if (tid < 32) {                                                      // exclusive scan of the 256 digit totals: 8 per lane
+        unsigned v[8], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] = hist[tid * 8 + i]; sum += v[i]; }
+        unsigned incl = sum;
+#pragma unroll
+        for (int sh = 1; sh < 32; sh <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, sh); if (tid >= sh) incl += u; }
+        unsigned ex = incl - sum;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { base[tid * 8 + i] = ex; ex += v[i]; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k >= ipt) break;
+        const int i = wbeg + k * 32 + ln;
+        if (i < Li) {
+          const unsigned long long x = kin[i];
+          const unsigned d = ((unsigned)(x >> 32) >> shift) & 255u;
+          kout[base[d] + wcnt[warp * 256 + d] + loc[k]] = x;
+        }
+      }
+      __syncthreads();
+      unsigned long long* sw = kin; kin = kout; kout = sw;
+    }
+    keys = kin;
+  } else
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = tid; i < (n >> 1); i += nthr) {
@@ -97,10 +173,10 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
     }
   }
 
-  // 3. number of real keys (pads sort last)
+  // 3. number of real keys (pads sort last; the radix form sorted the first L entries only)
   if (tid == 0) {
-    int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] == kPadKey) hi = mid; else lo = mid + 1; }
+    int lo = 0, hi = radix ? (int)L : n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] == pad) hi = mid; else lo = mid + 1; }
     s_nvalid = lo;
   }
   __syncthreads();
@@ -136,13 +212,34 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
   int pos = s_warp_tot[tid >> 5] + incl - heads;
   for (int i = c0; i < c1; ++i)
     if ((i == 0) || ((unsigned)(keys[i] >> 32) != (unsigned)(keys[i - 1] >> 32))) seg_start[pos++] = i;
-  int U = s_unique;
+  U = s_unique;
   if (tid == 0) {
     seg_start[U] = nvalid;
     if (U > capacity) bad |= DQRM_STATUS_CAPACITY;
     uniq_count[t] = (int)(U > capacity ? capacity : U);
   }
-  __syncthreads();
+  }                                                                      // (cr == 0)
+  // the other CTAs of the cluster read CTA 0's sorted keys / segment starts / counters through distributed shared memory
+  int* q_nlong = &s_nlong;
+  int* q_long_j = s_long_j;
+  unsigned* q_max = &s_max;
+  if (csize > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (cr != 0 && radix) {                                                // which buffer CTA 0's sort ended in
+      int key_bits = 1;
+      while ((1ll << key_bits) <= nrows) ++key_bits;
+      if (((key_bits + 7) / 8) & 1) keys += n;
+    }
+    keys = cluster.map_shared_rank(keys, 0);
+    seg_start = cluster.map_shared_rank(seg_start, 0);
+    q_nlong = cluster.map_shared_rank(&s_nlong, 0);
+    q_long_j = cluster.map_shared_rank(s_long_j, 0);
+    q_max = cluster.map_shared_rank(&s_max, 0);
+    U = *cluster.map_shared_rank(&s_unique, 0);
+  } else {
+    __syncthreads();
+  }
   if (U > capacity) U = (int)capacity;
 
   // 5. segmented fold of dy over each unique row
@@ -195,14 +292,13 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
       m = max(m, abs_bits4(acc[c]));
     }
   };
-  if (tid == 0) s_nlong = 0;
-  __syncthreads();
   // 5a. rows with <= kFoldBlock duplicates: left fold each; longer rows are queued.  A lane group folds
   // kRowsInFlight rows at once (step s of all of them together): several independent gathers in flight per group
   // instead of one dependent load per unique row.
   constexpr int kRowsInFlight = 4, kShortRow = 4;
-  const int gstride = nthr / group;
-  for (int jb = tid / group; jb < U; jb += gstride * kRowsInFlight) {
+  const int gstride = (nthr / group) * csize;                           // lane groups of the whole cluster
+  const int gfirst = cr * (nthr / group) + tid / group;
+  for (int jb = gfirst; jb < U; jb += gstride * kRowsInFlight) {
     int p0[kRowsInFlight], len[kRowsInFlight], maxlen = 0;
 #pragma unroll
     for (int r = 0; r < kRowsInFlight; ++r) {
@@ -212,7 +308,7 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
         p0[r] = seg_start[j];
         len[r] = seg_start[j + 1] - p0[r];
         if (len[r] > kFoldBlock && partials != nullptr) {
-          if (lane == 0) s_long_j[atomicAdd(&s_nlong, 1)] = j;             // queue order is irrelevant to the results
+          if (lane == 0) q_long_j[atomicAdd(q_nlong, 1)] = j;              // queue order is irrelevant to the results
           len[r] = 0;
         }
       }
@@ -257,15 +353,15 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
   }
   // rows with 5..kFoldBlock duplicates: one row at a time, 8 gathers in flight (a separate loop keeps the two
   // register working sets apart: 64 registers per thread at 1024 threads)
-  for (int j = tid / group; j < U; j += gstride) {
+  for (int j = gfirst; j < U; j += gstride) {
     const int p0 = seg_start[j], p1 = seg_start[j + 1];
     if (p1 - p0 <= kShortRow || (p1 - p0 > kFoldBlock && partials != nullptr)) continue;
     float4 acc[COLS];
     fold(p0, p1, acc);
     emit(j, p0, acc);
   }
-  __syncthreads();
-  const int nlong = s_nlong;
+  if (csize > 1) cg::this_cluster().sync(); else __syncthreads();       // the queue of long rows is complete
+  const int nlong = cr == 0 ? s_nlong : 0;                               // (long rows: CTA 0, from its own shared memory)
   if (nlong > 0) {                                                       // CTA-uniform
     // 5b. work items = blocks of kFoldBlock consecutive lookups of the queued rows
     if (tid == 0) {
@@ -317,9 +413,11 @@ embbag_bwd_cta_kernel(const __grid_constant__ BwdArgs a, int dim4, int group,
     }
   }
 
-  // 6. per-table gradient scale
-  const unsigned bm = block_max_u32(m, &s_max);
-  if (tid == 0 && grad_scale_local) grad_scale_local[t] = scale_of(__uint_as_float(bm), grad_bits);
+  // 6. per-table gradient scale: warp maxima into CTA 0's slot (CTA 0 stays resident until every reader is done)
+  m = warp_max_u32(m);
+  if ((tid & 31) == 0 && m) atomicMax(q_max, m);
+  if (csize > 1) cg::this_cluster().sync(); else __syncthreads();
+  if (cr == 0 && tid == 0 && grad_scale_local) grad_scale_local[t] = scale_of(__uint_as_float(s_max), grad_bits);
   if (bad) atomicOr(status, bad);
 }
 
@@ -502,7 +600,18 @@ static int bwd_impl(int num_tables, const int64_t* rows, int dim,
   int threads = n / 2;
   if (threads < 128) threads = 128;
   if (threads > 1024) threads = 1024;
-  const size_t smem = (size_t)n * sizeof(unsigned long long) + ((size_t)n + 4) * sizeof(int);
+  // stable radix sort in shared memory from 1024 keys while a second key buffer fits (<= 8192 keys); DQRM_BWD_CTA_SORT=bitonic pins the network
+  int radix = (n >= 1024 && n <= 8192) ? 1 : 0;
+  if (const char* e = getenv("DQRM_BWD_CTA_SORT")) { if (!strcmp(e, "bitonic")) radix = 0; }
+  const size_t smem = radix ? (size_t)n * 2 * sizeof(unsigned long long) + ((size_t)n + 4) * sizeof(int) +
+                                  ((size_t)(threads / 32) * 256 + 512) * sizeof(unsigned)
+                            : (size_t)n * sizeof(unsigned long long) + ((size_t)n + 4) * sizeof(int);
+  // CTAs per table.  A thread-block cluster per table (DQRM_BWD_CLUSTER=2|4|8) folds 3x faster in isolation, but inside
+  // a training step this kernel runs on a side stream BESIDE the bottom-MLP backward: measured at Terabyte shape, batch
+  // 8192, 26 clusters of 4 x 1024 threads slow that critical chain more than they save (step 8.12 -> 8.24 ms), so the
+  // default stays one CTA per table.
+  int csize = 1;
+  if (const char* e = getenv("DQRM_BWD_CLUSTER")) { const int v = atoi(e); if (v >= 1 && v <= 8) csize = v; }
 #define DQRM_BWD(COLS)                                                                                         \
   do {                                                                                                         \
     auto kern = embbag_bwd_cta_kernel<COLS>;                                                                   \
@@ -511,11 +620,22 @@ static int bwd_impl(int num_tables, const int64_t* rows, int dim,
       DQRM_REQUIRE(e == cudaSuccess, -EIO, "embbag_bwd: cannot opt in to %zu B shared memory: %s", smem,       \
                    cudaGetErrorString(e));                                                                     \
     }                                                                                                          \
-    kern<<<num_tables, threads, smem, st>>>(a, dim / 4, rl.group, reinterpret_cast<const long long*>(indices), \
-                                            reinterpret_cast<const long long*>(offsets), bags, dout,           \
-                                            dout_table_stride, dout_bag_stride, fwd_scale, capacity, uniq_rows, \
-                                            uniq_count, grad_sums, grad_bits, grad_scale_local, status,        \
-                                            partials, items);                                                 \
+    cudaLaunchConfig_t cfg = {};                                                                               \
+    cfg.gridDim = dim3((unsigned)(num_tables * csize));                                                        \
+    cfg.blockDim = dim3((unsigned)threads);                                                                    \
+    cfg.dynamicSmemBytes = smem;                                                                               \
+    cfg.stream = st;                                                                                           \
+    cudaLaunchAttribute attr[1];                                                                               \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                          \
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;    \
+    cfg.attrs = attr;                                                                                          \
+    cfg.numAttrs = csize > 1 ? 1 : 0;                                                                          \
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a, dim / 4, rl.group, reinterpret_cast<const long long*>(indices), \
+                                        reinterpret_cast<const long long*>(offsets), (long long)bags, dout,    \
+                                        (long long)dout_table_stride, (long long)dout_bag_stride, fwd_scale,   \
+                                        (long long)capacity, uniq_rows, uniq_count, grad_sums, grad_bits,      \
+                                        grad_scale_local, status, partials, (long long)items, csize, radix);   \
+    DQRM_REQUIRE(le == cudaSuccess, -EIO, "embbag_bwd_cta_kernel: %s", cudaGetErrorString(le));                \
   } while (0)
   if (rl.cols == 1) DQRM_BWD(1);
   else if (rl.cols == 2) DQRM_BWD(2);

@@ -272,12 +272,19 @@ def test_large_path_one_kernel_sort(case):
         assert bits_equal(cpu(g.grad_scale_local[0]), O.grad_scale_spec(sums, 8))
 
 
-@pytest.mark.parametrize("path,lookups", [("cta", None), ("sort", None), ("auto", None), ("cta", 6000), ("auto", 6000)])
+@pytest.mark.parametrize("path,lookups", [("cta", None), ("sort", None), ("auto", None), ("cta", 6000), ("auto", 6000),
+                                          ("cta_cluster4", 6000), ("cta_cluster8", None), ("cta_bitonic", 6000)])
 def test_max_cta_lookups_boundary(path, lookups, monkeypatch):
     """Exactly DQRM_BWD_CTA_MAX_LOOKUPS lookups (largest single-CTA sort) with heavy duplication, on the single-CTA
     path, on the whole-chip sort kernel, and on whichever the cost model picks (one table of >= 4k lookups: the sort
     kernel): the same bits either way."""
     _lib, synthetic, tables, qm, qu = _mods()
+    if path.startswith("cta_cluster"):         # the single-CTA sort with a thread-block cluster folding (DSMEM reads)
+        monkeypatch.setenv("DQRM_BWD_CLUSTER", path[-1])
+        path = "cta"
+    if path == "cta_bitonic":                  # 6000 lookups sort by shared-memory radix passes by default
+        monkeypatch.setenv("DQRM_BWD_CTA_SORT", "bitonic")
+        path = "cta"
     if path != "auto":
         monkeypatch.setenv("DQRM_BWD_PATH", path)
     rows, dim, B = 300, 16, lookups or _lib.BWD_CTA_MAX_LOOKUPS
