@@ -209,11 +209,11 @@ def reference_arm(cfg, batch, steps, warmup):
     import sgd_quantized_gradients_parallel_comm as sgd        # oracle/_ref
     assert os.path.dirname(os.path.abspath(drv.__file__)) == REF_DIR
     if not dist.is_initialized():
-        import socket
-        with socket.socket() as sk:
-            sk.bind(("127.0.0.1", 0))
-            port = sk.getsockname()[1]
-        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+        # a private one-rank Gloo group over a FileStore: under torchrun a tcp:// rendezvous would be taken for the
+        # agent's store (TORCHELASTIC_USE_AGENT_STORE) and wait for a server that nobody starts
+        import tempfile
+        store = os.path.join(tempfile.mkdtemp(prefix="dqrm_ref_"), "store")
+        dist.init_process_group("gloo", init_method=f"file://{store}", rank=0, world_size=1)
     t0 = time.perf_counter()
     drv.full_precision_flag = False                            # train(): = args.pretrain_and_quantize (drv:1425-1426)
     rows, dim = cfg["rows"], cfg["dim"]
