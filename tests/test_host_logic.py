@@ -280,3 +280,25 @@ def test_oracle_ref_manifest_matches_files():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle._ref" not in src and "oracle/_ref" not in src and "from oracle" not in src, f
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (small workload, CPU only): one JSON line with the contract's keys; kind
+    "reference" when oracle/_ref travelled (the unmodified reference, one Gloo rank), "port" otherwise.  Launched under
+    torchrun with two ranks as the driver does for N > 1: rank 0 alone prints, the other exits 0."""
+    import json, os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "small",
+           "--steps", "2", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 2 and d["warmup"] == 1
+    assert d["higher_is_better"] is True and d["unit"] == "samples/s" and d["value"] > 0
+    assert d["config"]["global_batch"] == 256 and "small-shape" in d["config"]["workload"]
+    have_ref = os.path.exists(os.path.join(root, "oracle", "_ref", "dlrm_s_pytorch_comm_grad.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
