@@ -565,6 +565,9 @@ class EmbeddingTableGroup:
         in place -- SGD, or RW-Adagrad with `momentum` -- without the sums travelling through memory on the
         radix-sort path.  Same table bits as backward() followed by sgd_apply()."""
         lib, st = self.lib, _lib.stream_ptr()
+        if getattr(self, "dp_world", 1) > 1:
+            raise _lib.DqrmLibraryError("backward_sgd is the single-process path (the data-parallel step exchanges the "
+                                        "de-duplicated gradients first: backward + exchange + merge_apply)")
         indices, offsets, idx_begin, ib, bags, full_precision = last if last is not None else self.last
         cap = max(max(idx_begin[k + 1] - idx_begin[k] for k in range(self.T)), 1)
         if self.fixed_capacity is not None:
