@@ -440,6 +440,39 @@ def test_bwd_sgd_fused(case, adagrad):
 
 
 
+@pytest.mark.parametrize("case", ["cta", "sort"])
+def test_bwd_sgd_vs_uncoalesced_reference_update(case):
+    """(a10) the reference's single-process update is torch.optim.SGD on the UNCOALESCED sparse gradient
+    (dlrm_s_pytorch_single_gpu.py:1944-1946): duplicates are applied one at a time, W += -lr*g1; W += -lr*g2 (oracle
+    sgd_sparse_spec), in an order that is undefined on CUDA.  dqrm_embbag_bwd_sgd sums a row's duplicates first (fixed
+    order) and applies once: equal to the reference's result within fp32 rounding of the row -- 1e-5 relative, the
+    north-star tolerance for updated weights -- and the set of changed rows is exactly unique(indices)."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    rng = np.random.RandomState(23)
+    if case == "cta":
+        rows, B, P = 5000, 300, 3
+    else:
+        rows, B, P = 100000, 9000, 7
+    idx, off = synthetic.random_bags(rows, B, P, rng)
+    W = synthetic.table_weights_numpy(rows, 16, rng)
+    g = tables.EmbeddingTableGroup([torch.tensor(W, device="cuda")], embedding_bit=4)
+    i2, o2, ib, bags = tables.EmbeddingTableGroup.pack_inputs([idx], [off], "cuda")
+    g.scan_scales()
+    g.forward(i2, o2, ib, bags)
+    dout = rng.randn(1, bags, 16).astype(np.float32)
+    g.backward_sgd(torch.tensor(dout, device="cuda"), 0.1)
+    g.check_status()
+    r0, v0 = O.embbag_backward_spec(dout[0], idx.numpy(), off.numpy(), O.table_scale_spec(W, 4))
+    Wref = W.copy()
+    O.sgd_sparse_spec(Wref, r0, v0, 0.1)
+    got = cpu(g.weights[0])
+    np.testing.assert_allclose(got, Wref, rtol=1e-5, atol=1e-7)
+    changed = np.nonzero((got != W).any(axis=1))[0]
+    assert set(changed.tolist()) <= set(np.unique(idx.numpy()).tolist())
+    U = int(g.uniq_count[0])
+    assert np.array_equal(cpu(g.uniq_rows[0, :U]), np.unique(idx.numpy()))
+
+
 def test_rwsadagrad_rows_vs_reference_golden():
     """dqrm_sgd_rows with momentum against 4 steps of the REFERENCE's optim/rwsadagrad.py:97-113
     (tests/golden/rwsadagrad_rows.npz: sparse gradients with duplicate rows, state and weights after every step)."""
