@@ -97,6 +97,32 @@ def gen_embeddings(qm):
     emb_case(qm, "emb_ragged_d16", 9, 16, 4, idx, off, seed=105)
 
 
+# ---------------------------------------------------------------- single-process SGD on the sparse gradient (a10)
+def gen_sgd_single(qm):
+    """The reference's single-process update (dlrm_s_pytorch_single_gpu.py:1944-1946): the reference's own
+    QuantEmbeddingBagTwo (forward, STE backward, UNCOALESCED sparse gradient) stepped by torch.optim.SGD for three
+    iterations on multi-hot bags with duplicate rows; tables after every step -> tests/golden/sgd_single.npz."""
+    rng = np.random.RandomState(31)
+    rows, dim, bits, B, lr = 400, 16, 4, 96, 0.1
+    W = synthetic.table_weights_numpy(rows, dim, rng)
+    E = qm.QuantEmbeddingBagTwo(rows, dim, bits, embedding_id=0)
+    E.embedding_bag.weight.data = torch.tensor(W)
+    opt = torch.optim.SGD(E.parameters(), lr=lr)
+    rec = dict(rows=rows, dim=dim, bits=bits, lr=lr, steps=3, W_init=W)
+    for step in range(3):
+        idx, off = synthetic.random_bags(rows, B, 6, rng)
+        dout = rng.randn(B, dim).astype(np.float32)
+        opt.zero_grad()
+        out = E(idx, off)
+        out.backward(torch.from_numpy(dout))
+        assert E.embedding_bag.weight.grad.is_sparse and not E.embedding_bag.weight.grad.is_coalesced()
+        opt.step()
+        rec[f"idx{step}"], rec[f"off{step}"], rec[f"dout{step}"] = _np(idx), _np(off), dout
+        rec[f"scale{step}"] = _np(E.eb_scaling_factor).copy()
+        rec[f"W{step}"] = _np(E.embedding_bag.weight.data).copy()
+    np.savez_compressed(os.path.join(GOLD, "sgd_single.npz"), **rec)
+
+
 # ---------------------------------------------------------------- QuantLinear
 def gen_linear(qm):
     rng = np.random.RandomState(21)
@@ -391,6 +417,10 @@ def main():
         gen_xchg(4, "xchg4", 29619)
         gen_xchg(2, "xchg2_ec", 29621, ec=True, steps=3)
         return
+    if "--only-sgd-single" in sys.argv:
+        qm, qu, sgd = import_reference()
+        gen_sgd_single(qm)
+        return
     if "--only-unquantized" in sys.argv:
         import_reference()
         gen_dp(2, False, "dp2_unquantized", 29615, emb_q=False)
@@ -404,6 +434,7 @@ def main():
     gen_dp(2, True, "dp2_multihot", 29613)
     gen_dp(4, False, "dp4_onehot", 29614)
     gen_rwsadagrad()
+    gen_sgd_single(qm)
     gen_dp(2, False, "dp2_unquantized", 29615, emb_q=False)     # emb_grad_quantized=False (sgd:319-329, 626)
     gen_dp(2, "nodup", "dp2_nodup", 29616)
     gen_xchg(1, "xchg1", 29620)

@@ -473,6 +473,25 @@ def test_bwd_sgd_vs_uncoalesced_reference_update(case):
     assert np.array_equal(cpu(g.uniq_rows[0, :U]), np.unique(idx.numpy()))
 
 
+def test_bwd_sgd_vs_reference_optimizer_golden():
+    """dqrm_embbag_bwd_sgd against the REFERENCE's single-process path (tests/golden/sgd_single.npz: its
+    QuantEmbeddingBagTwo + torch.optim.SGD on the uncoalesced sparse gradient, three steps, duplicate rows): forward
+    scales bit-exact at every step, tables within 1e-5."""
+    _lib, synthetic, tables, qm, qu = _mods()
+    gd = load_golden("sgd_single")
+    rows, dim, lr = int(gd["rows"]), int(gd["dim"]), float(gd["lr"])
+    g = tables.EmbeddingTableGroup([torch.tensor(gd["W_init"], device="cuda")], embedding_bit=int(gd["bits"]))
+    for s in range(int(gd["steps"])):
+        idx, off = torch.tensor(gd[f"idx{s}"]), torch.tensor(gd[f"off{s}"])
+        i2, o2, ib, bags = tables.EmbeddingTableGroup.pack_inputs([idx], [off], "cuda")
+        g.scan_scales()
+        assert cpu(g.scale[0]).tobytes() == gd[f"scale{s}"].astype(np.float32).tobytes()
+        g.forward(i2, o2, ib, bags)
+        g.backward_sgd(torch.tensor(gd[f"dout{s}"], device="cuda").view(1, bags, dim), lr)
+        g.check_status()
+        np.testing.assert_allclose(cpu(g.weights[0]), gd[f"W{s}"], rtol=1e-5, atol=1e-7)
+
+
 def test_rwsadagrad_rows_vs_reference_golden():
     """dqrm_sgd_rows with momentum against 4 steps of the REFERENCE's optim/rwsadagrad.py:97-113
     (tests/golden/rwsadagrad_rows.npz: sparse gradients with duplicate rows, state and weights after every step)."""

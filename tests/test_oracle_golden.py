@@ -332,3 +332,25 @@ def test_exchange_on_injected_gradients_bit_exact(name):
     for i in range(len(cfg["layers"])):
         assert mlp_w[i][0].tobytes() == g[f"final_lin{i}_W"].tobytes()
         assert mlp_w[i][1].tobytes() == g[f"final_lin{i}_b"].tobytes()
+
+
+def test_single_process_sgd_vs_reference_optimizer():
+    """(a10) tests/golden/sgd_single.npz: the reference's QuantEmbeddingBagTwo stepped by torch.optim.SGD on its
+    UNCOALESCED sparse gradient (dlrm_s_pytorch_single_gpu.py:1944-1946), three iterations with duplicate rows.  The
+    oracle's per-duplicate update (sgd_sparse_spec, storage order) and the coalesced form the CUDA path uses (sum the
+    duplicates in the fixed fold order, apply once) both reproduce the reference's tables within 1e-5 (+ 1e-7 absolute:
+    elements that cancel to ~0);
+    forward scales bit-exact at every step."""
+    g = load_golden("sgd_single")
+    lr = float(g["lr"])
+    W_dup, W_co = g["W_init"].copy(), g["W_init"].copy()
+    for s in range(int(g["steps"])):
+        sc = O.table_scale_spec(W_co, 4)
+        assert np.asarray(sc, dtype=np.float32).tobytes() == g[f"scale{s}"].astype(np.float32).tobytes()
+        r0, v0 = O.embbag_backward_spec(g[f"dout{s}"], g[f"idx{s}"], g[f"off{s}"], O.table_scale_spec(W_dup, 4))
+        O.sgd_sparse_spec(W_dup, r0, v0, lr)
+        np.testing.assert_allclose(W_dup, g[f"W{s}"], rtol=1e-5, atol=1e-7)     # (torch adds a row's duplicates in its own order)
+        r1, v1 = O.embbag_backward_spec(g[f"dout{s}"], g[f"idx{s}"], g[f"off{s}"], sc)
+        ur, sums = O.coalesce_spec(r1, v1)
+        O.weight_update_emb_unquantized_spec(W_co, ur, sums, lr)
+        np.testing.assert_allclose(W_co, g[f"W{s}"], rtol=1e-5, atol=1e-7)
