@@ -220,6 +220,11 @@ def test_c_abi_rejects_bad_arguments_before_any_launch():
         (lib.dqrm_dense_grad_quant_gathered(16, 16, 4, 16, 4, 2, 16, 16, 16, None), -errno.EINVAL, b"int8"),
         (lib.dqrm_bce_loss_grad(None, None, 4, None, None, None), -errno.EINVAL, b"bce_loss_grad"),
         (lib.dqrm_p2p_allgather(one, 17, 0, 0, 64, 16, None), -errno.EINVAL, b"world"),
+        # the fused backward + row update: a missing table array, then a table pointer that is not 16-byte aligned
+        (lib.dqrm_embbag_bwd_sgd(1, None, rows, 16, 16, 16, rows, 4, 16, 64, 16, None, 8, 16, 16, 16,
+                                 0.1, None, 1.0, None, 1e-10, 16, 16, 1024, None), -errno.EINVAL, b"embbag_bwd_sgd"),
+        (lib.dqrm_embbag_bwd_sgd(1, (C.c_void_p * 1)(24), rows, 16, 16, 16, rows, 4, 16, 64, 16, None, 8, 16, 16, 16,
+                                 0.1, None, 1.0, None, 1e-10, 16, 16, 1024, None), -errno.EINVAL, b"aligned"),
     ]
     for i, (rc, want, frag) in enumerate(cases):
         assert rc == want, (i, rc, want)
