@@ -479,7 +479,7 @@ class Runner:
                 # DRAM bytes of THIS run are not measurable outside a profiler: null here; the ncu capture of the same
                 # kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch) is committed under profiles/
                 "traffic": None,
-                "traffic_ncu": "profiles/r01_scan_kernel_ncu_full.txt: 2.1686e9 B per unsharded Kaggle launch = 1.004 x algorithmic",
+                "traffic_ncu": "profiles/r02b_scan_kernel_ncu_full.txt: 2.1646e9 B per unsharded Kaggle launch = 1.002 x algorithmic",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                 "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_launch": algo,
                 "avg_launch_ms": scan_ms, "share_of_step": scan_ms / ms_per_step}
